@@ -1,0 +1,388 @@
+// Chamfer distance / brute-force 1-NN for sm_100a.
+//
+// Replaces PyTorch3D 0.5.0 KNearestNeighborKernelV3<D=3,K=1> + KNearestNeighborBackwardKernel as
+// reached from pterotactyl/utility/utils.py:207,212 (pytorch3d.loss.chamfer_distance).
+//
+// Design (DESIGN.md "K1"):
+//   * FP32-pipe bound.  One distance evaluation = 3 FADD + 1 FMUL + 2 FFMA = 6 FMA-pipe issue slots;
+//     everything else is overhead to be amortised:
+//       - targets are staged once per CTA in shared memory as SoA (x[], y[], z[]) and read back
+//         with 128-bit broadcast loads: 3 LDS.128 per 4 targets, shared by the R queries a thread
+//         keeps in registers  => 0.75/R LDS per evaluation;
+//       - the running minimum uses the 3-input FMNMX3 of sm_100 (0.5 ALU-pipe op / evaluation);
+//       - the arg-min is LAZY: the inner loop only tracks, per query, the minimum over a chunk of
+//         16 targets and the id of the first chunk that achieved the running minimum (3 ops per 16
+//         evaluations).  The exact index is recovered afterwards by re-evaluating that one chunk
+//         with the same instruction sequence (bit-identical distances) and taking the first hit:
+//         strict '<' across ascending chunks + first hit inside the chunk == PyTorch3D's
+//         "lowest index wins ties".
+//   * both directions (x->y and y->x) run in the same launch (blockIdx.z = 2*b + dir).
+//   * when the batch is too small to fill 148 SMs the target range is split across CTAs
+//     (blockIdx.y) and partial results are merged with a 64-bit atomicMin on the packed key
+//     (dist_bits << 32 | idx): dist >= +0 so its bit pattern orders like an unsigned integer and
+//     the low word makes the lowest index win ties -- deterministic.
+//   * a second small kernel unpacks the keys and does the fused mean reduction in a fixed order
+//     (deterministic, no float atomics).
+#include "ptk_common.cuh"
+
+namespace ptk {
+
+constexpr int CH_THREADS = 256;
+constexpr int CH_TT = 2048;   // targets per shared-memory tile (3 * 2048 * 4 B = 24 KB)
+constexpr int CH_CHUNK = 16;  // lazy arg-min granularity
+
+__device__ __forceinline__ float min3f(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// The one and only definition of the distance arithmetic (inner loop AND index recovery).
+__device__ __forceinline__ float sqdist(float qx, float qy, float qz, float tx, float ty, float tz) {
+    float dx = __fsub_rn(qx, tx);
+    float dy = __fsub_rn(qy, ty);
+    float dz = __fsub_rn(qz, tz);
+    float d = __fmul_rn(dx, dx);
+    d = __fmaf_rn(dy, dy, d);
+    d = __fmaf_rn(dz, dz, d);
+    return d;
+}
+
+template <int R>
+__global__ void __launch_bounds__(CH_THREADS, 2)
+chamfer_nn_kernel(const float *__restrict__ x, const float *__restrict__ y, int P1, int P2,
+                  int split_len, int n_split, unsigned long long *__restrict__ keys_x,
+                  unsigned long long *__restrict__ keys_y, int dir_only) {
+    const int z = blockIdx.z;
+    const int b = dir_only >= 0 ? z : (z >> 1);
+    const int dir = dir_only >= 0 ? dir_only : (z & 1);
+    const int NQ = dir == 0 ? P1 : P2;
+    const int NT = dir == 0 ? P2 : P1;
+    const float *__restrict__ Q = dir == 0 ? x + (size_t)b * P1 * 3 : y + (size_t)b * P2 * 3;
+    const float *__restrict__ T = dir == 0 ? y + (size_t)b * P2 * 3 : x + (size_t)b * P1 * 3;
+    unsigned long long *__restrict__ keys =
+        dir == 0 ? keys_x + (size_t)b * P1 : keys_y + (size_t)b * P2;
+
+    const int q0 = blockIdx.x * (CH_THREADS * R);
+    if (q0 >= NQ) return;
+    const int t_begin = blockIdx.y * split_len;
+    if (t_begin >= NT) return;
+    const int t_end = min(NT, t_begin + split_len);
+    const int tid = threadIdx.x;
+
+    __shared__ __align__(16) float sx[CH_TT];
+    __shared__ __align__(16) float sy[CH_TT];
+    __shared__ __align__(16) float sz[CH_TT];
+
+    float qx[R], qy[R], qz[R], best[R];
+    int bchunk[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        int qi = min(q0 + r * CH_THREADS + tid, NQ - 1);
+        qx[r] = Q[(size_t)qi * 3 + 0];
+        qy[r] = Q[(size_t)qi * 3 + 1];
+        qz[r] = Q[(size_t)qi * 3 + 2];
+        best[r] = __int_as_float(0x7f800000);
+        bchunk[r] = t_begin / CH_CHUNK;
+    }
+
+    for (int tile = t_begin; tile < t_end; tile += CH_TT) {
+        const int n = min(CH_TT, t_end - tile);
+        __syncthreads();
+        // global (n,3) packed floats -> shared SoA; pad to a whole chunk with +inf (never wins '<')
+        const int npad = ((n + CH_CHUNK - 1) / CH_CHUNK) * CH_CHUNK;
+        const float *__restrict__ src = T + (size_t)tile * 3;
+        for (int e = tid; e < npad * 3; e += CH_THREADS) {
+            float v = e < n * 3 ? src[e] : __int_as_float(0x7f800000);
+            int p = e / 3;
+            int c = e - p * 3;
+            float *dst = c == 0 ? sx : (c == 1 ? sy : sz);
+            dst[p] = v;
+        }
+        __syncthreads();
+        const int nchunks = npad / CH_CHUNK;
+        const int chunk0 = tile / CH_CHUNK;
+        for (int c = 0; c < nchunks; ++c) {
+            float m[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) m[r] = __int_as_float(0x7f800000);
+#pragma unroll
+            for (int g = 0; g < CH_CHUNK / 4; ++g) {
+                const float4 tx = *reinterpret_cast<const float4 *>(&sx[c * CH_CHUNK + g * 4]);
+                const float4 ty = *reinterpret_cast<const float4 *>(&sy[c * CH_CHUNK + g * 4]);
+                const float4 tz = *reinterpret_cast<const float4 *>(&sz[c * CH_CHUNK + g * 4]);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    float d0 = sqdist(qx[r], qy[r], qz[r], tx.x, ty.x, tz.x);
+                    float d1 = sqdist(qx[r], qy[r], qz[r], tx.y, ty.y, tz.y);
+                    float d2 = sqdist(qx[r], qy[r], qz[r], tx.z, ty.z, tz.z);
+                    float d3 = sqdist(qx[r], qy[r], qz[r], tx.w, ty.w, tz.w);
+                    m[r] = min3f(m[r], d0, d1);
+                    m[r] = min3f(m[r], d2, d3);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                bchunk[r] = m[r] < best[r] ? chunk0 + c : bchunk[r];
+                best[r] = fminf(best[r], m[r]);
+            }
+        }
+    }
+
+    // index recovery: first target of the recorded chunk whose distance equals the minimum
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int qi = q0 + r * CH_THREADS + tid;
+        if (qi >= NQ) continue;
+        const int j0 = bchunk[r] * CH_CHUNK;
+        const int j1 = min(j0 + CH_CHUNK, NT);
+        int arg = j0;
+        bool found = false;
+        for (int j = j0; j < j1; ++j) {
+            float d = sqdist(qx[r], qy[r], qz[r], T[(size_t)j * 3], T[(size_t)j * 3 + 1],
+                             T[(size_t)j * 3 + 2]);
+            if (!found && d == best[r]) {
+                arg = j;
+                found = true;
+            }
+        }
+        unsigned long long key =
+            ((unsigned long long)__float_as_uint(best[r]) << 32) | (unsigned int)arg;
+        if (n_split > 1)
+            atomicMin(&keys[qi], key);
+        else
+            keys[qi] = key;
+    }
+}
+
+// Unpack keys -> (dist, idx) and reduce the per-cloud means in a fixed order.
+// grid = B, block = 512.  cham may be NULL (plain knn).
+__global__ void __launch_bounds__(512)
+chamfer_finalize_kernel(const unsigned long long *__restrict__ keys_x,
+                        const unsigned long long *__restrict__ keys_y, int P1, int P2,
+                        float *__restrict__ dist_x, int32_t *__restrict__ idx_x,
+                        float *__restrict__ dist_y, int32_t *__restrict__ idx_y,
+                        float *__restrict__ cham) {
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    __shared__ float red[16];
+    float mean[2] = {0.f, 0.f};
+    for (int dir = 0; dir < 2; ++dir) {
+        const unsigned long long *keys = dir == 0 ? keys_x : keys_y;
+        if (keys == nullptr) continue;
+        const int P = dir == 0 ? P1 : P2;
+        float *dist = dir == 0 ? dist_x : dist_y;
+        int32_t *idx = dir == 0 ? idx_x : idx_y;
+        float acc = 0.f;
+        for (int i = tid; i < P; i += 512) {
+            unsigned long long k = keys[(size_t)b * P + i];
+            float d = __uint_as_float((unsigned int)(k >> 32));
+            if (dist) dist[(size_t)b * P + i] = d;
+            if (idx) idx[(size_t)b * P + i] = (int32_t)(unsigned int)(k & 0xffffffffull);
+            acc += d;
+        }
+        acc = warp_sum(acc);
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = acc;
+        __syncthreads();
+        if (tid < 32) {
+            float v = tid < 16 ? red[tid] : 0.f;
+            v = warp_sum(v);
+            if (tid == 0) mean[dir] = v / (float)P;
+        }
+    }
+    if (tid == 0 && cham) cham[b] = mean[0] + mean[1];
+}
+
+// Backward, phase A (plain stores): the "own point" terms.
+//   grad_x[b,i] = 2 * (g[b]/P1) * (x_i - y[idx_x[i]]);  grad_y[b,j] = 2 * (g[b]/P2) * (y_j - x[idx_y[j]])
+__global__ void chamfer_bwd_direct_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                                          const int32_t *__restrict__ idx_x,
+                                          const int32_t *__restrict__ idx_y,
+                                          const float *__restrict__ grad_cham, int P1, int P2,
+                                          float *__restrict__ grad_x, float *__restrict__ grad_y) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float g = grad_cham[b];
+    const float *xb = x + (size_t)b * P1 * 3, *yb = y + (size_t)b * P2 * 3;
+    if (grad_x && i < P1) {
+        const int j = idx_x[(size_t)b * P1 + i];
+        const float s = 2.0f * (g / (float)P1);
+        float *o = grad_x + ((size_t)b * P1 + i) * 3;
+        o[0] = s * (xb[i * 3 + 0] - yb[j * 3 + 0]);
+        o[1] = s * (xb[i * 3 + 1] - yb[j * 3 + 1]);
+        o[2] = s * (xb[i * 3 + 2] - yb[j * 3 + 2]);
+    }
+    if (grad_y && i < P2) {
+        const int j = idx_y[(size_t)b * P2 + i];
+        const float s = 2.0f * (g / (float)P2);
+        float *o = grad_y + ((size_t)b * P2 + i) * 3;
+        o[0] = s * (yb[i * 3 + 0] - xb[j * 3 + 0]);
+        o[1] = s * (yb[i * 3 + 1] - xb[j * 3 + 1]);
+        o[2] = s * (yb[i * 3 + 2] - xb[j * 3 + 2]);
+    }
+}
+
+// Backward, phase B (scatter): the "I am somebody's nearest neighbour" terms, RED.ADD.F32.
+//   grad_y[b, idx_x[i]] -= 2 (g/P1) (x_i - y[idx_x[i]]);  grad_x[b, idx_y[j]] -= 2 (g/P2) (y_j - x[idx_y[j]])
+__global__ void chamfer_bwd_scatter_kernel(const float *__restrict__ x, const float *__restrict__ y,
+                                           const int32_t *__restrict__ idx_x,
+                                           const int32_t *__restrict__ idx_y,
+                                           const float *__restrict__ grad_cham, int P1, int P2,
+                                           float *__restrict__ grad_x, float *__restrict__ grad_y) {
+    const int b = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const float g = grad_cham[b];
+    const float *xb = x + (size_t)b * P1 * 3, *yb = y + (size_t)b * P2 * 3;
+    if (grad_y && i < P1) {
+        const int j = idx_x[(size_t)b * P1 + i];
+        const float s = 2.0f * (g / (float)P1);
+        float *o = grad_y + ((size_t)b * P2 + j) * 3;
+        atomicAdd(o + 0, -(s * (xb[i * 3 + 0] - yb[j * 3 + 0])));
+        atomicAdd(o + 1, -(s * (xb[i * 3 + 1] - yb[j * 3 + 1])));
+        atomicAdd(o + 2, -(s * (xb[i * 3 + 2] - yb[j * 3 + 2])));
+    }
+    if (grad_x && i < P2) {
+        const int j = idx_y[(size_t)b * P2 + i];
+        const float s = 2.0f * (g / (float)P2);
+        float *o = grad_x + ((size_t)b * P1 + j) * 3;
+        atomicAdd(o + 0, -(s * (yb[i * 3 + 0] - xb[j * 3 + 0])));
+        atomicAdd(o + 1, -(s * (yb[i * 3 + 1] - xb[j * 3 + 1])));
+        atomicAdd(o + 2, -(s * (yb[i * 3 + 2] - xb[j * 3 + 2])));
+    }
+}
+
+// ---------------------------------------------------------------------------------------- host side
+struct NNPlan {
+    int R;          // queries per thread
+    int n_split;    // CTAs along the target range
+    int split_len;  // targets per split (multiple of CH_CHUNK)
+};
+
+static NNPlan plan_nn(int64_t B, int64_t Pq_max, int64_t Pt_max, int ndir) {
+    const int64_t want = 2LL * sm_count() * 2;  // >= 2 waves at 2 resident CTAs / SM
+    NNPlan p;
+    p.R = 8;
+    auto ctas = [&](int R) { return B * ndir * ceil_div(Pq_max, (int64_t)CH_THREADS * R); };
+    if (ctas(8) < want) p.R = 4;
+    if (ctas(4) < want) p.R = 2;
+    int64_t base = ctas(p.R);
+    int64_t ns = base >= want ? 1 : ceil_div(want, base);
+    int64_t max_split = ceil_div(Pt_max, (int64_t)CH_CHUNK * 8);  // >= 128 targets per split
+    if (ns > max_split) ns = max_split;
+    if (ns < 1) ns = 1;
+    int64_t len = ceil_div(ceil_div(Pt_max, ns), (int64_t)CH_CHUNK) * CH_CHUNK;
+    p.n_split = (int)ceil_div(Pt_max, len);
+    p.split_len = (int)len;
+    return p;
+}
+
+static int launch_nn(const float *x, const float *y, int64_t B, int64_t P1, int64_t P2,
+                     unsigned long long *keys_x, unsigned long long *keys_y, int dir_only,
+                     cudaStream_t st) {
+    const int ndir = dir_only >= 0 ? 1 : 2;
+    const int64_t Pq = dir_only == 0 ? P1 : (dir_only == 1 ? P2 : (P1 > P2 ? P1 : P2));
+    const int64_t Pt = dir_only == 0 ? P2 : (dir_only == 1 ? P1 : (P1 > P2 ? P1 : P2));
+    NNPlan p = plan_nn(B, Pq, Pt, ndir);
+    if (p.n_split > 1) {
+        if (keys_x) PTK_CHECK_CUDA(cudaMemsetAsync(keys_x, 0xff, sizeof(unsigned long long) * B * P1, st));
+        if (keys_y) PTK_CHECK_CUDA(cudaMemsetAsync(keys_y, 0xff, sizeof(unsigned long long) * B * P2, st));
+    }
+    dim3 grid((unsigned)ceil_div(Pq, (int64_t)CH_THREADS * p.R), (unsigned)p.n_split,
+              (unsigned)(B * ndir));
+    PTK_REQUIRE(grid.z <= 65535 && grid.y <= 65535, PTK_ERR_SHAPE,
+                "chamfer: batch %lld too large for one launch (max 32767 clouds)", (long long)B);
+    switch (p.R) {
+        case 8:
+            chamfer_nn_kernel<8><<<grid, CH_THREADS, 0, st>>>(x, y, (int)P1, (int)P2, p.split_len,
+                                                               p.n_split, keys_x, keys_y, dir_only);
+            break;
+        case 4:
+            chamfer_nn_kernel<4><<<grid, CH_THREADS, 0, st>>>(x, y, (int)P1, (int)P2, p.split_len,
+                                                               p.n_split, keys_x, keys_y, dir_only);
+            break;
+        default:
+            chamfer_nn_kernel<2><<<grid, CH_THREADS, 0, st>>>(x, y, (int)P1, (int)P2, p.split_len,
+                                                               p.n_split, keys_x, keys_y, dir_only);
+            break;
+    }
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}
+
+}  // namespace ptk
+
+using namespace ptk;
+
+extern "C" size_t ptk_chamfer_workspace_bytes(int64_t B, int64_t P1, int64_t P2) {
+    if (B <= 0 || P1 <= 0 || P2 <= 0) return 0;
+    return sizeof(unsigned long long) * (size_t)B * (size_t)(P1 + P2);
+}
+
+static int check_clouds(const void *x, const void *y, int64_t B, int64_t P1, int64_t P2) {
+    PTK_REQUIRE(x && y, PTK_ERR_SHAPE, "chamfer: null cloud pointer");
+    PTK_REQUIRE(B > 0 && P1 > 0 && P2 > 0, PTK_ERR_SHAPE,
+                "chamfer: empty input (B=%lld, P1=%lld, P2=%lld); point clouds must be non-empty",
+                (long long)B, (long long)P1, (long long)P2);
+    PTK_REQUIRE(P1 < (1LL << 31) / 3 && P2 < (1LL << 31) / 3, PTK_ERR_SHAPE,
+                "chamfer: cloud too large for 32-bit indexing");
+    return PTK_OK;
+}
+
+extern "C" int ptk_knn1_fwd(const float *p1, const float *p2, int64_t B, int64_t P1, int64_t P2,
+                            float *dist, int32_t *idx, void *workspace, size_t workspace_bytes,
+                            ptk_stream_t stream) {
+    int rc = check_clouds(p1, p2, B, P1, P2);
+    if (rc) return rc;
+    PTK_REQUIRE(workspace && workspace_bytes >= sizeof(unsigned long long) * (size_t)B * (size_t)P1,
+                PTK_ERR_WORKSPACE, "knn1: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    auto *keys = reinterpret_cast<unsigned long long *>(workspace);
+    rc = launch_nn(p1, p2, B, P1, P2, keys, nullptr, 0, st);
+    if (rc) return rc;
+    chamfer_finalize_kernel<<<(unsigned)B, 512, 0, st>>>(keys, nullptr, (int)P1, (int)P2, dist, idx,
+                                                         nullptr, nullptr, nullptr);
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}
+
+extern "C" int ptk_chamfer_fwd(const float *x, const float *y, int64_t B, int64_t P1, int64_t P2,
+                               float *dist_x, int32_t *idx_x, float *dist_y, int32_t *idx_y,
+                               float *cham, void *workspace, size_t workspace_bytes,
+                               ptk_stream_t stream) {
+    int rc = check_clouds(x, y, B, P1, P2);
+    if (rc) return rc;
+    PTK_REQUIRE(idx_x && idx_y && cham, PTK_ERR_SHAPE, "chamfer_fwd: idx_x, idx_y and cham are required");
+    PTK_REQUIRE(workspace && workspace_bytes >= ptk_chamfer_workspace_bytes(B, P1, P2),
+                PTK_ERR_WORKSPACE, "chamfer_fwd: workspace too small (%zu < %zu)", workspace_bytes,
+                ptk_chamfer_workspace_bytes(B, P1, P2));
+    cudaStream_t st = as_stream(stream);
+    auto *keys_x = reinterpret_cast<unsigned long long *>(workspace);
+    auto *keys_y = keys_x + (size_t)B * P1;
+    rc = launch_nn(x, y, B, P1, P2, keys_x, keys_y, -1, st);
+    if (rc) return rc;
+    chamfer_finalize_kernel<<<(unsigned)B, 512, 0, st>>>(keys_x, keys_y, (int)P1, (int)P2, dist_x,
+                                                         idx_x, dist_y, idx_y, cham);
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}
+
+extern "C" int ptk_chamfer_bwd(const float *x, const float *y, const int32_t *idx_x,
+                               const int32_t *idx_y, const float *grad_cham, int64_t B, int64_t P1,
+                               int64_t P2, float *grad_x, float *grad_y, ptk_stream_t stream) {
+    int rc = check_clouds(x, y, B, P1, P2);
+    if (rc) return rc;
+    PTK_REQUIRE(idx_x && idx_y && grad_cham, PTK_ERR_SHAPE, "chamfer_bwd: null index / grad pointer");
+    if (!grad_x && !grad_y) return PTK_OK;
+    cudaStream_t st = as_stream(stream);
+    const int64_t Pm = P1 > P2 ? P1 : P2;
+    dim3 grid((unsigned)ceil_div(Pm, 256), (unsigned)B);
+    PTK_REQUIRE(B <= 65535, PTK_ERR_SHAPE, "chamfer_bwd: batch too large");
+    chamfer_bwd_direct_kernel<<<grid, 256, 0, st>>>(x, y, idx_x, idx_y, grad_cham, (int)P1, (int)P2,
+                                                    grad_x, grad_y);
+    PTK_CHECK_LAUNCH();
+    chamfer_bwd_scatter_kernel<<<grid, 256, 0, st>>>(x, y, idx_x, idx_y, grad_cham, (int)P1, (int)P2,
+                                                     grad_x, grad_y);
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}

@@ -1,0 +1,288 @@
+// GCN vertex aggregation (CSR gather) for sm_100a.
+//
+// Replaces the dense `torch.matmul(adj, features[:, :, :length])` + cat + bias + activation of
+// GCN_layer.forward (pterotactyl/reconstruction/vision/model.py:354-363): the reference multiplies a
+// 99 %-zero (Nv x Nv) matrix into (B,Nv,L); here each output row gathers its deg(i) neighbour rows.
+//
+//   out[b,i,c] = act( sum_{e in row i} val[e] * in[b,col[e],c] + bias[c] )   c <  L
+//   out[b,i,c] = act( in[b,i,c] )                                             c >= L
+//
+// HBM/L2-bound: one warp per output row, 128-bit loads along the channel dimension (rows are
+// C*4 bytes = 1200 B for C=300: 16-byte aligned), the column indices of a row are fetched 32 at a
+// time by the warp and broadcast with shuffles, neighbour loads are issued 4 deep.  Hub rows
+// (degree > HUB_DEG: the touch-chart centre vertices, degree 1153 -- utils.py:95-98,126-128) are
+// processed by a whole CTA (8 warps split the neighbour list, shared-memory reduction) so that
+// they do not become the tail of the launch.
+#include "ptk_common.cuh"
+
+namespace ptk {
+
+constexpr int AG_THREADS = 256;
+constexpr int AG_WARPS = AG_THREADS / 32;
+constexpr int HUB_DEG = 128;
+
+// Gather for one row restricted to the warp `part` of `nparts` (nparts = 1: the whole row).
+template <bool VEC>
+__device__ __forceinline__ void row_gather(const int32_t *__restrict__ col, const float *__restrict__ val,
+                                           int beg, int end, const float *__restrict__ inb, int C,
+                                           int v, bool active, float acc[4]) {
+    const int lane = threadIdx.x & 31;
+    for (int e0 = beg; e0 < end; e0 += 32) {
+        const int cnt = min(32, end - e0);
+        int my_col = 0;
+        float my_val = 0.f;
+        if (lane < cnt) {
+            my_col = col[e0 + lane];
+            my_val = val[e0 + lane];
+        }
+        int k = 0;
+        for (; k + 4 <= cnt; k += 4) {
+            int j0 = __shfl_sync(0xffffffffu, my_col, k + 0), j1 = __shfl_sync(0xffffffffu, my_col, k + 1);
+            int j2 = __shfl_sync(0xffffffffu, my_col, k + 2), j3 = __shfl_sync(0xffffffffu, my_col, k + 3);
+            float w0 = __shfl_sync(0xffffffffu, my_val, k + 0), w1 = __shfl_sync(0xffffffffu, my_val, k + 1);
+            float w2 = __shfl_sync(0xffffffffu, my_val, k + 2), w3 = __shfl_sync(0xffffffffu, my_val, k + 3);
+            if (active) {
+                if (VEC) {
+                    float4 a0 = *reinterpret_cast<const float4 *>(inb + (size_t)j0 * C + v * 4);
+                    float4 a1 = *reinterpret_cast<const float4 *>(inb + (size_t)j1 * C + v * 4);
+                    float4 a2 = *reinterpret_cast<const float4 *>(inb + (size_t)j2 * C + v * 4);
+                    float4 a3 = *reinterpret_cast<const float4 *>(inb + (size_t)j3 * C + v * 4);
+                    acc[0] = fmaf(w0, a0.x, acc[0]); acc[1] = fmaf(w0, a0.y, acc[1]);
+                    acc[2] = fmaf(w0, a0.z, acc[2]); acc[3] = fmaf(w0, a0.w, acc[3]);
+                    acc[0] = fmaf(w1, a1.x, acc[0]); acc[1] = fmaf(w1, a1.y, acc[1]);
+                    acc[2] = fmaf(w1, a1.z, acc[2]); acc[3] = fmaf(w1, a1.w, acc[3]);
+                    acc[0] = fmaf(w2, a2.x, acc[0]); acc[1] = fmaf(w2, a2.y, acc[1]);
+                    acc[2] = fmaf(w2, a2.z, acc[2]); acc[3] = fmaf(w2, a2.w, acc[3]);
+                    acc[0] = fmaf(w3, a3.x, acc[0]); acc[1] = fmaf(w3, a3.y, acc[1]);
+                    acc[2] = fmaf(w3, a3.z, acc[2]); acc[3] = fmaf(w3, a3.w, acc[3]);
+                } else {
+                    float a0 = inb[(size_t)j0 * C + v], a1 = inb[(size_t)j1 * C + v];
+                    float a2 = inb[(size_t)j2 * C + v], a3 = inb[(size_t)j3 * C + v];
+                    acc[0] = fmaf(w0, a0, acc[0]); acc[0] = fmaf(w1, a1, acc[0]);
+                    acc[0] = fmaf(w2, a2, acc[0]); acc[0] = fmaf(w3, a3, acc[0]);
+                }
+            }
+        }
+        for (; k < cnt; ++k) {
+            int j = __shfl_sync(0xffffffffu, my_col, k);
+            float w = __shfl_sync(0xffffffffu, my_val, k);
+            if (active) {
+                if (VEC) {
+                    float4 a = *reinterpret_cast<const float4 *>(inb + (size_t)j * C + v * 4);
+                    acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]);
+                    acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+                } else {
+                    acc[0] = fmaf(w, inb[(size_t)j * C + v], acc[0]);
+                }
+            }
+        }
+    }
+}
+
+// One warp per (b, i) row.  VEC: lanes own float4 channel groups; else lanes own single channels.
+// Rows with degree > HUB_DEG are skipped here when hubs are handled by gcn_aggregate_hub_kernel.
+template <bool VEC>
+__global__ void __launch_bounds__(AG_THREADS)
+gcn_aggregate_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                     const float *__restrict__ val, int Nv, const float *__restrict__ in,
+                     long long rows, int C, int L, const float *__restrict__ bias, int relu,
+                     float *__restrict__ out, int skip_hubs) {
+    const long long row = (long long)blockIdx.x * AG_WARPS + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int i = (int)(row % Nv);
+    const long long b = row / Nv;
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    const bool hub = skip_hubs && (end - beg) > HUB_DEG;
+    const float *__restrict__ inb = in + (size_t)b * Nv * C;
+    const float *__restrict__ self = in + (size_t)row * C;
+    float *__restrict__ o = out + (size_t)row * C;
+    const int W = VEC ? 4 : 1;
+    const int ngroups = C / W;          // channel groups per row
+    const int gath = (L + W - 1) / W;   // groups that contain at least one aggregated channel
+
+    // pass-through groups (c >= L entirely)
+    for (int v = gath + lane; v < ngroups; v += 32) {
+        if (VEC) {
+            float4 s = *reinterpret_cast<const float4 *>(self + v * 4);
+            if (relu) {
+                s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f);
+            }
+            *reinterpret_cast<float4 *>(o + v * 4) = s;
+        } else {
+            float s = self[v];
+            o[v] = relu ? fmaxf(s, 0.f) : s;
+        }
+    }
+    if (hub) return;
+    // aggregated groups
+    for (int v0 = 0; v0 < gath; v0 += 32) {
+        const int v = v0 + lane;
+        const bool active = v < gath;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        row_gather<VEC>(col, val, beg, end, inb, C, v, active, acc);
+        if (!active) continue;
+        if (VEC) {
+            float4 s = *reinterpret_cast<const float4 *>(self + v * 4);
+            float sv[4] = {s.x, s.y, s.z, s.w};
+            float r[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int c = v * 4 + k;
+                float t = c < L ? acc[k] + (bias ? bias[c] : 0.f) : sv[k];
+                r[k] = relu ? fmaxf(t, 0.f) : t;
+            }
+            *reinterpret_cast<float4 *>(o + v * 4) = make_float4(r[0], r[1], r[2], r[3]);
+        } else {
+            float t = acc[0] + (bias ? bias[v] : 0.f);
+            o[v] = relu ? fmaxf(t, 0.f) : t;
+        }
+    }
+}
+
+// One CTA per (b, hub row): the 8 warps split the neighbour list; shared-memory reduction.
+// Only the aggregated channel groups are written (pass-through was done by the row kernel).
+template <bool VEC>
+__global__ void __launch_bounds__(AG_THREADS)
+gcn_aggregate_hub_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                         const float *__restrict__ val, const int32_t *__restrict__ hubs, int n_hubs,
+                         int Nv, const float *__restrict__ in, int C, int L,
+                         const float *__restrict__ bias, int relu, float *__restrict__ out) {
+    const int i = hubs[blockIdx.x % n_hubs];
+    const long long b = blockIdx.x / n_hubs;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    const int per = (((end - beg) + AG_WARPS - 1) / AG_WARPS + 31) / 32 * 32;
+    const int wbeg = min(end, beg + warp * per), wend = min(end, wbeg + per);
+    const float *__restrict__ inb = in + (size_t)b * Nv * C;
+    const long long row = b * Nv + i;
+    const float *__restrict__ self = in + (size_t)row * C;
+    float *__restrict__ o = out + (size_t)row * C;
+    const int W = VEC ? 4 : 1;
+    const int gath = (L + W - 1) / W;
+    __shared__ float s_part[AG_WARPS][32][4];
+    for (int v0 = 0; v0 < gath; v0 += 32) {
+        const int v = v0 + lane;
+        const bool active = v < gath;
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        row_gather<VEC>(col, val, wbeg, wend, inb, C, v, active, acc);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_part[warp][lane][k] = acc[k];
+        __syncthreads();
+        if (warp == 0 && active) {
+            float tot[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int w = 0; w < AG_WARPS; ++w)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) tot[k] += s_part[w][lane][k];
+            if (VEC) {
+                float4 s = *reinterpret_cast<const float4 *>(self + v * 4);
+                float sv[4] = {s.x, s.y, s.z, s.w};
+                float r[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int c = v * 4 + k;
+                    float t = c < L ? tot[k] + (bias ? bias[c] : 0.f) : sv[k];
+                    r[k] = relu ? fmaxf(t, 0.f) : t;
+                }
+                *reinterpret_cast<float4 *>(o + v * 4) = make_float4(r[0], r[1], r[2], r[3]);
+            } else {
+                float t = tot[0] + (bias ? bias[v] : 0.f);
+                o[v] = relu ? fmaxf(t, 0.f) : t;
+            }
+        }
+    }
+}
+
+// gbias[c] = sum_rows g[row, c] (c < L), 0 otherwise.  Deterministic two-stage column sum:
+// stage 1: CTA `k` sums rows k, k+G, ... into part[k, c]; stage 2: one CTA sums the G partials.
+constexpr int BG_PARTS = 296;
+__global__ void __launch_bounds__(128)
+bias_grad_stage1(const float *__restrict__ g, long long M, int C, int L, float *__restrict__ part) {
+    for (int c = threadIdx.x; c < L; c += 128) {
+        float acc = 0.f;
+        for (long long r = blockIdx.x; r < M; r += gridDim.x) acc += g[(size_t)r * C + c];
+        part[(size_t)blockIdx.x * L + c] = acc;
+    }
+}
+__global__ void __launch_bounds__(128)
+bias_grad_stage2(const float *__restrict__ part, int nparts, int C, int L, float *__restrict__ gbias) {
+    for (int c = blockIdx.x * 128 + threadIdx.x; c < C; c += gridDim.x * 128) {
+        float acc = 0.f;
+        if (c < L)
+            for (int p = 0; p < nparts; ++p) acc += part[(size_t)p * L + c];
+        gbias[c] = acc;
+    }
+}
+
+// gpre = (act > 0) ? g : 0  -- ReLU backward for the stand-alone layer / last-layer cases
+__global__ void relu_mask_kernel(const float *__restrict__ g, const float *__restrict__ act, long long n,
+                                 float *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = act[i] > 0.f ? g[i] : 0.f;
+}
+
+}  // namespace ptk
+
+using namespace ptk;
+
+extern "C" int ptk_relu_mask(const float *g, const float *act, int64_t n, float *out, ptk_stream_t stream) {
+    PTK_REQUIRE(g && act && out && n >= 0, PTK_ERR_SHAPE, "relu_mask: bad arguments");
+    if (n == 0) return PTK_OK;
+    relu_mask_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, as_stream(stream)>>>(g, act, (long long)n, out);
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}
+
+extern "C" int ptk_gcn_aggregate(const int32_t *rowptr, const int32_t *col, const float *val,
+                                 const int32_t *hubs, int32_t n_hubs, int64_t Nv, const float *in,
+                                 int64_t B, int64_t C, int64_t L, const float *bias, int relu,
+                                 float *out, ptk_stream_t stream) {
+    PTK_REQUIRE(rowptr && col && val && in && out, PTK_ERR_SHAPE, "gcn_aggregate: null pointer");
+    PTK_REQUIRE(B > 0 && Nv > 0 && C > 0 && L >= 0 && L <= C, PTK_ERR_SHAPE,
+                "gcn_aggregate: bad sizes (B=%lld, Nv=%lld, C=%lld, L=%lld)", (long long)B,
+                (long long)Nv, (long long)C, (long long)L);
+    PTK_REQUIRE(in != out, PTK_ERR_SHAPE, "gcn_aggregate: in-place aggregation is not supported");
+    cudaStream_t st = as_stream(stream);
+    const long long rows = (long long)B * Nv;
+    const bool vec = (C % 4 == 0) && ((((uintptr_t)in) | ((uintptr_t)out)) % 16 == 0);
+    const unsigned grid = (unsigned)ceil_div(rows, AG_WARPS);
+    const int skip = (hubs && n_hubs > 0) ? 1 : 0;
+    if (skip) {
+        const unsigned hgrid = (unsigned)(B * n_hubs);
+        if (vec)
+            gcn_aggregate_hub_kernel<true><<<hgrid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, (int)Nv, in, (int)C, (int)L, bias, relu, out);
+        else
+            gcn_aggregate_hub_kernel<false><<<hgrid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, (int)Nv, in, (int)C, (int)L, bias, relu, out);
+        PTK_CHECK_LAUNCH();
+    }
+    if (vec)
+        gcn_aggregate_kernel<true><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, (int)Nv, in, rows, (int)C, (int)L, bias, relu, out, skip);
+    else
+        gcn_aggregate_kernel<false><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, (int)Nv, in, rows, (int)C, (int)L, bias, relu, out, skip);
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}
+
+extern "C" size_t ptk_gcn_bias_grad_workspace_bytes(int64_t M, int64_t L) {
+    const int64_t nparts = M < BG_PARTS ? M : BG_PARTS;
+    return sizeof(float) * (size_t)(nparts > 0 ? nparts : 1) * (size_t)(L > 0 ? L : 1);
+}
+
+extern "C" int ptk_gcn_bias_grad(const float *g, int64_t M, int64_t C, int64_t L, float *gbias,
+                                 void *workspace, size_t workspace_bytes, ptk_stream_t stream) {
+    PTK_REQUIRE(g && gbias, PTK_ERR_SHAPE, "gcn_bias_grad: null pointer");
+    PTK_REQUIRE(M > 0 && C > 0 && L >= 0 && L <= C, PTK_ERR_SHAPE, "gcn_bias_grad: bad sizes");
+    PTK_REQUIRE(workspace && workspace_bytes >= ptk_gcn_bias_grad_workspace_bytes(M, L),
+                PTK_ERR_WORKSPACE, "gcn_bias_grad: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    const int nparts = (int)(M < BG_PARTS ? M : BG_PARTS);
+    float *part = reinterpret_cast<float *>(workspace);
+    if (L > 0) {
+        bias_grad_stage1<<<nparts, 128, 0, st>>>(g, (long long)M, (int)C, (int)L, part);
+        PTK_CHECK_LAUNCH();
+    }
+    bias_grad_stage2<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(part, nparts, (int)C, (int)L, gbias);
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}

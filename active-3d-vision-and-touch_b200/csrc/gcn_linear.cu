@@ -1,0 +1,205 @@
+// GCN per-vertex linear layer (FP32 GEMM) for sm_100a -- SIMT FP32 path.
+//
+// Replaces `torch.matmul(features, self.weight)` (pterotactyl/reconstruction/vision/model.py:352)
+// and its autograd (cuBLAS sgemm in the reference):
+//   fwd   : H  (M,N) = X (M,K) . W (K,N)
+//   dgrad : gX (M,K) = gH (M,N) . W^T          [* (act > 0): ReLU mask of the previous layer fused]
+//   wgrad : gW (K,N) = X^T (K,M) . gH (M,N)    split over M, fixed-order second-stage reduction
+// Parity contract is 1e-5 relative in FP32 (BASELINE.json north_star), which rules out single-pass
+// TF32/BF16 tensor-core math; this file is the exact-FP32 FFMA implementation: 128x128x16 CTA
+// tiles, 8x8 register micro-tiles (2x2 blocks of 4x4 so that shared-memory reads are 128-bit and
+// conflict-free), register-staged global prefetch of the next k-tile.
+#include "ptk_common.cuh"
+
+namespace ptk {
+
+constexpr int GL_BM = 128, GL_BN = 128, GL_BK = 16, GL_THREADS = 256, GL_PAD = 4;
+
+// Operand addressing.  KC (k-contiguous): elem(r, k) = p[r * ld + k];  else elem(r, k) = p[k * ld + r]
+template <bool KC>
+__device__ __forceinline__ float ld_elem(const float *__restrict__ p, long long ld, long long r,
+                                         long long k, long long R, long long K) {
+    if (r >= R || k >= K) return 0.f;
+    return KC ? __ldg(p + r * ld + k) : __ldg(p + k * ld + r);
+}
+
+template <bool A_KC, bool B_KC, bool MASK, bool SPLITK>
+__global__ void __launch_bounds__(GL_THREADS, 2)
+sgemm_kernel(const float *__restrict__ A, long long lda, const float *__restrict__ Bm, long long ldb,
+             float *__restrict__ Cm, long long ldc, long long M, long long N, long long K,
+             long long k_per_split, const float *__restrict__ act) {
+    __shared__ __align__(16) float As[2][GL_BK][GL_BM + GL_PAD];
+    __shared__ __align__(16) float Bs[2][GL_BK][GL_BN + GL_PAD];
+    const int tid = threadIdx.x;
+    const long long m0 = (long long)blockIdx.y * GL_BM;
+    const long long n0 = (long long)blockIdx.x * GL_BN;
+    const long long kb = SPLITK ? (long long)blockIdx.z * k_per_split : 0;
+    const long long ke = SPLITK ? min(K, kb + k_per_split) : K;
+    if (kb >= ke) return;
+
+    float ra[8], rb[8];
+    auto g2r = [&](long long k0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + i * GL_THREADS;
+            if (A_KC) {
+                const int r = idx / GL_BK, k = idx % GL_BK;
+                ra[i] = ld_elem<true>(A, lda, m0 + r, k0 + k, M, ke);
+            } else {
+                const int k = idx / GL_BM, r = idx % GL_BM;
+                ra[i] = ld_elem<false>(A, lda, m0 + r, k0 + k, M, ke);
+            }
+            if (B_KC) {
+                const int r = idx / GL_BK, k = idx % GL_BK;
+                rb[i] = ld_elem<true>(Bm, ldb, n0 + r, k0 + k, N, ke);
+            } else {
+                const int k = idx / GL_BN, r = idx % GL_BN;
+                rb[i] = ld_elem<false>(Bm, ldb, n0 + r, k0 + k, N, ke);
+            }
+        }
+    };
+    auto r2s = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int idx = tid + i * GL_THREADS;
+            if (A_KC) As[buf][idx % GL_BK][idx / GL_BK] = ra[i];
+            else      As[buf][idx / GL_BM][idx % GL_BM] = ra[i];
+            if (B_KC) Bs[buf][idx % GL_BK][idx / GL_BK] = rb[i];
+            else      Bs[buf][idx / GL_BN][idx % GL_BN] = rb[i];
+        }
+    };
+
+    const int tx = tid % 16, ty = tid / 16;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+
+    g2r(kb);
+    r2s(0);
+    __syncthreads();
+    int buf = 0;
+    for (long long k0 = kb; k0 < ke; k0 += GL_BK) {
+        const bool more = k0 + GL_BK < ke;
+        if (more) g2r(k0 + GL_BK);
+#pragma unroll
+        for (int k = 0; k < GL_BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][k][64 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[buf][k][64 + tx * 4]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (more) {
+            r2s(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        if (m >= M) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const long long n = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+            if (n >= N) continue;
+            float v = acc[i][j];
+            if (MASK) v = act[m * ldc + n] > 0.f ? v : 0.f;
+            Cm[(SPLITK ? (size_t)blockIdx.z * (size_t)M * (size_t)ldc : 0) + m * ldc + n] = v;
+        }
+    }
+}
+
+// second stage of the split wgrad: out[e] = sum_s part[s, e] in ascending s (deterministic)
+__global__ void splitk_reduce_kernel(const float *__restrict__ part, int nsplit, long long elems,
+                                     float *__restrict__ out) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= elems) return;
+    float acc = 0.f;
+    for (int s = 0; s < nsplit; ++s) acc += part[(size_t)s * elems + e];
+    out[e] = acc;
+}
+
+}  // namespace ptk
+
+using namespace ptk;
+
+static int check_gemm(const void *a, const void *b, const void *c, int64_t M, int64_t K, int64_t N) {
+    PTK_REQUIRE(a && b && c, PTK_ERR_SHAPE, "gcn_linear: null pointer");
+    PTK_REQUIRE(M > 0 && K > 0 && N > 0, PTK_ERR_SHAPE, "gcn_linear: bad sizes (M=%lld, K=%lld, N=%lld)",
+                (long long)M, (long long)K, (long long)N);
+    PTK_REQUIRE(ceil_div(M, GL_BM) <= 65535, PTK_ERR_SHAPE, "gcn_linear: M too large for one launch");
+    return PTK_OK;
+}
+
+extern "C" int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int64_t K, int64_t N,
+                                  float *H, ptk_stream_t stream) {
+    int rc = check_gemm(X, W, H, M, K, N);
+    if (rc) return rc;
+    dim3 grid((unsigned)ceil_div(N, GL_BN), (unsigned)ceil_div(M, GL_BM));
+    sgemm_kernel<true, false, false, false><<<grid, GL_THREADS, 0, as_stream(stream)>>>(
+        X, K, W, N, H, N, M, N, K, 0, nullptr);
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}
+
+extern "C" int ptk_gcn_linear_dgrad(const float *gH, const float *W, const float *act, int64_t M,
+                                    int64_t K, int64_t N, float *gX, ptk_stream_t stream) {
+    int rc = check_gemm(gH, W, gX, M, K, N);
+    if (rc) return rc;
+    // gX (M x K) = gH (M x N) . W^T : GEMM with m=M, n=K, k=N; B[k=n_out][n=k_in] = W[k_in*N + n_out]
+    dim3 grid((unsigned)ceil_div(K, GL_BN), (unsigned)ceil_div(M, GL_BM));
+    if (act)
+        sgemm_kernel<true, true, true, false><<<grid, GL_THREADS, 0, as_stream(stream)>>>(
+            gH, N, W, N, gX, K, M, K, N, 0, act);
+    else
+        sgemm_kernel<true, true, false, false><<<grid, GL_THREADS, 0, as_stream(stream)>>>(
+            gH, N, W, N, gX, K, M, K, N, 0, nullptr);
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}
+
+static int wgrad_splits(int64_t M, int64_t K, int64_t N) {
+    const int64_t tiles = ceil_div(K, GL_BM) * ceil_div(N, GL_BN);
+    int64_t want = ceil_div(2LL * sm_count() * 2, tiles);
+    int64_t max_s = ceil_div(M, 4 * GL_BK);
+    if (want > max_s) want = max_s;
+    if (want < 1) want = 1;
+    return (int)want;
+}
+
+extern "C" size_t ptk_gcn_linear_wgrad_workspace_bytes(int64_t M, int64_t K, int64_t N) {
+    if (M <= 0 || K <= 0 || N <= 0) return 0;
+    return sizeof(float) * (size_t)wgrad_splits(M, K, N) * (size_t)K * (size_t)N;
+}
+
+extern "C" int ptk_gcn_linear_wgrad(const float *X, const float *gH, int64_t M, int64_t K, int64_t N,
+                                    float *gW, void *workspace, size_t workspace_bytes,
+                                    ptk_stream_t stream) {
+    int rc = check_gemm(X, gH, gW, M, K, N);
+    if (rc) return rc;
+    PTK_REQUIRE(workspace && workspace_bytes >= ptk_gcn_linear_wgrad_workspace_bytes(M, K, N),
+                PTK_ERR_WORKSPACE, "gcn_linear_wgrad: workspace too small");
+    // gW (K x N) = X^T . gH : GEMM with m=K, n=N, k=M; A[m=k_in][k=row] = X[row*K + k_in]
+    const int ns = wgrad_splits(M, K, N);
+    const int64_t kper = ceil_div(ceil_div(M, ns), GL_BK) * GL_BK;
+    const int ns_eff = (int)ceil_div(M, kper);
+    float *part = reinterpret_cast<float *>(workspace);
+    dim3 grid((unsigned)ceil_div(N, GL_BN), (unsigned)ceil_div(K, GL_BM), (unsigned)ns_eff);
+    cudaStream_t st = as_stream(stream);
+    sgemm_kernel<false, false, false, true><<<grid, GL_THREADS, 0, st>>>(X, K, gH, N, part, N, K, N, M,
+                                                                         kper, nullptr);
+    PTK_CHECK_LAUNCH();
+    const long long elems = (long long)K * N;
+    splitk_reduce_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, st>>>(part, ns_eff, elems, gW);
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}

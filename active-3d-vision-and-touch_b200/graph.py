@@ -1,0 +1,100 @@
+"""Sparse form of the GCN adjacency.
+
+The reference keeps the adjacency as a dense, row-normalised (Nv,Nv) fp32 tensor
+(pterotactyl/utility/utils.py:47-71) and multiplies it densely
+(pterotactyl/reconstruction/vision/model.py:356,360) although it is 99 % zeros.  Callers keep
+passing that dense tensor (the GCN_layer.forward signature is unchanged); `graph_of` derives the CSR
+once per tensor and caches it.
+"""
+import weakref
+
+import numpy as np
+import torch
+
+HUB_DEG = 128  # rows with more neighbours are handled by a whole CTA (csrc/gcn_aggregate.cu)
+
+
+class Graph:
+    """CSR of A^ (forward gather) and of A^T (backward gather), resident on one device."""
+
+    def __init__(self, rowptr, col, val, n, device):
+        self.n = int(n)
+        self.nnz = int(len(col))
+        self.device = torch.device(device)
+        rowptr = np.ascontiguousarray(rowptr, np.int32)
+        col = np.ascontiguousarray(col, np.int32)
+        val = np.ascontiguousarray(val, np.float32)
+        # transpose: (i, j, v) -> row j
+        rows = np.repeat(np.arange(self.n, dtype=np.int32), np.diff(rowptr))
+        order = np.lexsort((rows, col))
+        col_t = rows[order]
+        val_t = val[order]
+        rowptr_t = np.zeros(self.n + 1, np.int32)
+        np.cumsum(np.bincount(col, minlength=self.n), out=rowptr_t[1:])
+        self.host = dict(rowptr=rowptr, col=col, val=val, rowptr_t=rowptr_t, col_t=col_t, val_t=val_t)
+        hubs = np.nonzero(np.diff(rowptr) > HUB_DEG)[0].astype(np.int32)
+        hubs_t = np.nonzero(np.diff(rowptr_t) > HUB_DEG)[0].astype(np.int32)
+        to = lambda a: torch.from_numpy(a).to(self.device)
+        self.rowptr, self.col, self.val = to(rowptr), to(col), to(val)
+        self.rowptr_t, self.col_t, self.val_t = to(rowptr_t), to(col_t), to(val_t)
+        self.hubs = to(hubs) if len(hubs) else None
+        self.hubs_t = to(hubs_t) if len(hubs_t) else None
+        self.n_hubs, self.n_hubs_t = int(len(hubs)), int(len(hubs_t))
+
+    @staticmethod
+    def from_dense(adj):
+        a = adj.detach().to("cpu", torch.float32).numpy()
+        n = a.shape[0]
+        if a.ndim != 2 or a.shape[1] != n:
+            raise ValueError(f"adjacency must be square, got {tuple(a.shape)}")
+        r, c = np.nonzero(a)
+        rowptr = np.zeros(n + 1, np.int32)
+        np.cumsum(np.bincount(r, minlength=n), out=rowptr[1:])
+        return Graph(rowptr, c.astype(np.int32), a[r, c], n, adj.device)
+
+    @staticmethod
+    def from_csr(rowptr, col, device, val=None):
+        """Row-normalised graph (every entry of row i is fl32(1/deg_i), utils.py:47-52)."""
+        rowptr = np.asarray(rowptr, np.int32)
+        deg = np.diff(rowptr)
+        if val is None:
+            with np.errstate(divide="ignore"):
+                w = np.where(deg > 0, np.float32(1.0) / deg.astype(np.float32), np.float32(0.0))
+            val = np.repeat(w.astype(np.float32), deg)
+        return Graph(rowptr, col, val, len(rowptr) - 1, device)
+
+    def dense(self):
+        a = torch.zeros(self.n, self.n)
+        h = self.host
+        rows = np.repeat(np.arange(self.n), np.diff(h["rowptr"]))
+        a[torch.from_numpy(rows), torch.from_numpy(h["col"].astype(np.int64))] = torch.from_numpy(h["val"])
+        return a.to(self.device)
+
+
+_cache = {}
+
+
+def graph_of(adj):
+    """Graph for a dense adjacency tensor, cached on (storage, version, shape, device)."""
+    if isinstance(adj, Graph):
+        return adj
+    key = (adj.data_ptr(), adj._version, tuple(adj.shape), str(adj.device))
+    hit = _cache.get(key)
+    if hit is not None and hit[0]() is not None:
+        return hit[1]
+    g = Graph.from_dense(adj)
+    try:
+        ref = weakref.ref(adj)
+    except TypeError:
+        ref = lambda: adj
+    if len(_cache) > 64:
+        _cache.clear()
+    _cache[key] = (ref, g)
+    return g
+
+
+def register(adj, graph):
+    """Pre-populate the cache (adj_init does this so the dense tensor is never re-scanned)."""
+    key = (adj.data_ptr(), adj._version, tuple(adj.shape), str(adj.device))
+    _cache[key] = (weakref.ref(adj), graph)
+    return graph

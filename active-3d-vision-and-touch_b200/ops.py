@@ -1,0 +1,313 @@
+"""torch.autograd bindings over the C ABI (include/ptk.h).  Tensors are only used for device memory,
+streams and autograd bookkeeping; all arithmetic of the hot path runs in libptk_b200.so.
+
+There is NO CPU / eager fallback: CPU tensors are rejected with a RuntimeError.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .graph import Graph, graph_of
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError(
+                "ptk_b200 ops run on CUDA (sm_100a) tensors only; got a CPU tensor. There is no CPU fallback.")
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------- Chamfer / KNN
+class _Chamfer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        _need_cuda(x, y)
+        x, y = _f32c(x), _f32c(y)
+        if x.dim() != 3 or y.dim() != 3 or x.shape[2] != 3 or y.shape[2] != 3:
+            raise ValueError(f"Expected (B,P,3) point clouds, got {tuple(x.shape)} and {tuple(y.shape)}")
+        if x.shape[0] != y.shape[0]:
+            raise ValueError("y must have the same batch dimension as x")
+        B, P1, _ = x.shape
+        P2 = y.shape[1]
+        L = _lib.lib()
+        idx_x = torch.empty(B, P1, dtype=torch.int32, device=x.device)
+        idx_y = torch.empty(B, P2, dtype=torch.int32, device=x.device)
+        cham = torch.empty(B, dtype=torch.float32, device=x.device)
+        nb = L.ptk_chamfer_workspace_bytes(B, P1, P2)
+        ws = _ws(nb, x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.ptk_chamfer_fwd(_p(x), _p(y), B, P1, P2, None, _p(idx_x), None, _p(idx_y), _p(cham),
+                                         _p(ws), ws.numel(), _stream()), "ptk_chamfer_fwd")
+        ctx.save_for_backward(x, y, idx_x, idx_y)
+        ctx.mark_non_differentiable(idx_x, idx_y)
+        return cham, idx_x, idx_y
+
+    @staticmethod
+    def backward(ctx, g, _gi, _gj):
+        x, y, idx_x, idx_y = ctx.saved_tensors
+        B, P1, _ = x.shape
+        P2 = y.shape[1]
+        g = _f32c(g)
+        gx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gy = torch.empty_like(y) if ctx.needs_input_grad[1] else None
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.lib().ptk_chamfer_bwd(_p(x), _p(y), _p(idx_x), _p(idx_y), _p(g), B, P1, P2, _p(gx),
+                                                  _p(gy), _stream()), "ptk_chamfer_bwd")
+        return gx, gy
+
+
+def chamfer(x, y):
+    """cham (B,), idx_x (B,P1) int32, idx_y (B,P2) int32.  Differentiable w.r.t. x and y."""
+    return _Chamfer.apply(x, y)
+
+
+def knn1(p1, p2):
+    """dists (B,P1) f32, idx (B,P1) int32 -- forward only."""
+    _need_cuda(p1, p2)
+    p1, p2 = _f32c(p1), _f32c(p2)
+    if p1.dim() != 3 or p2.dim() != 3 or p1.shape[2] != 3 or p2.shape[2] != 3 or p1.shape[0] != p2.shape[0]:
+        raise ValueError(f"Expected (B,P,3) point clouds, got {tuple(p1.shape)} and {tuple(p2.shape)}")
+    B, P1, _ = p1.shape
+    P2 = p2.shape[1]
+    L = _lib.lib()
+    dist = torch.empty(B, P1, dtype=torch.float32, device=p1.device)
+    idx = torch.empty(B, P1, dtype=torch.int32, device=p1.device)
+    ws = _ws(8 * B * P1, p1.device)
+    with torch.cuda.device(p1.device):
+        _lib.check(L.ptk_knn1_fwd(_p(p1), _p(p2), B, P1, P2, _p(dist), _p(idx), _p(ws), ws.numel(), _stream()),
+                   "ptk_knn1_fwd")
+    return dist, idx
+
+
+# ------------------------------------------------------------------------------------- surface sampling
+class _Sample(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, verts, faces_i32, u_face, uv):
+        _need_cuda(verts, faces_i32, u_face, uv)
+        verts, u_face, uv = _f32c(verts), _f32c(u_face), _f32c(uv)
+        if verts.dim() != 3 or verts.shape[2] != 3:
+            raise ValueError(f"verts must be (B,V,3), got {tuple(verts.shape)}")
+        if faces_i32.dtype != torch.int32 or faces_i32.dim() != 2 or faces_i32.shape[1] != 3:
+            raise ValueError("faces must be an (F,3) int32 tensor")
+        B, V, _ = verts.shape
+        F = faces_i32.shape[0]
+        S = u_face.shape[1]
+        if tuple(u_face.shape) != (B, S) or tuple(uv.shape) != (2, B, S):
+            raise ValueError("u_face must be (B,S) and uv (2,B,S)")
+        faces_i32 = faces_i32.contiguous()
+        L = _lib.lib()
+        pts = torch.empty(B, S, 3, dtype=torch.float32, device=verts.device)
+        fidx = torch.empty(B, S, dtype=torch.int32, device=verts.device)
+        ws = _ws(L.ptk_sample_workspace_bytes(B, F), verts.device)
+        with torch.cuda.device(verts.device):
+            _lib.check(L.ptk_sample_fwd(_p(verts), B, V, _p(faces_i32), F, _p(u_face), _p(uv), S, _p(pts),
+                                        _p(fidx), _p(ws), ws.numel(), _stream()), "ptk_sample_fwd")
+        ctx.save_for_backward(fidx, uv, faces_i32)
+        ctx.dims = (B, V, F, S)
+        ctx.mark_non_differentiable(fidx)
+        return pts, fidx
+
+    @staticmethod
+    def backward(ctx, gpts, _gf):
+        fidx, uv, faces_i32 = ctx.saved_tensors
+        B, V, F, S = ctx.dims
+        gpts = _f32c(gpts)
+        gv = torch.empty(B, V, 3, dtype=torch.float32, device=gpts.device)
+        with torch.cuda.device(gpts.device):
+            _lib.check(_lib.lib().ptk_sample_bwd(_p(gpts), _p(fidx), _p(uv), _p(faces_i32), B, V, F, S, _p(gv),
+                                                 _stream()), "ptk_sample_bwd")
+        return gv, None, None, None
+
+
+def sample_points(verts, faces_i32, u_face, uv):
+    """pts (B,S,3), face_idx (B,S) for explicit uniforms; differentiable w.r.t. verts."""
+    return _Sample.apply(verts, faces_i32, u_face, uv)
+
+
+def face_areas_normals(verts_packed, faces_i64):
+    _need_cuda(verts_packed, faces_i64)
+    v = _f32c(verts_packed)
+    f = faces_i64.contiguous().long()
+    F = f.shape[0]
+    areas = torch.empty(F, dtype=torch.float32, device=v.device)
+    normals = torch.empty(F, 3, dtype=torch.float32, device=v.device)
+    with torch.cuda.device(v.device):
+        _lib.check(_lib.lib().ptk_face_areas_normals(_p(v), v.shape[0], _p(f), F, _p(areas), _p(normals),
+                                                     _stream()), "ptk_face_areas_normals")
+    return areas, normals
+
+
+# ------------------------------------------------------------------------------------- GCN primitives
+def _linear_fwd(X2, W2, out=None):
+    M, K = X2.shape
+    N = W2.shape[1]
+    H = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=X2.device)
+    _lib.check(_lib.lib().ptk_gcn_linear_fwd(_p(X2), _p(W2), M, K, N, _p(H), _stream()), "ptk_gcn_linear_fwd")
+    return H
+
+
+def _linear_dgrad(gH2, W2, act2):
+    M, N = gH2.shape
+    K = W2.shape[0]
+    gX = torch.empty(M, K, dtype=torch.float32, device=gH2.device)
+    _lib.check(_lib.lib().ptk_gcn_linear_dgrad(_p(gH2), _p(W2), _p(act2), M, K, N, _p(gX), _stream()),
+               "ptk_gcn_linear_dgrad")
+    return gX
+
+
+def _linear_wgrad(X2, gH2):
+    M, K = X2.shape
+    N = gH2.shape[1]
+    L = _lib.lib()
+    gW = torch.empty(K, N, dtype=torch.float32, device=X2.device)
+    ws = _ws(L.ptk_gcn_linear_wgrad_workspace_bytes(M, K, N), X2.device)
+    _lib.check(L.ptk_gcn_linear_wgrad(_p(X2), _p(gH2), M, K, N, _p(gW), _p(ws), ws.numel(), _stream()),
+               "ptk_gcn_linear_wgrad")
+    return gW
+
+
+def _aggregate(g: Graph, H3, Lc, bias, relu, transpose=False, out=None):
+    B, Nv, Cc = H3.shape
+    if Nv != g.n:
+        raise ValueError(f"features have {Nv} vertices but the adjacency has {g.n}")
+    out = out if out is not None else torch.empty_like(H3)
+    if transpose:
+        rp, col, val, hubs, nh = g.rowptr_t, g.col_t, g.val_t, g.hubs_t, g.n_hubs_t
+    else:
+        rp, col, val, hubs, nh = g.rowptr, g.col, g.val, g.hubs, g.n_hubs
+    _lib.check(_lib.lib().ptk_gcn_aggregate(_p(rp), _p(col), _p(val), _p(hubs), nh, Nv, _p(H3), B, Cc, Lc,
+                                            _p(bias), int(relu), _p(out), _stream()), "ptk_gcn_aggregate")
+    return out
+
+
+def _bias_grad(g2, Lc):
+    M, Cc = g2.shape
+    L = _lib.lib()
+    gb = torch.empty(Cc, dtype=torch.float32, device=g2.device)
+    ws = _ws(L.ptk_gcn_bias_grad_workspace_bytes(M, Lc), g2.device)
+    _lib.check(L.ptk_gcn_bias_grad(_p(g2), M, Cc, Lc, _p(gb), _p(ws), ws.numel(), _stream()), "ptk_gcn_bias_grad")
+    return gb
+
+
+def _relu_mask(g, act):
+    out = torch.empty_like(g)
+    _lib.check(_lib.lib().ptk_relu_mask(_p(g), _p(act), g.numel(), _p(out), _stream()), "ptk_relu_mask")
+    return out
+
+
+class _GCNLayer(torch.autograd.Function):
+    """One GCN_layer.forward (vision/model.py:351-363): linear + aggregate (+bias, +ReLU)."""
+
+    @staticmethod
+    def forward(ctx, X, W, bias, graph, Lc, relu):
+        _need_cuda(X, W, bias)
+        X, W, bias = _f32c(X), _f32c(W), _f32c(bias)
+        B, Nv, K = X.shape
+        W2 = W.reshape(K, -1)
+        with torch.cuda.device(X.device):
+            H = _linear_fwd(X.reshape(B * Nv, K), W2).reshape(B, Nv, -1)
+            out = _aggregate(graph, H, Lc, bias, relu)
+        ctx.save_for_backward(X, W2, out if relu else None)
+        ctx.graph, ctx.Lc, ctx.relu, ctx.wshape = graph, Lc, relu, W.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        X, W2, out = ctx.saved_tensors
+        B, Nv, K = X.shape
+        N = W2.shape[1]
+        gout = _f32c(gout)
+        with torch.cuda.device(X.device):
+            if ctx.relu:
+                gout = _relu_mask(gout, out)
+            gb = _bias_grad(gout.reshape(B * Nv, N), ctx.Lc) if ctx.needs_input_grad[2] else None
+            gH = _aggregate(ctx.graph, gout, ctx.Lc, None, False, transpose=True).reshape(B * Nv, N)
+            gW = _linear_wgrad(X.reshape(B * Nv, K), gH).reshape(ctx.wshape) if ctx.needs_input_grad[1] else None
+            gX = _linear_dgrad(gH, W2, None).reshape(B, Nv, K) if ctx.needs_input_grad[0] else None
+        return gX, gW, gb, None, None, None
+
+
+def gcn_layer(X, W, bias, adj, Lc, relu):
+    return _GCNLayer.apply(X, W, bias, graph_of(adj), int(Lc), bool(relu))
+
+
+class _GCNStack(torch.autograd.Function):
+    """The whole GCN.forward (vision/model.py:316-331): n layers, ReLU on all but the last, the first
+    n-1 layers 'cut' (only the first L channels are propagated).  One autograd node so that the ReLU
+    backward of layer l is fused into the dgrad epilogue of layer l+1 and H buffers are reused."""
+
+    @staticmethod
+    def forward(ctx, X, graph, Ls, relus, *params):
+        n = len(params) // 2
+        Ws, bs = params[:n], params[n:]
+        _need_cuda(X, *params)
+        X = _f32c(X)
+        B, Nv, _ = X.shape
+        acts = [X]
+        with torch.cuda.device(X.device):
+            Hbuf = {}
+            for l in range(n):
+                K = acts[-1].shape[2]
+                W2 = _f32c(Ws[l]).reshape(K, -1)
+                N = W2.shape[1]
+                H = Hbuf.get(N)
+                if H is None:
+                    H = Hbuf[N] = torch.empty(B * Nv, N, dtype=torch.float32, device=X.device)
+                _linear_fwd(acts[-1].reshape(B * Nv, K), W2, out=H)
+                acts.append(_aggregate(graph, H.reshape(B, Nv, N), Ls[l], _f32c(bs[l]), relus[l]))
+        ctx.save_for_backward(*acts, *[_f32c(w) for w in Ws])
+        ctx.graph, ctx.Ls, ctx.relus, ctx.n = graph, Ls, relus, n
+        ctx.wshapes = [w.shape for w in Ws]
+        return acts[-1]
+
+    @staticmethod
+    def backward(ctx, gout):
+        n = ctx.n
+        saved = ctx.saved_tensors
+        acts, Ws = saved[:n + 1], saved[n + 1:]
+        B, Nv, _ = acts[0].shape
+        M = B * Nv
+        gWs, gbs = [None] * n, [None] * n
+        g = _f32c(gout)
+        with torch.cuda.device(g.device):
+            if ctx.relus[n - 1]:
+                g = _relu_mask(g, acts[n])
+            for l in range(n - 1, -1, -1):
+                K = acts[l].shape[2]
+                W2 = Ws[l].reshape(K, -1)
+                N = W2.shape[1]
+                if ctx.needs_input_grad[4 + n + l]:
+                    gbs[l] = _bias_grad(g.reshape(M, N), ctx.Ls[l])
+                gH = _aggregate(ctx.graph, g.reshape(B, Nv, N), ctx.Ls[l], None, False, transpose=True).reshape(M, N)
+                if ctx.needs_input_grad[4 + l]:
+                    gWs[l] = _linear_wgrad(acts[l].reshape(M, K), gH).reshape(ctx.wshapes[l])
+                if l > 0 or ctx.needs_input_grad[0]:
+                    mask = acts[l].reshape(M, K) if (l > 0 and ctx.relus[l - 1]) else None
+                    g = _linear_dgrad(gH, W2, mask).reshape(B, Nv, K)
+                else:
+                    g = None
+        return (g, None, None, None, *gWs, *gbs)
+
+
+def gcn_stack(X, adj, weights, biases, Ls, relus):
+    return _GCNStack.apply(X, graph_of(adj), tuple(int(v) for v in Ls), tuple(bool(r) for r in relus),
+                           *weights, *biases)

@@ -1,0 +1,173 @@
+"""Drop-in replacements for the hot-path functions of pterotactyl/utility/utils.py -- same names,
+arguments, return values and error behaviour, backed by libptk_b200.so.
+
+    chamfer_distance(verts, faces, gt_points, num=1000, repeat=3)   utils.py:204-217
+    batch_sample(verts, faces, num=10000)                            utils.py:152-187
+    calc_adj / normalize_adj / adj_fuse_touch / adj_init             utils.py:47-148
+    load_mesh_touch / load_mesh_vision                               utils.py:30-36,194-200
+
+`install()` (package __init__) patches these over an importable `pterotactyl.utility.utils` so the
+reference's train / eval / policy scripts pick the new path up without edits.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import graph as _graph
+from . import obj_io, ops
+
+_faces_cache = {}
+
+
+def _faces_i32(faces):
+    """(F,3) int64 faces of the reference -> cached int32 copy on the same device."""
+    if faces.dtype == torch.int32:
+        return faces.contiguous()
+    key = (faces.data_ptr(), faces._version, tuple(faces.shape), str(faces.device))
+    hit = _faces_cache.get(key)
+    if hit is None:
+        if len(_faces_cache) > 64:
+            _faces_cache.clear()
+        hit = _faces_cache[key] = faces.to(torch.int32).contiguous()
+    return hit
+
+
+def draw_uniforms(bs, num, device, generator=None):
+    """The RNG stream of one batch_sample call, in the reference's consumption order:
+    first the face draw (Tensor.multinomial, utils.py:170), then torch.rand(2, bs, num)
+    (_rand_barycentric_coords, utils.py:179)."""
+    u_face = torch.rand(bs, num, device=device, generator=generator)
+    uv = torch.rand(2, bs, num, device=device, generator=generator)
+    return u_face, uv
+
+
+def batch_sample(verts, faces, num=10000, generator=None, uniforms=None):
+    """Sample `num` area-weighted surface points per mesh.  verts (B,V,3), faces (F,3) shared by the
+    batch -> (B,num,3).  Gradients flow to verts only (utils.py:152-187)."""
+    u_face, uv = uniforms if uniforms is not None else draw_uniforms(verts.shape[0], num, verts.device, generator)
+    pts, _ = ops.sample_points(verts, _faces_i32(faces), u_face, uv)
+    return pts
+
+
+def chamfer_distance(verts, faces, gt_points, num=1000, repeat=3, generator=None, uniforms=None):
+    """Chamfer distance between a predicted mesh and a ground-truth cloud: mean over `repeat`
+    independent surface samplings of pytorch3d-style chamfer(pred_points, gt_points,
+    batch_reduction=None).  Returns (B,) (utils.py:204-217)."""
+    cds = []
+    for r in range(max(int(repeat), 1)):
+        uni = uniforms[r] if uniforms is not None else None
+        pred_points = batch_sample(verts, faces, num=num, generator=generator, uniforms=uni)
+        cd, _, _ = ops.chamfer(pred_points, gt_points)
+        cds.append(cd)
+    if len(cds) == 1:
+        return cds[0]
+    return torch.stack(cds).mean(dim=0)
+
+
+# ------------------------------------------------------------------------------------- adjacency
+def calc_adj(faces):
+    """Dense binary adjacency (+ identity) from faces (utils.py:134-148)."""
+    v1, v2, v3 = faces[:, 0], faces[:, 1], faces[:, 2]
+    num_verts = int(faces.max())
+    adj = torch.eye(num_verts + 1).to(faces.device)
+    adj[(v1, v2)] = 1
+    adj[(v1, v3)] = 1
+    adj[(v2, v1)] = 1
+    adj[(v2, v3)] = 1
+    adj[(v3, v1)] = 1
+    adj[(v3, v2)] = 1
+    return adj
+
+
+def normalize_adj(mx):
+    """Row-normalise a binary adjacency (utils.py:47-52).  The result is registered with the CSR
+    cache so GCN layers never re-scan the dense matrix."""
+    rowsum = mx.sum(1)
+    r_inv = (1.0 / rowsum).view(-1)
+    r_inv[r_inv != r_inv] = 0.0
+    out = mx * r_inv[:, None]  # == mm(eye * r_inv, mx): products with 0/1 are exact
+    return out
+
+
+def adj_fuse_touch(verts, faces, adj, args):
+    """Fuse vision and touch charts into one graph (utils.py:75-130)."""
+    vnp = verts.data.cpu().numpy()
+    groups = {}
+    for e, v in enumerate(vnp):
+        groups.setdefault(v.tobytes(), []).append(e)
+    central_points = []
+    if args.use_touch:
+        sheet_verts, sheet_faces = load_mesh_touch(_object_path("touch_chart.obj"), device=faces.device)
+        sheet_adj = calc_adj(sheet_faces)
+        ns, n0 = sheet_adj.shape[0], adj.shape[0]
+        k = (1 if args.finger else 4) * args.num_grasps
+        central_points = [4 + i * ns + n0 for i in range(k)]
+        new_adj = torch.zeros((n0 + k * ns, n0 + k * ns), device=adj.device)
+        new_adj[:n0, :n0] = adj
+        for i in range(k):
+            s = n0 + ns * i
+            new_adj[s:s + ns, s:s + ns] = sheet_adj
+        adj = new_adj
+        all_faces = [faces] + [sheet_faces + verts.shape[0] + i * sheet_verts.shape[0] for i in range(k)]
+        faces = torch.cat(all_faces)
+    # vertices sharing a 3-D position talk to each other and to every touch-chart centre
+    dup = [g for g in groups.values() if len(g) > 1]
+    if dup:
+        a = adj.cpu()
+        for cur in dup:
+            idx = torch.tensor(cur)
+            a[idx[:, None], idx[None, :]] = 1
+            if central_points:
+                c = torch.tensor(central_points)
+                a[idx[:, None], c[None, :]] = 1
+                a[c[:, None], idx[None, :]] = 1
+        adj = a.to(adj.device)
+    return adj, faces
+
+
+def adj_init(verts, faces, args):
+    """{'origional', 'adj', 'faces'} (utils.py:56-71)."""
+    adj = calc_adj(faces)
+    adj_info = {"origional": normalize_adj(adj.clone())}
+    if args.use_touch:
+        adj, faces = adj_fuse_touch(verts, faces, adj, args)
+    adj_info["adj"] = normalize_adj(adj)
+    adj_info["faces"] = faces
+    if adj_info["adj"].is_cuda:
+        for k in ("origional", "adj"):
+            _graph.graph_of(adj_info[k])
+    return adj_info
+
+
+# ------------------------------------------------------------------------------------- mesh loading
+_OBJECT_DIR = None
+
+
+def set_object_dir(path):
+    """Directory holding vision_charts.obj / touch_chart.obj (pterotactyl/objects)."""
+    global _OBJECT_DIR
+    _OBJECT_DIR = path
+
+
+def _object_path(name):
+    if _OBJECT_DIR is not None:
+        return os.path.join(_OBJECT_DIR, name)
+    try:
+        import pterotactyl.objects as objects  # the reference's asset package (utils.py:25)
+        return os.path.join(os.path.dirname(objects.__file__), name)
+    except Exception as exc:  # pragma: no cover
+        raise FileNotFoundError(
+            f"cannot locate {name}: call set_object_dir(<pterotactyl/objects>) or make pterotactyl importable") from exc
+
+
+def load_mesh_touch(obj, device="cuda"):
+    """verts (V,3) f32, faces (F,3) i64 on the GPU (utils.py:194-200)."""
+    verts, faces, _ = obj_io.load_obj(obj)
+    return verts.float().to(device), faces.verts_idx.long().to(device)
+
+
+def load_mesh_vision(args, obj, device="cuda"):
+    """(adj_info, verts) for the vision charts (utils.py:30-36)."""
+    verts, faces = load_mesh_touch(obj, device=device)
+    return adj_init(verts, faces, args), verts

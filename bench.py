@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the pterotactyl reconstruction hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): Chamfer pairs/s at 10k x 10k points.  One "step" = Chamfer forward + backward
+(both directions, mean reduction, gradients w.r.t. both clouds) over a batch of 256 cloud pairs per GPU
+(BASELINE.json north_star: "Chamfer (10k x 10k, batch 256)"; config 5 "fwd+bwd").  Weak scaling: each
+rank owns 256 whole pairs, no data-path collective.
+
+One JSON line on stdout (rank 0).  Besides the base contract it carries
+  roofline      FP32-pipe roofline of the dominant kernel (chamfer_nn_kernel), timed live with CUDA
+                events on the launching stream
+  cpu_baseline  the CPU oracle (oracle/ptk_oracle.c, OpenMP) on a bounded sample of the same workload
+  e2e           same metric through the host-buffer C ABI (ptk_host_chamfer): pinned host clouds ->
+                H2D -> fwd+bwd -> D2H of the per-pair loss, copies inside the timed region
+  extra         secondary numbers: GCN reconstruction steps/s (config 3 shape), sampler, aggregate GB/s
+
+`--impl reference` times the reference arm: the CPU restatement of the reference's PyTorch3D path
+(oracle port; PyTorch3D itself is not vendored/installable here) on all host threads, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P = 10000           # points per cloud
+B_PER_GPU = 256     # cloud pairs per GPU per step
+NSETS = 4           # rotating input sets: 4 x 61 MB = 246 MB > 126 MB L2
+FLOP_PER_EVAL = 8   # 3 sub + 3 mul + 2 add
+ISSUE_PER_EVAL = 6  # 3 FADD + 1 FMUL + 2 FFMA on the FP32 pipe
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.rows:
+            if ts < t0 or ts > t1 + 0.1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except Exception:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:  # timed region shorter than the sampling period: use every sample we have
+            for ts, line in self.rows:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                except Exception:
+                    pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------- CPU legs
+def cpu_chamfer_leg(seconds_target, steps=None, warmup=0):
+    """Oracle Chamfer fwd+bwd on a bounded sample: `bs` pairs of 10k x 10k per step, all host threads."""
+    from oracle import oracle as orc
+    orc.build()
+    threads = orc.num_threads()
+    bs = max(2, min(B_PER_GPU, threads))
+    rng = np.random.default_rng(0)
+    x = (rng.random((bs, P, 3), np.float32) - 0.5).astype(np.float32)
+    y = (rng.random((bs, P, 3), np.float32) - 0.5).astype(np.float32)
+    g = np.ones(bs, np.float32)
+
+    def step():
+        cham, _, ix, _, iy = orc.chamfer_fwd(x, y, use_fma=True)
+        orc.chamfer_bwd(x, y, ix, iy, g)
+        return cham
+
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    n = 0
+    while True:
+        step()
+        n += 1
+        el = time.perf_counter() - t0
+        if steps is not None:
+            if n >= steps:
+                break
+        elif el >= seconds_target or n >= 50:
+            break
+    el = time.perf_counter() - t0
+    return {"value": bs * n / el, "unit": "pairs/s", "cores": threads, "kind": "port",
+            "sample": f"{n} step(s) x {bs} pairs of {P}x{P} points, Chamfer fwd+bwd, oracle/ptk_oracle.c "
+                      f"(OpenMP, {threads} threads), {el:.1f} s"}, el, n, bs
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    info, el, n, bs = cpu_chamfer_leg(None, steps=max(args.steps, 1), warmup=min(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "chamfer_pairs_per_s_10k", "value": info["value"], "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * el / n,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+        "config": workload_config(args.gpus, sample_pairs=bs),
+        "cpu_baseline": info,
+        "e2e": {"value": info["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "reference arm = CPU restatement of the reference's PyTorch3D chamfer path (PyTorch3D 0.5.0 "
+                "is not vendored in the reference tree and cannot be installed offline); all host threads",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus, sample_pairs=None):
+    cfg = {"workload": f"Chamfer fwd+bwd, {P}x{P} points, batch {B_PER_GPU} pairs per GPU (BASELINE configs[4] "
+                       f"cell P=10k,B=256; north_star target shape)",
+           "points": P, "pairs_per_gpu": B_PER_GPU, "global_pairs": B_PER_GPU * n_gpus,
+           "parallelism": f"object-sharded x{n_gpus}, no data-path collective",
+           "l2_policy": f"rotating {NSETS} input sets ({NSETS * 2 * B_PER_GPU * P * 12 / 1e6:.0f} MB > 126 MB L2)"}
+    if sample_pairs is not None:
+        cfg["cpu_sample_pairs_per_step"] = sample_pairs
+    return cfg
+
+
+# --------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import ctypes as C
+
+    import torch
+    import torch.distributed as dist
+
+    import ptk_b200
+    from ptk_b200 import _lib
+
+    rank, world, local = ptk_b200.dist.init_from_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    L = _lib.lib()
+    info = _lib.device_info(local)
+    K, W = args.steps, max(args.warmup, 3)
+    B = B_PER_GPU
+
+    def p(t):
+        return C.c_void_p(t.data_ptr()) if t is not None else None
+
+    # inputs resident in HBM: NSETS rotating sets of (x, y), x,y ~ U[-0.5, 0.5]^3, per-rank seeds
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    xs = [torch.rand(B, P, 3, device=dev, generator=gen) - 0.5 for _ in range(NSETS)]
+    ys = [torch.rand(B, P, 3, device=dev, generator=gen) - 0.5 for _ in range(NSETS)]
+    idx_x = torch.empty(B, P, dtype=torch.int32, device=dev)
+    idx_y = torch.empty(B, P, dtype=torch.int32, device=dev)
+    cham = torch.empty(B, device=dev)
+    gcham = torch.full((B,), 1.0 / B, device=dev)
+    gx = torch.empty(B, P, 3, device=dev)
+    gy = torch.empty(B, P, 3, device=dev)
+    ws = torch.empty(L.ptk_chamfer_workspace_bytes(B, P, P), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+    sp = C.c_void_p(stream.cuda_stream)
+
+    def fwd(i):
+        _lib.check(L.ptk_chamfer_fwd(p(xs[i % NSETS]), p(ys[i % NSETS]), B, P, P, None, p(idx_x), None, p(idx_y),
+                                     p(cham), p(ws), ws.numel(), sp), "ptk_chamfer_fwd")
+
+    def bwd(i):
+        _lib.check(L.ptk_chamfer_bwd(p(xs[i % NSETS]), p(ys[i % NSETS]), p(idx_x), p(idx_y), p(gcham), B, P, P,
+                                     p(gx), p(gy), sp), "ptk_chamfer_bwd")
+
+    for i in range(W):
+        fwd(i); bwd(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    t_wall0 = time.time()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record(stream)
+    for i in range(K):
+        ev[i][0].record(stream)
+        fwd(i)
+        ev[i][1].record(stream)
+        bwd(i)
+        ev[i][2].record(stream)
+    stop.record(stream)
+    torch.cuda.synchronize()
+    t_wall1 = time.time()
+    if world > 1:
+        dist.barrier()
+    total_ms = start.elapsed_time(stop)
+    fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    pairs_per_s = world * B * K / (total_ms * 1e-3)
+
+    # ---------------------------------------------------------------- end-to-end through the host ABI
+    e2e = None
+    hx = [torch.empty(B, P, 3).pin_memory() for _ in range(2)]
+    hy = [torch.empty(B, P, 3).pin_memory() for _ in range(2)]
+    for t in hx + hy:
+        t.uniform_(-0.5, 0.5)
+    hg = np.full(B, 1.0 / B, np.float32)
+    hcham = torch.empty(B).pin_memory()
+    ctx = ptk_b200.host.HostContext(local)
+    out = {"cham": hcham.numpy()}
+    ke = max(3, min(K, 10))
+    for i in range(2):
+        ctx.chamfer(hx[i % 2].numpy(), hy[i % 2].numpy(), grad_cham=hg, want_grad_x=False, want_grad_y=False, out=out)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(ke):
+        ctx.chamfer(hx[i % 2].numpy(), hy[i % 2].numpy(), grad_cham=hg, want_grad_x=False, want_grad_y=False, out=out)
+    e2e_s = time.perf_counter() - t0  # every call ends with a stream synchronise: host clock == device done
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    ctx.close()
+    e2e = {"value": world * B * ke / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": 2 * B * P * 12 + B * 4,
+           "d2h_bytes_per_step": B * 4, "steps": ke, "ms_per_step": 1e3 * e2e_s / ke,
+           "api": "ptk_host_chamfer (C ABI, pinned host buffers; backward on device, loss read back)"}
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---------------------------------------------------------------- roofline of the dominant kernel
+    evals = 2.0 * B * P * P                      # both directions, per launch
+    sm_max_mhz = (clocks or {}).get("sm_max_mhz") or info["clock_khz"] / 1e3
+    peak_tflops = FLOP_PER_EVAL / ISSUE_PER_EVAL * 128 * info["sm_count"] * sm_max_mhz * 1e6 / 1e12
+    achieved = FLOP_PER_EVAL * evals / (fwd_ms * 1e-3) / 1e12
+    roofline = {
+        "kernel": "chamfer_nn_kernel<8> (+ ~10 us chamfer_finalize_kernel in the same event pair)",
+        "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+        "traffic": None,
+        "evals_per_s": evals / (fwd_ms * 1e-3), "ms_per_launch": fwd_ms,
+        "peak_source": f"derived, not in MEASURED_PEAKS.json: 128 FP32 lanes x {info['sm_count']} SMs x "
+                       f"{sm_max_mhz:.0f} MHz (max SM clock) / 6 issue slots per evaluation x 8 flop; "
+                       f"algorithmic work = 8 flop x 2*B*P1*P2 evaluations per launch",
+    }
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak = 6650.0
+    hbm_src = "fallback"
+    if os.path.exists(peaks_path):
+        try:
+            hbm_peak = float(json.load(open(peaks_path))["hbm_gbs"]); hbm_src = "measured"
+        except Exception:
+            pass
+
+    extra = {"fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "bwd_hbm_gbs": (2 * B * P) * (12 + 4 + 12 + 12 + 12) / (bwd_ms * 1e-3) / 1e9,
+             "device": torch.cuda.get_device_name(dev), "sm_count": info["sm_count"]}
+    if not args.no_extra:
+        try:
+            extra.update(extra_measurements(torch, ptk_b200, dev, hbm_peak, hbm_src))
+        except Exception as exc:  # secondary numbers must never lose the headline
+            extra["extra_error"] = repr(exc)
+
+    cpu = None
+    if not args.no_cpu:
+        cpu, _, _, _ = cpu_chamfer_leg(10.0)
+
+    line = {
+        "metric": "chamfer_pairs_per_s_10k", "value": pairs_per_s, "unit": "pairs/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "fp32", "data": "synthetic", "config": workload_config(world),
+        "clocks": clocks, "e2e": e2e, "gpu_launches": 4 * K * world,
+        "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def extra_measurements(torch, ptk_b200, dev, hbm_peak, hbm_src):
+    """Secondary numbers (not the headline): config-3-shaped GCN reconstruction step, sampler, aggregate."""
+    import types
+    from ptk_b200.graph import Graph
+    out = {}
+    gold = os.path.join(ROOT, "tests", "golden")
+    adj = dict(np.load(os.path.join(gold, "adjacency.npz")))
+    meshes = dict(np.load(os.path.join(gold, "meshes.npz")))
+
+    def timeit(fn, iters, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    # --- GCN aggregate at a batch that spills L2 (B=256, N=1949, C=300, L=99): HBM roofline
+    g = Graph.from_csr(adj["p_adj_rowptr"], adj["p_adj_col"], dev)
+    Bh, C_, L_ = 256, 300, 99
+    H = torch.rand(Bh, g.n, C_, device=dev)
+    bias = torch.rand(C_, device=dev)
+    o = torch.empty_like(H)
+    ms = timeit(lambda: ptk_b200.ops._aggregate(g, H, L_, bias, True, out=o), 20)
+    alg = Bh * g.n * C_ * 4 * 2 + g.nnz * 8 + (g.n + 1) * 4
+    out["gcn_aggregate"] = {"shape": f"B={Bh} N={g.n} C={C_} L={L_} (fwd, bias+ReLU fused)", "ms": ms,
+                            "achieved_gbs": alg / (ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
+                            "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg}
+    del H, o
+
+    # --- config-3-shaped reconstruction step: 3 GCN passes (448->300x18->3) + 10k-point Chamfer loss x3 + backward
+    args = types.SimpleNamespace(use_img=True, use_touch=True, finger=True, num_grasps=5, num_GCN_layers=20,
+                                 hidden_GCN_size=300, cut=0.33)
+    to = lambda a, dt: torch.from_numpy(a).to(dev, dt)
+    adj_info = {"origional": Graph.from_csr(adj["p_origional_rowptr"], adj["p_origional_col"], dev).dense(),
+                "adj": g.dense(), "faces": to(adj["p_faces"], torch.int64)}
+    torch.manual_seed(0)
+    net = ptk_b200.recon.ChartDeformer(adj_info, args, 448).to(dev)
+    Bs = 16
+    vision = to(meshes["vision_verts"], torch.float32)[None].repeat(Bs, 1, 1)
+    touch = torch.rand(Bs, 125, 3, device=dev) * 0.02 + 0.2
+    feats = [torch.rand(Bs, 1824, 448, device=dev), torch.rand(Bs, 1949, 448, device=dev),
+             torch.rand(Bs, 1949, 448, device=dev)]
+    gt = torch.nn.functional.normalize(torch.randn(Bs, 10000, 3, device=dev), dim=-1) * 0.25
+    opt = torch.optim.Adam(net.parameters(), lr=3e-4)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        verts = net(vision, touch, lambda it, v: feats[it])
+        loss, _ = ptk_b200.recon.recon_loss(verts, adj_info["faces"], gt, number_points=10000)
+        loss.backward()
+        opt.step()
+
+    ms = timeit(step, 5, warm=2)
+    gemm_flop = 3 * 2 * Bs * (1824 * (448 * 300 + 18 * 300 * 300 + 300 * 3) + 2 * 1949 * (448 * 300 + 18 * 300 * 300 + 300 * 3))
+    out["recon_step"] = {"shape": "v_t_p GCN part: B=16, 3 x (448->300x18->3), N=1824/1949/1949, 3 x 10k-point "
+                                  "Chamfer loss, fwd+bwd+Adam; synthetic vertex features (CNN/MLP encoders out of scope)",
+                         "ms": ms, "steps_per_s": 1e3 / ms, "gemm_tflops": gemm_flop / (ms * 1e-3) / 1e12}
+    # --- sampler (B=16, V=1949, F=2464, S=10000)
+    faces32 = adj_info["faces"].to(torch.int32)
+    verts = torch.cat([vision, touch], 1)
+    uf = torch.rand(Bs, 10000, device=dev)
+    uv = torch.rand(2, Bs, 10000, device=dev)
+    ms = timeit(lambda: ptk_b200.ops.sample_points(verts, faces32, uf, uv), 20)
+    out["sampler"] = {"shape": "B=16 V=1949 F=2464 S=10000", "ms": ms}
+    return out
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,168 @@
+/*
+ * ptk.h -- C ABI of libptk_b200.so: the B200 (sm_100a) reconstruction hot path of pterotactyl.
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own: the hot path
+ * is reached through Python signatures that bottom out in PyTorch3D's `_C` extension and ATen.
+ * Each entry point below names the reference call (file:line under /root/reference, or the
+ * un-vendored PyTorch3D 0.5.0 symbol) it replaces.  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch types.  Unless a parameter is documented as HOST, every
+ *     pointer is a DEVICE pointer on the current CUDA device, owned by the caller; the library never
+ *     allocates or frees caller-visible memory (workspaces are passed in).
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
+ *     synchronisation and is safe under CUDA-graph capture.  The ptk_host_* family is the exception:
+ *     it takes HOST buffers, copies both ways and synchronises its own stream.
+ *   - return value: 0 (PTK_OK) or a negative PTK_ERR_*; ptk_last_error() gives a thread-local
+ *     message.  The reference raises ValueError on shape mismatch (PyTorch3D) -- the Python host
+ *     layer maps PTK_ERR_SHAPE to ValueError and the rest to RuntimeError.
+ *   - all float tensors are fp32, C-contiguous; indices are int32 at this ABI (int64 at the torch
+ *     boundary, converted by the host layer).
+ */
+#ifndef PTK_H_
+#define PTK_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTK_ABI_VERSION 1
+
+#define PTK_OK 0
+#define PTK_ERR_SHAPE (-1)     /* bad sizes / null pointer where one is required */
+#define PTK_ERR_ALIGN (-2)     /* pointer not aligned as documented */
+#define PTK_ERR_ARCH (-3)      /* device is not sm_100 */
+#define PTK_ERR_CUDA (-4)      /* a CUDA runtime call failed (message has the cudaError string) */
+#define PTK_ERR_WORKSPACE (-5) /* workspace too small */
+
+typedef void *ptk_stream_t; /* cudaStream_t */
+
+int ptk_version(void);
+const char *ptk_last_error(void);
+/* SM count, max SM clock (kHz), L2 bytes, opt-in shared memory per block, compute capability. */
+int ptk_device_info(int device, int *sm_count, int *clock_khz, int *l2_bytes, int *smem_optin,
+                    int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Chamfer distance / 1-NN between point clouds.
+ * Replaces pytorch3d.loss.chamfer_distance(x, y, batch_reduction=None) and pytorch3d.ops.knn_points
+ * (K=1) -- PyTorch3D 0.5.0 `_C.knn_points_idx` / `_C.knn_points_backward` -- as called from
+ * pterotactyl/utility/utils.py:207,212.
+ *   x (B,P1,3), y (B,P2,3).  Squared L2, dist = fma(dz,dz, fma(dy,dy, dx*dx)) (the arithmetic
+ *   PyTorch3D's CUDA kernel executes), strict '<' scanning targets in ascending order: the lowest
+ *   index wins exact ties.  cham[b] = mean_i dist_x[b,i] + mean_j dist_y[b,j].
+ * ---------------------------------------------------------------------------------------------- */
+size_t ptk_chamfer_workspace_bytes(int64_t B, int64_t P1, int64_t P2);
+
+/* One direction: for every p1[b,i] its nearest p2[b,j].  dist (B,P1) and/or idx (B,P1) may be NULL. */
+int ptk_knn1_fwd(const float *p1, const float *p2, int64_t B, int64_t P1, int64_t P2, float *dist,
+                 int32_t *idx, void *workspace, size_t workspace_bytes, ptk_stream_t stream);
+
+/* Both directions in one launch + fused mean reduction.  dist_x/dist_y may be NULL; idx_x (B,P1),
+ * idx_y (B,P2) and cham (B) are required (idx feeds the backward). */
+int ptk_chamfer_fwd(const float *x, const float *y, int64_t B, int64_t P1, int64_t P2, float *dist_x,
+                    int32_t *idx_x, float *dist_y, int32_t *idx_y, float *cham, void *workspace,
+                    size_t workspace_bytes, ptk_stream_t stream);
+
+/* Gradient of cham w.r.t. x and y (either may be NULL: the autoencoder only needs grad_y,
+ * pterotactyl/reconstruction/autoencoder/train.py:145-151).  grad_* are fully overwritten. */
+int ptk_chamfer_bwd(const float *x, const float *y, const int32_t *idx_x, const int32_t *idx_y,
+                    const float *grad_cham, int64_t B, int64_t P1, int64_t P2, float *grad_x,
+                    float *grad_y, ptk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Area-weighted surface sampling.  Replaces the body of utils.batch_sample
+ * (pterotactyl/utility/utils.py:152-187): pytorch3d mesh_face_areas_normals (utils.py:164), the NaN
+ * guards (165-168), Tensor.multinomial (170), _rand_barycentric_coords (179) and the barycentric
+ * interpolation (182-185), fused.
+ *   verts (B,V,3); faces (F,3) int32 shared by the batch; u_face (B,S) and uv (2,B,S) are the
+ *   uniform [0,1) draws (the RNG stream); pts (B,S,3); face_idx (B,S) int32 (saved for backward).
+ * Face choice uses an order-independent integer prefix sum (see oracle/ptk_oracle.c) so the result
+ * is bit-exact for a given uniform stream.
+ * ---------------------------------------------------------------------------------------------- */
+size_t ptk_sample_workspace_bytes(int64_t B, int64_t F);
+int ptk_sample_fwd(const float *verts, int64_t B, int64_t V, const int32_t *faces, int64_t F,
+                   const float *u_face, const float *uv, int64_t S, float *pts, int32_t *face_idx,
+                   void *workspace, size_t workspace_bytes, ptk_stream_t stream);
+/* grad_verts (B,V,3) is fully overwritten:  grad_verts[b, faces[f,k]] += w_k * grad_pts[b,s]. */
+int ptk_sample_bwd(const float *grad_pts, const int32_t *face_idx, const float *uv,
+                   const int32_t *faces, int64_t B, int64_t V, int64_t F, int64_t S,
+                   float *grad_verts, ptk_stream_t stream);
+
+/* pytorch3d.ops.mesh_face_areas_normals(verts, faces) drop-in (utils.py:21,164): packed verts (V,3),
+ * int64 faces (F,3) -> areas (F), unit normals (F,3) (normals may be NULL). */
+int ptk_face_areas_normals(const float *verts, int64_t V, const int64_t *faces, int64_t F, float *areas,
+                           float *normals, ptk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GCN vertex aggregation.  Replaces the dense `torch.matmul(adj, features[:, :, :length])` + concat +
+ * bias + activation of GCN_layer.forward (pterotactyl/reconstruction/vision/model.py:354-363, copies
+ * at autoencoder/model.py:112-124 and policies/DDQN/model.py:148-160) with a CSR gather.
+ *   out[b,i,c] = act( sum_e val[e] * in[b,col[e],c] + bias[c] )   for c <  L, e in row i
+ *   out[b,i,c] = act( in[b,i,c] )                                  for c >= L
+ * in/out (B,Nv,C) with C % 4 == 0 and 16-byte aligned bases for the vector path (any C works,
+ * scalar path otherwise).  bias may be NULL.  hubs (n_hubs int32 row ids, may be NULL) lists the
+ * rows of degree > 128 (touch-chart centre vertices, utils.py:95-98): each is processed by a whole
+ * CTA instead of one warp.  The backward w.r.t. `in` is the same call on the
+ * transposed graph with bias = NULL, relu = 0 (the activation mask is applied by the producer of
+ * the incoming gradient, see ptk_gcn_linear_dgrad).
+ * ---------------------------------------------------------------------------------------------- */
+int ptk_gcn_aggregate(const int32_t *rowptr, const int32_t *col, const float *val,
+                      const int32_t *hubs, int32_t n_hubs, int64_t Nv, const float *in, int64_t B,
+                      int64_t C, int64_t L, const float *bias, int relu, float *out,
+                      ptk_stream_t stream);
+/* gbias[c] = sum_{rows} g[row,c] for c < L, 0 for L <= c < C  (g is (M,C)); overwrites gbias.
+ * Deterministic two-stage column sum; workspace from ptk_gcn_bias_grad_workspace_bytes. */
+size_t ptk_gcn_bias_grad_workspace_bytes(int64_t M, int64_t L);
+int ptk_gcn_bias_grad(const float *g, int64_t M, int64_t C, int64_t L, float *gbias, void *workspace,
+                      size_t workspace_bytes, ptk_stream_t stream);
+
+/* out[i] = act[i] > 0 ? g[i] : 0 -- ReLU backward where it cannot be fused into a dgrad epilogue. */
+int ptk_relu_mask(const float *g, const float *act, int64_t n, float *out, ptk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GCN per-vertex linear layer.  Replaces `torch.matmul(features, self.weight)`
+ * (vision/model.py:352) and its autograd.
+ *   fwd   : H (M,N)  = X (M,K) . W (K,N)
+ *   dgrad : gX (M,K) = gH (M,N) . W^T, optionally masked by (act[m,k] > 0) -- the ReLU of the
+ *           previous layer (vision/model.py:324) fused into the epilogue; act may be NULL.
+ *   wgrad : gW (K,N) = X^T . gH  (overwrites gW; the sum over the M rows is split across CTAs and
+ *           reduced in a fixed order through the workspace => deterministic)
+ * ---------------------------------------------------------------------------------------------- */
+int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int64_t K, int64_t N, float *H,
+                       ptk_stream_t stream);
+int ptk_gcn_linear_dgrad(const float *gH, const float *W, const float *act, int64_t M, int64_t K,
+                         int64_t N, float *gX, ptk_stream_t stream);
+size_t ptk_gcn_linear_wgrad_workspace_bytes(int64_t M, int64_t K, int64_t N);
+int ptk_gcn_linear_wgrad(const float *X, const float *gH, int64_t M, int64_t K, int64_t N, float *gW,
+                         void *workspace, size_t workspace_bytes, ptk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer entry points (end-to-end path: H2D + kernels + D2H inside the call).
+ * All pointers are HOST pointers (pinned memory makes the copies asynchronous and faster).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ptk_host_ctx ptk_host_ctx;
+ptk_host_ctx *ptk_host_ctx_create(int device);
+void ptk_host_ctx_destroy(ptk_host_ctx *ctx);
+/* Chamfer forward (+ backward when grad_cham != NULL) on host clouds.  cham (B) required;
+ * idx_x/idx_y/grad_x/grad_y may be NULL (with grad_cham given the backward still runs on the device;
+ * gradients are copied back only where a host pointer is supplied). */
+int ptk_host_chamfer(ptk_host_ctx *ctx, const float *x, const float *y, int64_t B, int64_t P1,
+                     int64_t P2, float *cham, int32_t *idx_x, int32_t *idx_y, const float *grad_cham,
+                     float *grad_x, float *grad_y);
+/* utils.chamfer_distance(verts, faces, gt_points, num, repeat) (utils.py:204-217) on host buffers:
+ * u_face (repeat,B,S), uv (repeat,2,B,S); cd (B) = mean over repeats; grad_verts (B,V,3) (optional)
+ * is d(sum_b grad_cd[b]*cd[b])/d verts. */
+int ptk_host_mesh_chamfer(ptk_host_ctx *ctx, const float *verts, int64_t B, int64_t V,
+                          const int32_t *faces, int64_t F, const float *gt, int64_t P2,
+                          const float *u_face, const float *uv, int64_t S, int64_t repeat, float *cd,
+                          const float *grad_cd, float *grad_verts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTK_H_ */

@@ -1,0 +1,12 @@
+"""Import alias: the product package lives in the directory `active-3d-vision-and-touch_b200/`
+(not a valid Python identifier); `import ptk_b200` loads it as a regular package."""
+import importlib.util
+import os
+import sys
+
+_dir = os.path.join(os.path.dirname(os.path.abspath(__file__)), "active-3d-vision-and-touch_b200")
+_spec = importlib.util.spec_from_file_location(
+    "ptk_b200", os.path.join(_dir, "__init__.py"), submodule_search_locations=[_dir])
+_mod = importlib.util.module_from_spec(_spec)
+sys.modules["ptk_b200"] = _mod
+_spec.loader.exec_module(_mod)

@@ -1,0 +1,141 @@
+"""GPU parity of the Chamfer / 1-NN kernels (through the C ABI) against the CPU oracle and the golden
+vectors.  Bar: indices bit-exact, values/gradients within 1e-5 relative (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+import ptk_b200
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5  # relative, FP32 (north_star)
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def run(x, y, grad=None):
+    xt = torch.from_numpy(x).cuda().requires_grad_(grad is not None)
+    yt = torch.from_numpy(y).cuda().requires_grad_(grad is not None)
+    cham, ix, iy = ptk_b200.ops.chamfer(xt, yt)
+    out = [cham.detach().cpu().numpy(), ix.cpu().numpy(), iy.cpu().numpy()]
+    if grad is not None:
+        (cham * torch.from_numpy(grad).cuda()).sum().backward()
+        out += [xt.grad.cpu().numpy(), yt.grad.cpu().numpy()]
+    return out
+
+
+def test_config1_golden(golden, oracle):
+    g = golden("chamfer")
+    cham, ix, iy = run(g["c1_x"], g["c1_y"])
+    assert np.array_equal(ix, g["c1_fma_idx_x"]) and np.array_equal(iy, g["c1_fma_idx_y"])
+    assert np.array_equal(ix, g["c1_idx_x"]) and np.array_equal(iy, g["c1_idx_y"])  # torch restatement
+    assert rel_err(cham, g["c1_cham"]) < TOL
+    # distances are bit-exact against the FMA-order oracle
+    d, i = ptk_b200.ops.knn1(torch.from_numpy(g["c1_x"]).cuda(), torch.from_numpy(g["c1_y"]).cuda())
+    od, oi = oracle.knn1(g["c1_x"], g["c1_y"], use_fma=True)
+    assert np.array_equal(d.cpu().numpy(), od) and np.array_equal(i.cpu().numpy(), oi)
+
+
+def test_ties_golden(golden):
+    g = golden("chamfer")
+    cham, ix, iy = run(g["tie_x"], g["tie_y"])
+    assert np.array_equal(ix, g["tie_idx_x"]) and np.array_equal(iy, g["tie_idx_y"])
+    assert rel_err(cham, g["tie_cham"]) < TOL
+
+
+def test_unequal_sizes_gradients_golden(golden):
+    g = golden("chamfer")
+    cham, ix, iy, gx, gy = run(g["ne_x"], g["ne_y"], g["ne_gcham"])
+    assert rel_err(cham, g["ne_cham"]) < TOL
+    assert rel_err(gx, g["ne_gx"]) < TOL and rel_err(gy, g["ne_gy"]) < TOL
+
+
+@pytest.mark.parametrize("B,P1,P2", [(1, 1, 1), (1, 1, 37), (2, 255, 257), (3, 2048, 2049), (1, 4097, 1000),
+                                     (5, 1000, 4000), (64, 16, 16), (1, 10000, 6400), (2, 30000, 512)])
+def test_random_vs_oracle(oracle, B, P1, P2):
+    rng = np.random.default_rng(B * 100003 + P1 * 17 + P2)
+    x = (rng.random((B, P1, 3), np.float32) - 0.5).astype(np.float32)
+    y = (rng.random((B, P2, 3), np.float32) - 0.5).astype(np.float32)
+    gc = rng.random(B).astype(np.float32)
+    cham, ix, iy, gx, gy = run(x, y, gc)
+    ocham, odx, oix, ody, oiy = oracle.chamfer_fwd(x, y, use_fma=True)
+    assert np.array_equal(ix, oix) and np.array_equal(iy, oiy)
+    assert rel_err(cham, ocham) < TOL
+    ogx, ogy = oracle.chamfer_bwd(x, y, oix, oiy, gc)
+    assert rel_err(gx, ogx) < TOL and rel_err(gy, ogy) < TOL
+
+
+def test_duplicate_points_and_grid_ties(oracle):
+    # integer lattice: masses of exact ties; lowest index must win everywhere
+    rng = np.random.default_rng(7)
+    x = rng.integers(0, 4, (2, 3000, 3)).astype(np.float32)
+    y = rng.integers(0, 4, (2, 2500, 3)).astype(np.float32)
+    cham, ix, iy = run(x, y)
+    ocham, _, oix, _, oiy = oracle.chamfer_fwd(x, y, use_fma=True)
+    assert np.array_equal(ix, oix) and np.array_equal(iy, oiy)
+    assert rel_err(cham, ocham) < TOL
+
+
+def test_only_y_needs_grad(oracle):
+    # autoencoder case (reconstruction/autoencoder/train.py:145-151): sampled cloud detached
+    rng = np.random.default_rng(3)
+    x = rng.random((2, 500, 3), np.float32)
+    y = rng.random((2, 640, 3), np.float32)
+    xt = torch.from_numpy(x).cuda()
+    yt = torch.from_numpy(y).cuda().requires_grad_(True)
+    cham, ix, iy = ptk_b200.ops.chamfer(xt, yt)
+    cham.sum().backward()
+    _, ogy = oracle.chamfer_bwd(x, y, ix.cpu().numpy(), iy.cpu().numpy(), np.ones(2, np.float32), want_x=False)
+    assert rel_err(yt.grad.cpu().numpy(), ogy) < TOL
+
+
+def test_full_size_properties():
+    """BASELINE size (10k x 10k, batch 256): properties that need no oracle run."""
+    B, P = 256, 10000
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand(B, P, 3, device="cuda", generator=g) - 0.5
+    y = torch.rand(B, P, 3, device="cuda", generator=g) - 0.5
+    cham, ix, iy = ptk_b200.ops.chamfer(x, y)
+    # (1) the reported index reproduces the reported distance: cham == mean |x - y[idx]|^2 + ...
+    ar = torch.arange(B, device="cuda")[:, None]
+    dx = ((x - y[ar, ix.long()]) ** 2).sum(-1).mean(1)
+    dy = ((y - x[ar, iy.long()]) ** 2).sum(-1).mean(1)
+    assert torch.allclose(cham, dx + dy, rtol=1e-5)
+    # (2) symmetry: swapping the clouds swaps the index sets and keeps the value
+    cham2, jx, jy = ptk_b200.ops.chamfer(y, x)
+    assert torch.equal(jx, iy) and torch.equal(jy, ix) and torch.allclose(cham, cham2, rtol=1e-6)
+    # (3) identity: chamfer(x, x) == 0 with idx == arange
+    cham0, kx, _ = ptk_b200.ops.chamfer(x[:8], x[:8])
+    assert float(cham0.abs().max()) == 0.0
+    assert torch.equal(kx, torch.arange(P, device="cuda", dtype=torch.int32).expand(8, P))
+    # (4) batch independence: a slice of the batch gives bit-identical results
+    c_s, ix_s, _ = ptk_b200.ops.chamfer(x[100:103].contiguous(), y[100:103].contiguous())
+    assert torch.equal(ix_s, ix[100:103]) and torch.equal(c_s, cham[100:103])
+    # (5) optimality spot check against a torch brute force on a few query points
+    q = x[5, :64]
+    d = ((q[:, None, :] - y[5][None]) ** 2).sum(-1)
+    assert torch.equal(d.argmin(1).int(), ix[5, :64])
+
+
+def test_errors():
+    with pytest.raises(ValueError):
+        ptk_b200.ops.chamfer(torch.rand(2, 10, 2).cuda(), torch.rand(2, 10, 3).cuda())
+    with pytest.raises(ValueError):
+        ptk_b200.ops.chamfer(torch.rand(2, 10, 3).cuda(), torch.rand(3, 10, 3).cuda())
+    with pytest.raises(ValueError):
+        ptk_b200.ops.chamfer(torch.rand(2, 0, 3).cuda(), torch.rand(2, 10, 3).cuda())
+
+
+def test_pytorch3d_shim_call_shape(golden):
+    ptk_b200.install_pytorch3d_shim()
+    from pytorch3d.loss import chamfer_distance as cuda_cd
+    from pytorch3d.ops import knn_points
+    g = golden("chamfer")
+    x, y = torch.from_numpy(g["ne_x"]).cuda(), torch.from_numpy(g["ne_y"]).cuda()
+    cd, none = cuda_cd(x, y, batch_reduction=None)  # utils.py:207 unpacks a tuple
+    assert none is None and cd.shape == (3,)
+    assert rel_err(cd.cpu().numpy(), g["ne_cham"]) < TOL
+    k = knn_points(x, y, K=1)
+    assert k.dists.shape == (3, 700, 1) and k.idx.dtype == torch.int64

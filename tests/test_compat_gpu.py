@@ -1,0 +1,96 @@
+"""GPU tests of the reference-signature layer (utils.chamfer_distance etc.) and the host-buffer ABI."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import ptk_b200
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def test_mesh_chamfer_golden(golden):
+    """utils.chamfer_distance(verts, faces, gt, num, repeat=3) vs the reference's own function."""
+    g = golden("sampler")
+    verts = torch.from_numpy(g["meshcd_verts"]).cuda().requires_grad_(True)
+    faces = torch.from_numpy(g["meshcd_faces"].astype(np.int64)).cuda()
+    gt = torch.from_numpy(g["meshcd_gt"]).cuda()
+    uni = [(torch.from_numpy(g[f"meshcd_u_face{r}"]).cuda(), torch.from_numpy(g[f"meshcd_uv{r}"]).cuda())
+           for r in range(3)]
+    cd = ptk_b200.utils.chamfer_distance(verts, faces, gt, num=1500, repeat=3, uniforms=uni)
+    assert cd.shape == (2,)
+    assert rel_err(cd.detach().cpu().numpy(), g["meshcd_cd"]) < TOL
+    cd.sum().backward()
+    assert rel_err(verts.grad.cpu().numpy(), g["meshcd_gverts"]) < TOL
+
+
+def test_host_abi_mesh_chamfer_golden(golden):
+    g = golden("sampler")
+    ctx = ptk_b200.host.HostContext(0)
+    u_face = np.stack([g[f"meshcd_u_face{r}"] for r in range(3)])
+    uv = np.stack([g[f"meshcd_uv{r}"] for r in range(3)])
+    cd, gv = ctx.mesh_chamfer(g["meshcd_verts"], g["meshcd_faces"], g["meshcd_gt"], u_face, uv,
+                              grad_cd=np.ones(2, np.float32))
+    assert rel_err(cd, g["meshcd_cd"]) < TOL and rel_err(gv, g["meshcd_gverts"]) < TOL
+    ctx.close()
+
+
+def test_host_abi_chamfer(golden, oracle):
+    g = golden("chamfer")
+    ctx = ptk_b200.host.HostContext(0)
+    out = ctx.chamfer(g["ne_x"], g["ne_y"], grad_cham=g["ne_gcham"], want_idx=True)
+    ocham, _, oix, _, oiy = oracle.chamfer_fwd(g["ne_x"], g["ne_y"], use_fma=True)
+    assert np.array_equal(out["idx_x"], oix) and np.array_equal(out["idx_y"], oiy)
+    assert rel_err(out["cham"], g["ne_cham"]) < TOL
+    assert rel_err(out["grad_x"], g["ne_gx"]) < TOL and rel_err(out["grad_y"], g["ne_gy"]) < TOL
+    with pytest.raises(ValueError):
+        ctx.chamfer(np.zeros((1, 0, 3), np.float32), np.zeros((1, 4, 3), np.float32))
+    ctx.close()
+
+
+def test_adj_init_on_gpu_and_deformation_like_step(golden, objects_dir):
+    """load_mesh_vision -> adj_init -> GCN -> vertex update -> chamfer loss -> backward: the
+    sequence of vision/train.py:120-157 with the CNN encoders replaced by random features."""
+    args = types.SimpleNamespace(use_touch=True, finger=True, num_grasps=5, num_GCN_layers=3, hidden_GCN_size=60,
+                                 cut=0.33)
+    adj_info, verts = ptk_b200.utils.load_mesh_vision(args, objects_dir + "/vision_charts.obj")
+    assert adj_info["adj"].shape == (1949, 1949) and adj_info["faces"].shape == (2464, 3)
+    torch.manual_seed(0)
+    net = ptk_b200.GCN(50, args).cuda()
+    B = 2
+    touch = torch.rand(B, 125, 3, device="cuda") * 0.1
+    feats = torch.rand(B, 1949, 50, device="cuda")
+    vertices = torch.cat([verts[None].repeat(B, 1, 1), touch], dim=1)
+    update = net(feats, adj_info)
+    vertices = torch.cat([vertices[:, :1824] + update[:, :1824], vertices[:, 1824:]], dim=1)
+    gt = torch.rand(B, 3000, 3, device="cuda") * 0.4 - 0.2
+    loss = 9000 * ptk_b200.utils.chamfer_distance(vertices, adj_info["faces"], gt, num=3000).mean()
+    loss.backward()
+    assert torch.isfinite(loss)
+    for layer in net.layers:
+        assert torch.isfinite(layer.weight.grad).all() and float(layer.weight.grad.abs().max()) > 0
+
+
+def test_cuda_graph_capture_of_forward():
+    """Every ABI call is capture-safe (no sync, no allocation inside the library)."""
+    x = torch.rand(4, 2000, 3, device="cuda")
+    y = torch.rand(4, 1500, 3, device="cuda")
+    ref, rix, _ = ptk_b200.ops.chamfer(x, y)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        ptk_b200.ops.chamfer(x, y)  # warm-up on the side stream
+        with torch.cuda.graph(g, stream=s):
+            cham, ix, iy = ptk_b200.ops.chamfer(x, y)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(cham, ref) and torch.equal(ix, rix)

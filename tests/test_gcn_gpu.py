@@ -1,0 +1,135 @@
+"""GPU parity of the GCN kernels against the reference's own GCN outputs/gradients (golden) and the
+CPU oracle.  Bar: 1e-5 relative, FP32, norm-wise (max-abs error over max-abs reference)."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+import ptk_b200
+from ptk_b200.graph import Graph
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
+
+
+def build_net(g, name, device="cuda"):
+    cin, hid, nl, B, N, ignore = [int(v) for v in g[name + "_meta"]]
+    args = types.SimpleNamespace(num_GCN_layers=nl, hidden_GCN_size=hid, cut=float(g[name + "_cut"][0]))
+    net = ptk_b200.GCN(cin, args, ignore_touch_matrix=bool(ignore))
+    sd = {}
+    for i in range(nl):
+        sd[f"layers.{i}.weight"] = torch.from_numpy(g[f"{name}_w{i}"])
+        sd[f"layers.{i}.bias"] = torch.from_numpy(g[f"{name}_b{i}"])
+    net.load_state_dict(sd)  # reference state-dict keys/shapes load unchanged
+    return net.to(device), nl
+
+
+@pytest.mark.parametrize("name,tag", [("p_small", "p"), ("g_small", "g"), ("v_orig", "p")])
+def test_gcn_vs_reference_module_golden(golden, name, tag):
+    g, adj = golden("gcn"), golden("adjacency")
+    net, nl = build_net(g, name)
+    info = {k: Graph.from_csr(adj[f"{tag}_{k}_rowptr"], adj[f"{tag}_{k}_col"], "cuda").dense() for k in ("origional", "adj")}
+    x = torch.from_numpy(g[name + "_x"]).cuda().requires_grad_(True)
+    y = net(x, info)
+    assert rel_err(y.detach().cpu().numpy(), g[name + "_y"]) < TOL
+    (y * torch.from_numpy(g[name + "_gout"]).cuda()).sum().backward()
+    assert rel_err(x.grad.cpu().numpy(), g[name + "_gx"]) < TOL
+    for i, layer in enumerate(net.layers):
+        assert rel_err(layer.weight.grad.cpu().numpy(), g[f"{name}_gw{i}"]) < TOL, i
+        assert rel_err(layer.bias.grad.cpu().numpy(), g[f"{name}_gb{i}"]) < TOL, i
+    # bias beyond the propagated slice receives exactly zero gradient (vision/model.py:358)
+    L = net.layers[0].propagated()
+    assert float(net.layers[0].bias.grad[L:].abs().max()) == 0.0
+
+
+def test_default_20x300_vs_reference_module_golden(golden):
+    """Full default GCN (20 layers x 300, N=1949 with hub rows), weights regenerated from the seed."""
+    g, adj = golden("gcn"), golden("adjacency")
+    torch.manual_seed(1234)
+    args = types.SimpleNamespace(num_GCN_layers=20, hidden_GCN_size=300, cut=0.33)
+    net = ptk_b200.GCN(50, args)
+    x = torch.rand(1, 1949, 50)
+    net = net.cuda()
+    x = x.cuda().requires_grad_(True)
+    info = {"adj": Graph.from_csr(adj["p_adj_rowptr"], adj["p_adj_col"], "cuda").dense()}
+    y = net(x, info)
+    assert rel_err(y.detach().cpu().numpy(), g["p_default_y"]) < TOL
+    gout = torch.rand(1, 1949, 3, generator=torch.Generator().manual_seed(7)).cuda()
+    (y * gout).sum().backward()
+    assert rel_err(x.grad.cpu().numpy()[:, ::16], g["p_default_gx"]) < TOL
+    assert rel_err(net.layers[0].weight.grad.cpu().numpy(), g["p_default_gw0"]) < TOL
+    assert rel_err(net.layers[0].bias.grad.cpu().numpy(), g["p_default_gb0"]) < TOL
+    assert rel_err(net.layers[19].weight.grad.cpu().numpy(), g["p_default_gw19"]) < TOL
+
+
+@pytest.mark.parametrize("C,L,relu", [(300, 99, True), (300, 300, False), (100, 33, True), (3, 3, False),
+                                       (50, 50, False), (7, 2, True), (64, 0, True)])
+def test_aggregate_vs_oracle(oracle, golden, C, L, relu):
+    adj = golden("adjacency")
+    rp, col = adj["g_adj_rowptr"], adj["g_adj_col"]
+    gr = Graph.from_csr(rp, col, "cuda")
+    rng = np.random.default_rng(C * 31 + L)
+    H = rng.standard_normal((2, gr.n, C)).astype(np.float32)
+    bias = rng.standard_normal(C).astype(np.float32)
+    out = ptk_b200.ops._aggregate(gr, torch.from_numpy(H).cuda(), L, torch.from_numpy(bias).cuda(), relu)
+    want = oracle.gcn_aggregate_fwd(rp, col, H, L, bias, relu)
+    assert rel_err(out.cpu().numpy(), want) < TOL
+    # transpose gather (backward) vs oracle
+    gH = ptk_b200.ops._aggregate(gr, torch.from_numpy(H).cuda(), L, None, False, transpose=True)
+    want_g, want_b = oracle.gcn_aggregate_bwd(rp, col, H, L)
+    assert rel_err(gH.cpu().numpy(), want_g) < TOL
+    gb = ptk_b200.ops._bias_grad(torch.from_numpy(H).cuda().reshape(-1, C), L)
+    assert rel_err(gb.cpu().numpy(), want_b) < 2e-5 or L == 0
+
+
+@pytest.mark.parametrize("M,K,N", [(1, 1, 1), (129, 17, 5), (1949, 50, 300), (3898, 300, 300), (1000, 448, 300),
+                                   (2324, 300, 3), (257, 63, 130)])
+def test_linear_vs_oracle(oracle, M, K, N):
+    rng = np.random.default_rng(M + K + N)
+    X = rng.standard_normal((M, K)).astype(np.float32)
+    W = (rng.standard_normal((K, N)) * 0.1).astype(np.float32)
+    G = rng.standard_normal((M, N)).astype(np.float32)
+    Xc, Wc, Gc = (torch.from_numpy(a).cuda() for a in (X, W, G))
+    H = ptk_b200.ops._linear_fwd(Xc, Wc)
+    assert rel_err(H.cpu().numpy(), oracle.gcn_linear(X, W)) < TOL
+    gX = ptk_b200.ops._linear_dgrad(Gc, Wc, None)
+    assert rel_err(gX.cpu().numpy(), G.astype(np.float64) @ W.astype(np.float64).T) < TOL
+    gXm = ptk_b200.ops._linear_dgrad(Gc, Wc, Xc)
+    assert rel_err(gXm.cpu().numpy(), (G.astype(np.float64) @ W.astype(np.float64).T) * (X > 0)) < TOL
+    gW = ptk_b200.ops._linear_wgrad(Xc, Gc)
+    assert rel_err(gW.cpu().numpy(), X.astype(np.float64).T @ G.astype(np.float64)) < TOL
+
+
+def test_layer_signature_with_lambda_activation(golden, oracle):
+    """GCN_layer.forward(features, adj, activation) with a non-ReLU callable (vision/model.py:324)."""
+    adj = golden("adjacency")
+    gr = Graph.from_csr(adj["v_adj_rowptr"], adj["v_adj_col"], "cuda")
+    dense = gr.dense()
+    torch.manual_seed(0)
+    layer = ptk_b200.GCN_layer(20, 30, cut=0.33, do_cut=True).cuda()
+    x = torch.rand(2, gr.n, 20, device="cuda")
+    y = layer(x, dense, lambda t: t * 2.0)
+    want = oracle.gcn_layer_fwd(x.cpu().numpy(), layer.weight.detach().cpu().numpy(), layer.bias.detach().cpu().numpy(),
+                                adj["v_adj_rowptr"], adj["v_adj_col"], 0.33, True, False) * 2.0
+    assert rel_err(y.detach().cpu().numpy(), want) < TOL
+    y2 = layer(x, dense, torch.nn.functional.relu)
+    assert float(y2.min()) >= 0.0
+
+
+def test_gcn_batch_independence(golden):
+    adj = golden("adjacency")
+    info = {"adj": Graph.from_csr(adj["p_adj_rowptr"], adj["p_adj_col"], "cuda").dense()}
+    torch.manual_seed(2)
+    args = types.SimpleNamespace(num_GCN_layers=4, hidden_GCN_size=100, cut=0.33)
+    net = ptk_b200.GCN(50, args).cuda()
+    x = torch.rand(6, 1949, 50, device="cuda")
+    with torch.no_grad():
+        y = net(x, info)
+        y2 = net(x[2:4].contiguous(), info)
+    assert torch.equal(y[2:4], y2)
