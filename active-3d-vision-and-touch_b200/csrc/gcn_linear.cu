@@ -128,6 +128,12 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ part, int nsplit,
     out[e] = acc;
 }
 
+// tensor-core path (gemm_tf32x3.cu)
+bool tf32x3_eligible(const void *A, const void *D, int64_t M, int64_t K, int64_t N);
+size_t tf32x3_workspace_bytes(int64_t K, int64_t N);
+int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act, int64_t M, int64_t K, int64_t N,
+                float *D, void *workspace, size_t workspace_bytes, cudaStream_t st);
+
 }  // namespace ptk
 
 using namespace ptk;
@@ -140,10 +146,22 @@ static int check_gemm(const void *a, const void *b, const void *c, int64_t M, in
     return PTK_OK;
 }
 
+extern "C" size_t ptk_gcn_linear_workspace_bytes(int64_t M, int64_t K, int64_t N) {
+    (void)M;
+    if (K <= 0 || N <= 0) return 0;
+    return tf32x3_workspace_bytes(K, N);
+}
+
 extern "C" int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int64_t K, int64_t N,
-                                  float *H, ptk_stream_t stream) {
+                                  float *H, int algo, void *workspace, size_t workspace_bytes,
+                                  ptk_stream_t stream) {
     int rc = check_gemm(X, W, H, M, K, N);
     if (rc) return rc;
+    PTK_REQUIRE(algo >= 0 && algo <= 2, PTK_ERR_SHAPE, "gcn_linear_fwd: algo must be 0, 1 or 2");
+    const int g_fwd_mode = algo;
+    if (g_fwd_mode != 1 && tf32x3_eligible(X, H, M, K, N))
+        return gemm_tf32x3(X, W, /*b_is_kn=*/1, nullptr, M, K, N, H, workspace, workspace_bytes, as_stream(stream));
+    PTK_REQUIRE(g_fwd_mode != 2, PTK_ERR_SHAPE, "gcn_linear_fwd: shape not eligible for the tensor-core path");
     dim3 grid((unsigned)ceil_div(N, GL_BN), (unsigned)ceil_div(M, GL_BM));
     sgemm_kernel<true, false, false, false><<<grid, GL_THREADS, 0, as_stream(stream)>>>(
         X, K, W, N, H, N, M, N, K, 0, nullptr);
@@ -152,9 +170,16 @@ extern "C" int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int
 }
 
 extern "C" int ptk_gcn_linear_dgrad(const float *gH, const float *W, const float *act, int64_t M,
-                                    int64_t K, int64_t N, float *gX, ptk_stream_t stream) {
+                                    int64_t K, int64_t N, float *gX, int algo, void *workspace,
+                                    size_t workspace_bytes, ptk_stream_t stream) {
     int rc = check_gemm(gH, W, gX, M, K, N);
     if (rc) return rc;
+    PTK_REQUIRE(algo >= 0 && algo <= 2, PTK_ERR_SHAPE, "gcn_linear_dgrad: algo must be 0, 1 or 2");
+    const int g_dgrad_mode = algo;
+    // gX (M x K) = gH (M x N) . W^T : reduction over N; W as stored (K x N) is the "N' x K'" operand
+    if (g_dgrad_mode != 1 && tf32x3_eligible(gH, gX, M, N, K) && (!act || ((uintptr_t)act % 16) == 0))
+        return gemm_tf32x3(gH, W, /*b_is_kn=*/0, act, M, N, K, gX, workspace, workspace_bytes, as_stream(stream));
+    PTK_REQUIRE(g_dgrad_mode != 2, PTK_ERR_SHAPE, "gcn_linear_dgrad: shape not eligible for the tensor-core path");
     // gX (M x K) = gH (M x N) . W^T : GEMM with m=M, n=K, k=N; B[k=n_out][n=k_in] = W[k_in*N + n_out]
     dim3 grid((unsigned)ceil_div(K, GL_BN), (unsigned)ceil_div(M, GL_BM));
     if (act)

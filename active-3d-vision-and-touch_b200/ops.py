@@ -157,19 +157,35 @@ def face_areas_normals(verts_packed, faces_i64):
 
 
 # ------------------------------------------------------------------------------------- GCN primitives
-def _linear_fwd(X2, W2, out=None):
+# GEMM algorithm selection (include/ptk.h: PTK_GEMM_*).  The TRAINING forward uses the exact-FP32 FFMA
+# kernel: its k-sequential FMA accumulation reproduces a scalar FP32 GEMM almost bit for bit, which keeps
+# the ReLU masks of a deep GCN identical to the reference's (a 1e-6 perturbation flips individual ReLUs and
+# moves 20-layer gradients by 1e-3 -- measured).  Inference forwards and the backward GEMMs,
+# whose errors enter the result smoothly, may use the 3xTF32 tensor-core kernel.
+GEMM_AUTO, GEMM_FFMA, GEMM_TF32X3 = 0, 1, 2
+algo = {"fwd_train": GEMM_FFMA, "fwd_infer": GEMM_AUTO, "dgrad": GEMM_FFMA}
+
+
+def _linear_fwd(X2, W2, out=None, algo_id=GEMM_FFMA):
     M, K = X2.shape
     N = W2.shape[1]
     H = out if out is not None else torch.empty(M, N, dtype=torch.float32, device=X2.device)
-    _lib.check(_lib.lib().ptk_gcn_linear_fwd(_p(X2), _p(W2), M, K, N, _p(H), _stream()), "ptk_gcn_linear_fwd")
+    L = _lib.lib()
+    ws = _ws(L.ptk_gcn_linear_workspace_bytes(M, K, N), X2.device)
+    _lib.check(L.ptk_gcn_linear_fwd(_p(X2), _p(W2), M, K, N, _p(H), algo_id, _p(ws), ws.numel(), _stream()),
+               "ptk_gcn_linear_fwd")
     return H
 
 
-def _linear_dgrad(gH2, W2, act2):
+def _linear_dgrad(gH2, W2, act2, algo_id=None):
+    algo_id = algo["dgrad"] if algo_id is None else algo_id
     M, N = gH2.shape
     K = W2.shape[0]
     gX = torch.empty(M, K, dtype=torch.float32, device=gH2.device)
-    _lib.check(_lib.lib().ptk_gcn_linear_dgrad(_p(gH2), _p(W2), _p(act2), M, K, N, _p(gX), _stream()),
+    L = _lib.lib()
+    ws = _ws(L.ptk_gcn_linear_workspace_bytes(M, K, N), gH2.device)
+    _lib.check(L.ptk_gcn_linear_dgrad(_p(gH2), _p(W2), _p(act2), M, K, N, _p(gX), algo_id, _p(ws), ws.numel(),
+                                      _stream()),
                "ptk_gcn_linear_dgrad")
     return gX
 
@@ -224,7 +240,9 @@ class _GCNLayer(torch.autograd.Function):
         B, Nv, K = X.shape
         W2 = W.reshape(K, -1)
         with torch.cuda.device(X.device):
-            H = _linear_fwd(X.reshape(B * Nv, K), W2).reshape(B, Nv, -1)
+            train = any(ctx.needs_input_grad[:3])
+            H = _linear_fwd(X.reshape(B * Nv, K), W2,
+                            algo_id=algo["fwd_train"] if train else algo["fwd_infer"]).reshape(B, Nv, -1)
             out = _aggregate(graph, H, Lc, bias, relu)
         ctx.save_for_backward(X, W2, out if relu else None)
         ctx.graph, ctx.Lc, ctx.relu, ctx.wshape = graph, Lc, relu, W.shape
@@ -263,6 +281,8 @@ class _GCNStack(torch.autograd.Function):
         X = _f32c(X)
         B, Nv, _ = X.shape
         acts = [X]
+        train = any(ctx.needs_input_grad)
+        fwd_algo = algo["fwd_train"] if train else algo["fwd_infer"]
         with torch.cuda.device(X.device):
             Hbuf = {}
             for l in range(n):
@@ -272,7 +292,7 @@ class _GCNStack(torch.autograd.Function):
                 H = Hbuf.get(N)
                 if H is None:
                     H = Hbuf[N] = torch.empty(B * Nv, N, dtype=torch.float32, device=X.device)
-                _linear_fwd(acts[-1].reshape(B * Nv, K), W2, out=H)
+                _linear_fwd(acts[-1].reshape(B * Nv, K), W2, out=H, algo_id=fwd_algo)
                 acts.append(_aggregate(graph, H.reshape(B, Nv, N), Ls[l], _f32c(bs[l]), relus[l]))
         ctx.save_for_backward(*acts, *[_f32c(w) for w in Ws])
         ctx.graph, ctx.Ls, ctx.relus, ctx.n = graph, Ls, relus, n

@@ -130,13 +130,23 @@ int ptk_relu_mask(const float *g, const float *act, int64_t n, float *out, ptk_s
  *   fwd   : H (M,N)  = X (M,K) . W (K,N)
  *   dgrad : gX (M,K) = gH (M,N) . W^T, optionally masked by (act[m,k] > 0) -- the ReLU of the
  *           previous layer (vision/model.py:324) fused into the epilogue; act may be NULL.
+ * Where the layer is a true GEMM (reduction >= 32, >= 16 output columns, 16-byte aligned rows) fwd and
+ * dgrad run on the tcgen05 tensor cores with the error-compensated 3xTF32 scheme (FP32-level accuracy,
+ * csrc/gemm_tf32x3.cu); otherwise on exact-FP32 FFMA kernels (csrc/gcn_linear.cu).
  *   wgrad : gW (K,N) = X^T . gH  (overwrites gW; the sum over the M rows is split across CTAs and
  *           reduced in a fixed order through the workspace => deterministic)
  * ---------------------------------------------------------------------------------------------- */
-int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int64_t K, int64_t N, float *H,
-                       ptk_stream_t stream);
+size_t ptk_gcn_linear_workspace_bytes(int64_t M, int64_t K, int64_t N); /* fwd and dgrad */
+/* algo: PTK_GEMM_AUTO (tensor cores where eligible), PTK_GEMM_FFMA (exact-FP32 FFMA, k-sequential
+ * accumulation like a scalar FP32 loop) or PTK_GEMM_TF32X3 (error if the shape is not eligible). */
+#define PTK_GEMM_AUTO 0
+#define PTK_GEMM_FFMA 1
+#define PTK_GEMM_TF32X3 2
+int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int64_t K, int64_t N, float *H, int algo,
+                       void *workspace, size_t workspace_bytes, ptk_stream_t stream);
 int ptk_gcn_linear_dgrad(const float *gH, const float *W, const float *act, int64_t M, int64_t K,
-                         int64_t N, float *gX, ptk_stream_t stream);
+                         int64_t N, float *gX, int algo, void *workspace, size_t workspace_bytes,
+                         ptk_stream_t stream);
 size_t ptk_gcn_linear_wgrad_workspace_bytes(int64_t M, int64_t K, int64_t N);
 int ptk_gcn_linear_wgrad(const float *X, const float *gH, int64_t M, int64_t K, int64_t N, float *gW,
                          void *workspace, size_t workspace_bytes, ptk_stream_t stream);
