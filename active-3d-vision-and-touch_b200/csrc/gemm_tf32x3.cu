@@ -6,33 +6,43 @@
 // error-compensated 3xTF32 scheme:
 //       a = a_hi + a_lo,  a_hi = tf32_rna(a),  a_lo = tf32_rna(a - a_hi)     (same for b)
 //       D = a_hi*b_lo + a_lo*b_hi + a_hi*b_hi        (a_lo*b_lo ~ 2^-22 relative is dropped)
-// with FP32 accumulation in tensor memory -- ~22+ mantissa bits per product, i.e. the error level of
-// an FP32 FMA chain of the same length, at 1/3 of the TF32 tensor rate instead of the FP32 SIMT rate.
+// CHUNKED ACCUMULATION.  The tensor core adds into its FP32 accumulator with truncation: measured here,
+// one accumulator carried over the whole reduction gives an error that grows LINEARLY with K (2.4e-6 at
+// K=300, 4x a scalar FP32 loop) and, being biased, linearly with network depth (3.6e-5 on the input
+// gradient of the 20-layer GCN).  So each TMEM accumulator only integrates ONE 32-wide k-block (the 8
+// small correction products first, then the 4 hi*hi products); a dedicated group of warps drains it
+// (tcgen05.ld) and adds it into FP32 registers with round-to-nearest while the tensor core fills the
+// next TMEM buffer.  Result: error at the level of a scalar FP32 loop, unbiased.
 //
 //   D (M x N) = A (M x K, row-major: K contiguous)  .  B^T   with B stored (N x K), K contiguous
 //     fwd   : A = X,  B = W^T (pre-transposed + pre-split, tiny)          D = H
 //     dgrad : A = gH, B = W   (as stored: (K_in x N_out) is "N x K")      D = gX  [* (act > 0)]
 //
-// One CTA = one 128-row tile x up to 320 columns (two UMMA N-parts), 192 threads:
-//   warp 0      TMA producer: raw FP32 A tile (128 x 32) + pre-split B_hi/B_lo tiles per k-block,
-//               SWIZZLE_128B, mbarrier expect_tx
-//   warp 1      MMA issuer (one elected lane): 3 x tcgen05.mma.kind::tf32 per 8-wide k-step and N-part,
-//               accumulators in TMEM; tcgen05.commit releases the smem stage / signals the epilogue
-//   warps 2-5   converter: split the raw A tile in place into a_hi (overwrites raw) and a_lo
-//               (elementwise, position preserving => swizzle-agnostic), fence.proxy.async, arrive;
-//               after the main loop the same four warps are the epilogue: tcgen05.ld 32x32b,
-//               optional ReLU-mask, 64-byte vector stores.
+// One CTA = one 128 x 160 output tile, 512 threads, 3-stage smem ring, 3 TMEM accumulator buffers:
+//   warp 0       TMA producer: raw FP32 A tile (128 x 32) + pre-split B_hi/B_lo tiles (160 x 32) per
+//                k-block, SWIZZLE_128B, mbarrier expect_tx
+//   warp 1       MMA issuer (one elected lane): 12 x tcgen05.mma.kind::tf32 (M128 N160 K8) per k-block;
+//                tcgen05.commit releases the smem stage and publishes the TMEM buffer
+//   warps 4-7    converter: split the raw A tile in place into a_hi (overwrites raw) and a_lo
+//                (elementwise, position preserving => swizzle-agnostic), fence.proxy.async, arrive
+//   warps 8-15   drain + epilogue: per k-block tcgen05.ld the finished buffer, acc += chunk (RN);
+//                at the end optional ReLU mask and 128-bit stores (thread = one row x 80 columns)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "ptk_common.cuh"
 
 namespace ptk {
 
 constexpr int TG_BM = 128;        // rows per CTA (UMMA M, cta_group::1)
+constexpr int TG_BN = 160;        // columns per CTA (UMMA N)
 constexpr int TG_BK = 32;         // fp32 elements per k-block = 128 B = one SWIZZLE_128B atom row
-constexpr int TG_STAGES = 2;
-constexpr int TG_THREADS = 192;
-constexpr int TG_MAX_BN = 320;    // columns per CTA (<= 2 UMMA parts of <= 256, TMEM has 512 columns)
+constexpr int TG_STAGES = 3;      // smem ring: 3 x 72 KB
+constexpr int TG_NBUF = 3;        // TMEM accumulator buffers: 3 x 160 columns
+constexpr int TG_THREADS = 512;
+constexpr int TG_A_BYTES = TG_BM * TG_BK * 4;   // 16 KB
+constexpr int TG_B_BYTES = TG_BN * TG_BK * 4;   // 20 KB
+constexpr int TG_STAGE_BYTES = 2 * TG_A_BYTES + 2 * TG_B_BYTES;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -98,50 +108,47 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
 
 struct TGParams {
     int M, N, K;          // D is M x N, reduction K
-    int n0_cols, n1_cols; // UMMA N of part 0 / part 1 (multiples of 16, n1 may be 0); per-CTA BN = n0 + n1
     float *D;
     const float *act;     // optional ReLU mask source, same shape as D
+    int dbg;              // development switches (PTK_TG_DEBUG): 1 = skip A split, 2 = skip drain loads, 4 = skip MMAs
 };
 
 template <bool MASK>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
-                   const __grid_constant__ CUtensorMap map_blo, const __grid_constant__ CUtensorMap map_bhi1,
-                   const __grid_constant__ CUtensorMap map_blo1, const TGParams p) {
+                   const __grid_constant__ CUtensorMap map_blo, const TGParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: per stage [A_hi(raw) 16 KB][A_lo 16 KB][B_hi bn*128][B_lo bn*128]; 1024-B aligned pieces
-    const int bn = p.n0_cols + p.n1_cols;
-    const uint32_t a_bytes = TG_BM * TG_BK * 4;            // 16384
-    const uint32_t b_bytes = (uint32_t)bn * TG_BK * 4;     // bn * 128 (bn multiple of 16 -> multiple of 2048)
-    const uint32_t stage_bytes = 2 * a_bytes + 2 * b_bytes;
+    // per stage: [A_hi (raw) 16 KB][A_lo 16 KB][B_hi 20 KB][B_lo 20 KB], every piece 1024-B aligned
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    __shared__ __align__(8) uint64_t bars[3 * TG_STAGES + 1];
+    __shared__ __align__(8) uint64_t bars[3 * TG_STAGES + 2 * TG_NBUF];
     __shared__ uint32_t tmem_base_slot;
-    const uint32_t bar_full = smem_u32(&bars[0]);               // TMA landed        (count 1 + tx)
-    const uint32_t bar_conv = smem_u32(&bars[TG_STAGES]);       // A split finished  (count 4: one per warp)
-    const uint32_t bar_empty = smem_u32(&bars[2 * TG_STAGES]);  // MMAs done reading (count 1, tcgen05.commit)
-    const uint32_t bar_accum = smem_u32(&bars[3 * TG_STAGES]);  // accumulators complete
+    const uint32_t bar_full = smem_u32(&bars[0]);                  // TMA landed         (1 + tx)
+    const uint32_t bar_conv = smem_u32(&bars[TG_STAGES]);          // A split finished   (4 warps)
+    const uint32_t bar_empty = smem_u32(&bars[2 * TG_STAGES]);     // MMAs done with smem (commit)
+    const uint32_t bar_tfull = smem_u32(&bars[3 * TG_STAGES]);     // TMEM buffer complete (commit)
+    const uint32_t bar_tempty = smem_u32(&bars[3 * TG_STAGES + TG_NBUF]);  // TMEM buffer drained (8 warps)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * TG_BM;
-    const int n_base = blockIdx.y * bn;
+    const int n_base = blockIdx.y * TG_BN;
     const int num_kb = (p.K + TG_BK - 1) / TG_BK;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bhi) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bhi1) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo1) : "memory");
         for (int s = 0; s < TG_STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_conv + 8 * s, 4);
             mbar_init(bar_empty + 8 * s, 1);
         }
-        mbar_init(bar_accum, 1);
+        for (int b = 0; b < TG_NBUF; ++b) {
+            mbar_init(bar_tfull + 8 * b, 1);
+            mbar_init(bar_tempty + 8 * b, 8);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: 512 columns (the whole SM's tensor memory; 1 CTA per SM by shared-memory size)
+    if (warp == 1) {  // TMEM: all 512 columns (1 CTA per SM by shared-memory size)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -157,65 +164,60 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 const int s = kb % TG_STAGES;
                 const uint32_t ph = (kb / TG_STAGES) & 1;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-                const uint32_t sbh = sa + 2 * a_bytes, sbl = sbh + b_bytes;
-                mbar_expect_tx(bar_full + 8 * s, a_bytes + 2 * b_bytes);
+                const uint32_t sa = smem_u32(smem + (size_t)s * TG_STAGE_BYTES);
+                mbar_expect_tx(bar_full + 8 * s, TG_A_BYTES + 2 * TG_B_BYTES);
                 tma_load_2d(sa, &map_a, bar_full + 8 * s, kb * TG_BK, m0);
-                tma_load_2d(sbh, &map_bhi, bar_full + 8 * s, kb * TG_BK, n_base);
-                tma_load_2d(sbl, &map_blo, bar_full + 8 * s, kb * TG_BK, n_base);
-                if (p.n1_cols > 0) {
-                    tma_load_2d(sbh + p.n0_cols * 128, &map_bhi1, bar_full + 8 * s, kb * TG_BK, n_base + p.n0_cols);
-                    tma_load_2d(sbl + p.n0_cols * 128, &map_blo1, bar_full + 8 * s, kb * TG_BK, n_base + p.n0_cols);
-                }
+                tma_load_2d(sa + 2 * TG_A_BYTES, &map_bhi, bar_full + 8 * s, kb * TG_BK, n_base);
+                tma_load_2d(sa + 2 * TG_A_BYTES + TG_B_BYTES, &map_blo, bar_full + 8 * s, kb * TG_BK, n_base);
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        const uint32_t idesc0 = make_idesc_tf32(p.n0_cols);
-        const uint32_t idesc1 = make_idesc_tf32(p.n1_cols > 0 ? p.n1_cols : 16);
+        const uint32_t idesc = make_idesc_tf32(TG_BN);
         for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % TG_STAGES;
-            const uint32_t ph = (kb / TG_STAGES) & 1;
-            mbar_wait(bar_full + 8 * s, ph);   // B tiles (and raw A) landed
-            mbar_wait(bar_conv + 8 * s, ph);   // A split done
+            const int s = kb % TG_STAGES, b = kb % TG_NBUF;
+            mbar_wait(bar_full + 8 * s, (kb / TG_STAGES) & 1);        // B tiles landed
+            mbar_wait(bar_conv + 8 * s, (kb / TG_STAGES) & 1);        // A split done
+            mbar_wait(bar_tempty + 8 * b, ((kb / TG_NBUF) & 1) ^ 1);  // accumulator buffer drained
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
-                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+            if (lane == 0 && !(p.dbg & 4)) {
+                const uint32_t sa = smem_u32(smem + (size_t)s * TG_STAGE_BYTES);
                 const uint64_t d_ahi = make_kmajor_sw128_desc(sa);
-                const uint64_t d_alo = make_kmajor_sw128_desc(sa + a_bytes);
-                const uint64_t d_bhi = make_kmajor_sw128_desc(sa + 2 * a_bytes);
-                const uint64_t d_blo = make_kmajor_sw128_desc(sa + 2 * a_bytes + b_bytes);
+                const uint64_t d_alo = make_kmajor_sw128_desc(sa + TG_A_BYTES);
+                const uint64_t d_bhi = make_kmajor_sw128_desc(sa + 2 * TG_A_BYTES);
+                const uint64_t d_blo = make_kmajor_sw128_desc(sa + 2 * TG_A_BYTES + TG_B_BYTES);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(b * TG_BN);
+                // small correction products first (into a cleared accumulator), then the hi*hi products
 #pragma unroll
                 for (int ks = 0; ks < TG_BK / 8; ++ks) {
                     const uint64_t ko = (uint64_t)(ks * 32 >> 4);  // +32 B per k-step inside the swizzle atom
-                    const uint32_t acc = (kb | ks) != 0;
-                    // part 0
-                    umma_tf32(tmem_base, d_ahi + ko, d_blo + ko, idesc0, acc);
-                    umma_tf32(tmem_base, d_alo + ko, d_bhi + ko, idesc0, 1);
-                    umma_tf32(tmem_base, d_ahi + ko, d_bhi + ko, idesc0, 1);
-                    if (p.n1_cols > 0) {
-                        const uint64_t bo = (uint64_t)((p.n0_cols * 128) >> 4);
-                        umma_tf32(tmem_base + p.n0_cols, d_ahi + ko, d_blo + bo + ko, idesc1, acc);
-                        umma_tf32(tmem_base + p.n0_cols, d_alo + ko, d_bhi + bo + ko, idesc1, 1);
-                        umma_tf32(tmem_base + p.n0_cols, d_ahi + ko, d_bhi + bo + ko, idesc1, 1);
-                    }
+                    umma_tf32(d_tmem, d_ahi + ko, d_blo + ko, idesc, ks != 0);
+                    umma_tf32(d_tmem, d_alo + ko, d_bhi + ko, idesc, 1);
                 }
-                umma_commit(bar_empty + 8 * s);            // stage free once these MMAs have read smem
-                if (kb == num_kb - 1) umma_commit(bar_accum);
+#pragma unroll
+                for (int ks = 0; ks < TG_BK / 8; ++ks) {
+                    const uint64_t ko = (uint64_t)(ks * 32 >> 4);
+                    umma_tf32(d_tmem, d_ahi + ko, d_bhi + ko, idesc, 1);
+                }
+                umma_commit(bar_empty + 8 * s);   // smem stage free once these MMAs have read it
+                umma_commit(bar_tfull + 8 * b);   // accumulator chunk complete
+            } else if (lane == 0) {
+                umma_commit(bar_empty + 8 * s);
+                umma_commit(bar_tfull + 8 * b);
             }
             __syncwarp();
         }
-    } else {
-        // ===================== converter warps (2..5) =====================
-        const int ct = threadIdx.x - 64;  // 0..127
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== converter warps =====================
+        const int ct = threadIdx.x - 128;  // 0..127
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % TG_STAGES;
-            const uint32_t ph = (kb / TG_STAGES) & 1;
-            mbar_wait(bar_full + 8 * s, ph);
-            float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * stage_bytes);
-            float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)s * stage_bytes + a_bytes);
+            mbar_wait(bar_full + 8 * s, (kb / TG_STAGES) & 1);
+            float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * TG_STAGE_BYTES);
+            float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)s * TG_STAGE_BYTES + TG_A_BYTES);
 #pragma unroll
             for (int i = 0; i < (TG_BM * TG_BK / 4) / 128; ++i) {
+                if (p.dbg & 1) break;
                 const int c = ct + i * 128;
                 float4 v = hi[c];
                 uint4 h, l;
@@ -229,46 +231,79 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_conv + 8 * s);
         }
-        // ===================== epilogue (same warps) =====================
-        mbar_wait(bar_accum, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int q = warp & 3;                    // TMEM lane quarter this warp may access
+    } else if (warp >= 8) {
+        // ===================== drain + epilogue warps =====================
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int half = (warp - 8) >> 2;       // column half: [0,80) or [80,160)
         const int row = m0 + q * 32 + lane;
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16);
-        for (int c0 = 0; c0 < bn; c0 += 16) {
-            uint32_t r[16];
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                : "r"(taddr + (uint32_t)c0));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int n = n_base + c0;
-            if (row < p.M && n < p.N) {
-                float *dst = p.D + (size_t)row * p.N + n;
-                if (n + 16 <= p.N && (p.N & 3) == 0) {
+        float acc[80];
 #pragma unroll
-                    for (int v = 0; v < 4; ++v) {
-                        float4 o = make_float4(__uint_as_float(r[4 * v]), __uint_as_float(r[4 * v + 1]),
-                                               __uint_as_float(r[4 * v + 2]), __uint_as_float(r[4 * v + 3]));
-                        if (MASK) {
-                            const float4 a = *reinterpret_cast<const float4 *>(p.act + (size_t)row * p.N + n + 4 * v);
-                            o.x = a.x > 0.f ? o.x : 0.f; o.y = a.y > 0.f ? o.y : 0.f;
-                            o.z = a.z > 0.f ? o.z : 0.f; o.w = a.w > 0.f ? o.w : 0.f;
-                        }
-                        *reinterpret_cast<float4 *>(dst + 4 * v) = o;
-                    }
-                } else {
-                    for (int j = 0; j < 16 && n + j < p.N; ++j) {
-                        float o = __uint_as_float(r[j]);
-                        if (MASK) o = p.act[(size_t)row * p.N + n + j] > 0.f ? o : 0.f;
-                        dst[j] = o;
+        for (int j = 0; j < 80; ++j) acc[j] = 0.f;
+        // ReLU mask of this thread's 80 outputs, fetched while the pipeline fills (bit j: act > 0)
+        uint32_t mbits[3] = {0u, 0u, 0u};
+        if (MASK && row < p.M) {
+            const int nb0 = n_base + half * 80;
+            const float *am = p.act + (size_t)row * p.N + nb0;
+            if ((p.N & 3) == 0) {
+#pragma unroll
+                for (int v = 0; v < 20; ++v) {
+                    if (nb0 + 4 * v + 4 <= p.N) {
+                        const float4 a = __ldg(reinterpret_cast<const float4 *>(am + 4 * v));
+                        const uint32_t m4 = (a.x > 0.f ? 1u : 0u) | (a.y > 0.f ? 2u : 0u) | (a.z > 0.f ? 4u : 0u) |
+                                            (a.w > 0.f ? 8u : 0u);
+                        mbits[(4 * v) >> 5] |= m4 << ((4 * v) & 31);
                     }
                 }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 80; ++j)
+                    if (nb0 + j < p.N && am[j] > 0.f) mbits[j >> 5] |= 1u << (j & 31);
             }
         }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int b = kb % TG_NBUF;
+            mbar_wait(bar_tfull + 8 * b, (kb / TG_NBUF) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * TG_BN + half * 80);
+#pragma unroll
+            for (int c0 = 0; c0 < 80; c0 += 16) {
+                if (p.dbg & 2) break;
+                uint32_t r[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr + (uint32_t)c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+        }
+        // epilogue: this thread owns row `row`, columns n_base + half*80 + [0, 80)
+        const int nb = n_base + half * 80;
+        if (row < p.M) {
+            float *dst = p.D + (size_t)row * p.N + nb;
+            if (MASK) {
+#pragma unroll
+                for (int j = 0; j < 80; ++j) acc[j] = (mbits[j >> 5] >> (j & 31)) & 1u ? acc[j] : 0.f;
+            }
+            if ((p.N & 3) == 0) {
+#pragma unroll
+                for (int v = 0; v < 20; ++v)
+                    if (nb + 4 * v + 4 <= p.N)
+                        *reinterpret_cast<float4 *>(dst + 4 * v) =
+                            make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 80; ++j)
+                    if (nb + j < p.N) dst[j] = acc[j];
+            }
+        }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -325,24 +360,6 @@ static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t c
     return PTK_OK;
 }
 
-// Column tiling: N -> n_tiles CTAs of (n0 + n1) columns, each part a multiple of 16 and <= 256.
-struct NTiling { int n_tiles, n0, n1; };
-static NTiling plan_n(int64_t N) {
-    const int64_t n16 = ceil_div(N, 16) * 16;
-    NTiling t;
-    if (n16 <= 256) { t.n_tiles = 1; t.n0 = (int)n16; t.n1 = 0; return t; }
-    if (n16 <= TG_MAX_BN) {  // two balanced parts in one CTA (A is read and split once)
-        t.n_tiles = 1;
-        t.n0 = (int)(ceil_div(n16 / 2, 16) * 16);
-        t.n1 = (int)(n16 - t.n0);
-        return t;
-    }
-    t.n_tiles = (int)ceil_div(n16, 256);
-    t.n0 = (int)(ceil_div(ceil_div(n16, t.n_tiles), 16) * 16);
-    t.n1 = 0;
-    return t;
-}
-
 bool tf32x3_eligible(const void *A, const void *D, int64_t M, int64_t K, int64_t N) {
     // TMA needs 16-byte aligned bases and row pitches; tiny reductions / outputs stay on the SIMT path
     return M >= 1 && K >= 32 && N >= 16 && (K % 4) == 0 && (((uintptr_t)A) % 16) == 0 && (((uintptr_t)D) % 16) == 0;
@@ -365,32 +382,31 @@ int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act
         split_tf32_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, st>>>(Bsrc, (int)N, (int)K, 0, b_hi, b_lo);
     PTK_CHECK_LAUNCH();
 
-    const NTiling t = plan_n(N);
-    CUtensorMap map_a, map_bhi, map_blo, map_bhi1, map_blo1;
+    CUtensorMap map_a, map_bhi, map_blo;
     int rc = make_map(&map_a, A, M, K, TG_BM);
     if (rc) return rc;
-    rc = make_map(&map_bhi, b_hi, N, K, t.n0);  // (N x K) K-major; box rows = width of the N-part
+    rc = make_map(&map_bhi, b_hi, N, K, TG_BN);  // (N x K) K-major; rows beyond N are zero-filled
     if (rc) return rc;
-    rc = make_map(&map_blo, b_lo, N, K, t.n0);
-    if (rc) return rc;
-    const int n1_box = t.n1 > 0 ? t.n1 : t.n0;
-    rc = make_map(&map_bhi1, b_hi, N, K, n1_box);
-    if (rc) return rc;
-    rc = make_map(&map_blo1, b_lo, N, K, n1_box);
+    rc = make_map(&map_blo, b_lo, N, K, TG_BN);
     if (rc) return rc;
 
     TGParams p;
-    p.M = (int)M; p.N = (int)N; p.K = (int)K; p.n0_cols = t.n0; p.n1_cols = t.n1; p.D = D; p.act = act;
-    const int bn = t.n0 + t.n1;
-    const size_t smem = (size_t)TG_STAGES * (2 * TG_BM * TG_BK * 4 + 2 * (size_t)bn * TG_BK * 4) + 1024;
-    dim3 grid((unsigned)ceil_div(M, TG_BM), (unsigned)t.n_tiles);
-    if (act) {
+    p.M = (int)M; p.N = (int)N; p.K = (int)K; p.D = D; p.act = act;
+    static int dbg = -1;
+    if (dbg < 0) { const char *e = getenv("PTK_TG_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
+    const size_t smem = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024;
+    dim3 grid((unsigned)ceil_div(M, TG_BM), (unsigned)ceil_div(N, TG_BN));
+    static bool attr_set = false;
+    if (!attr_set) {
         PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gemm_tf32x3_kernel<true><<<grid, TG_THREADS, smem, st>>>(map_a, map_bhi, map_blo, map_bhi1, map_blo1, p);
-    } else {
         PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        gemm_tf32x3_kernel<false><<<grid, TG_THREADS, smem, st>>>(map_a, map_bhi, map_blo, map_bhi1, map_blo1, p);
+        attr_set = true;
     }
+    if (act)
+        gemm_tf32x3_kernel<true><<<grid, TG_THREADS, smem, st>>>(map_a, map_bhi, map_blo, p);
+    else
+        gemm_tf32x3_kernel<false><<<grid, TG_THREADS, smem, st>>>(map_a, map_bhi, map_blo, p);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }

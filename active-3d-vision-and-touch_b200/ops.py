@@ -163,7 +163,7 @@ def face_areas_normals(verts_packed, faces_i64):
 # moves 20-layer gradients by 1e-3 -- measured).  Inference forwards and the backward GEMMs,
 # whose errors enter the result smoothly, may use the 3xTF32 tensor-core kernel.
 GEMM_AUTO, GEMM_FFMA, GEMM_TF32X3 = 0, 1, 2
-algo = {"fwd_train": GEMM_FFMA, "fwd_infer": GEMM_AUTO, "dgrad": GEMM_FFMA}
+algo = {"fwd_train": GEMM_FFMA, "fwd_infer": GEMM_AUTO, "dgrad": GEMM_AUTO}
 
 
 def _linear_fwd(X2, W2, out=None, algo_id=GEMM_FFMA):
