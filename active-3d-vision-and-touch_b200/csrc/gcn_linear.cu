@@ -134,6 +134,11 @@ size_t tf32x3_workspace_bytes(int64_t K, int64_t N);
 int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act, int64_t M, int64_t K, int64_t N,
                 float *D, void *workspace, size_t workspace_bytes, cudaStream_t st);
 
+bool wgrad_tf32x3_eligible(const void *X, const void *gH, int64_t M, int64_t Kin, int64_t Nout);
+size_t wgrad_tf32x3_workspace_bytes(int64_t M, int64_t Kin, int64_t Nout);
+int wgrad_tf32x3(const float *X, const float *gH, int64_t M, int64_t Kin, int64_t Nout, void *workspace,
+                 size_t workspace_bytes, float **part_out, int *n_splits, cudaStream_t st);
+
 }  // namespace ptk
 
 using namespace ptk;
@@ -203,16 +208,30 @@ static int wgrad_splits(int64_t M, int64_t K, int64_t N) {
 
 extern "C" size_t ptk_gcn_linear_wgrad_workspace_bytes(int64_t M, int64_t K, int64_t N) {
     if (M <= 0 || K <= 0 || N <= 0) return 0;
-    return sizeof(float) * (size_t)wgrad_splits(M, K, N) * (size_t)K * (size_t)N;
+    const size_t a = sizeof(float) * (size_t)wgrad_splits(M, K, N) * (size_t)K * (size_t)N;
+    const size_t b = wgrad_tf32x3_workspace_bytes(M, K, N);
+    return a > b ? a : b;
 }
 
 extern "C" int ptk_gcn_linear_wgrad(const float *X, const float *gH, int64_t M, int64_t K, int64_t N,
-                                    float *gW, void *workspace, size_t workspace_bytes,
+                                    float *gW, int algo, void *workspace, size_t workspace_bytes,
                                     ptk_stream_t stream) {
     int rc = check_gemm(X, gH, gW, M, K, N);
     if (rc) return rc;
+    PTK_REQUIRE(algo >= 0 && algo <= 2, PTK_ERR_SHAPE, "gcn_linear_wgrad: algo must be 0, 1 or 2");
     PTK_REQUIRE(workspace && workspace_bytes >= ptk_gcn_linear_wgrad_workspace_bytes(M, K, N),
                 PTK_ERR_WORKSPACE, "gcn_linear_wgrad: workspace too small");
+    if (algo != 1 && wgrad_tf32x3_eligible(X, gH, M, K, N)) {
+        float *part = nullptr;
+        int ns = 0;
+        rc = wgrad_tf32x3(X, gH, M, K, N, workspace, workspace_bytes, &part, &ns, as_stream(stream));
+        if (rc) return rc;
+        const long long elems = (long long)K * N;
+        splitk_reduce_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, as_stream(stream)>>>(part, ns, elems, gW);
+        PTK_CHECK_LAUNCH();
+        return PTK_OK;
+    }
+    PTK_REQUIRE(algo != 2, PTK_ERR_SHAPE, "gcn_linear_wgrad: shape not eligible for the tensor-core path");
     // gW (K x N) = X^T . gH : GEMM with m=K, n=N, k=M; A[m=k_in][k=row] = X[row*K + k_in]
     const int ns = wgrad_splits(M, K, N);
     const int64_t kper = ceil_div(ceil_div(M, ns), GL_BK) * GL_BK;

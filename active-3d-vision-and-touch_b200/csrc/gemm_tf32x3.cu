@@ -311,6 +311,215 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
 }
 
+// =================================================================================================
+// wgrad:  gW (K_in x N_out) = X^T (K_in x M) . gH (M x N_out)      -- reduction over the M rows.
+//
+// Both operands are activations that are row-major over the REDUCTION index (X[row][k_in],
+// gH[row][n_out]), i.e. "MN-major" for the tensor core.  Instead of MN-major descriptors the
+// converter warps -- which rewrite every element anyway to split it -- also transpose: TMA brings
+// un-swizzled raw tiles raw[32 rows][128 k_in] / raw[32 rows][160 n_out]; each converter thread reads
+// 4 consecutive rows of one column (conflict-free) and writes one 16-byte hi chunk and one lo chunk
+// into the canonical K-major SWIZZLE_128B operand tiles (chunk ^= row & 7).  From there on the
+// pipeline is the one above: 12 UMMAs per 32-row k-block into one of 3 TMEM buffers, drained and added
+// in FP32 registers.  The reduction is split over gridDim.z; partial tiles go to a workspace and are
+// summed in a fixed order by splitk_reduce (deterministic).
+//   warp 0: TMA   warp 1: MMA   warps 4-11: converter/transposer   warps 12-27: drain (40 columns each)
+constexpr int WG_NR = 2;                          // raw ring slots
+constexpr int WG_NS = 2;                          // split (operand) ring stages
+constexpr int WG_RAW_A = TG_BK * TG_BM * 4;       // 16 KB  raw[32][128]
+constexpr int WG_RAW_B = TG_BK * TG_BN * 4;       // 20 KB  raw[32][160]
+constexpr int WG_RAW_BYTES = WG_RAW_A + WG_RAW_B;
+constexpr int WG_THREADS = 896;
+constexpr int WG_CONV_WARPS = 8;
+constexpr int WG_DRAIN_WARPS = 16;
+
+struct WGParams {
+    int M, Kin, Nout;     // X is M x Kin, gH is M x Nout
+    int kb_per_split, num_kb_total;
+    float *part;          // (gridDim.z, Kin, Nout)
+};
+
+__device__ __forceinline__ void split4(const float v0, const float v1, const float v2, const float v3, uint4 &h,
+                                       uint4 &l) {
+    h.x = tf32_rna(v0); h.y = tf32_rna(v1); h.z = tf32_rna(v2); h.w = tf32_rna(v3);
+    l.x = tf32_rna(v0 - __uint_as_float(h.x)); l.y = tf32_rna(v1 - __uint_as_float(h.y));
+    l.z = tf32_rna(v2 - __uint_as_float(h.z)); l.w = tf32_rna(v3 - __uint_as_float(h.w));
+}
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_g,
+                    const WGParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t *split_base = smem;                                   // WG_NS x TG_STAGE_BYTES (1024-aligned pieces)
+    uint8_t *raw_base = smem + (size_t)WG_NS * TG_STAGE_BYTES;    // WG_NR x WG_RAW_BYTES
+    __shared__ __align__(8) uint64_t bars[2 * WG_NR + 2 * WG_NS + 2 * TG_NBUF];
+    __shared__ uint32_t tmem_base_slot;
+    const uint32_t bar_rfull = smem_u32(&bars[0]);
+    const uint32_t bar_rempty = smem_u32(&bars[WG_NR]);
+    const uint32_t bar_sfull = smem_u32(&bars[2 * WG_NR]);
+    const uint32_t bar_sempty = smem_u32(&bars[2 * WG_NR + WG_NS]);
+    const uint32_t bar_tfull = smem_u32(&bars[2 * WG_NR + 2 * WG_NS]);
+    const uint32_t bar_tempty = smem_u32(&bars[2 * WG_NR + 2 * WG_NS + TG_NBUF]);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * TG_BM;   // k_in offset of this tile
+    const int n0 = blockIdx.y * TG_BN;   // n_out offset
+    const int kb_begin = blockIdx.z * p.kb_per_split;
+    const int nk = min(p.num_kb_total, kb_begin + p.kb_per_split) - kb_begin;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_g) : "memory");
+        for (int i = 0; i < WG_NR; ++i) { mbar_init(bar_rfull + 8 * i, 1); mbar_init(bar_rempty + 8 * i, WG_CONV_WARPS); }
+        for (int i = 0; i < WG_NS; ++i) { mbar_init(bar_sfull + 8 * i, WG_CONV_WARPS); mbar_init(bar_sempty + 8 * i, 1); }
+        for (int i = 0; i < TG_NBUF; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, WG_DRAIN_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < nk; ++i) {
+                const int r = i % WG_NR;
+                mbar_wait(bar_rempty + 8 * r, ((i / WG_NR) & 1) ^ 1);
+                const uint32_t ra = smem_u32(raw_base + (size_t)r * WG_RAW_BYTES);
+                mbar_expect_tx(bar_rfull + 8 * r, WG_RAW_BYTES);
+                tma_load_2d(ra, &map_x, bar_rfull + 8 * r, m0, (kb_begin + i) * TG_BK);
+                tma_load_2d(ra + WG_RAW_A, &map_g, bar_rfull + 8 * r, n0, (kb_begin + i) * TG_BK);
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = make_idesc_tf32(TG_BN);
+        for (int i = 0; i < nk; ++i) {
+            const int s = i % WG_NS, b = i % TG_NBUF;
+            mbar_wait(bar_sfull + 8 * s, (i / WG_NS) & 1);
+            mbar_wait(bar_tempty + 8 * b, ((i / TG_NBUF) & 1) ^ 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(split_base + (size_t)s * TG_STAGE_BYTES);
+                const uint64_t d_ahi = make_kmajor_sw128_desc(sa);
+                const uint64_t d_alo = make_kmajor_sw128_desc(sa + TG_A_BYTES);
+                const uint64_t d_bhi = make_kmajor_sw128_desc(sa + 2 * TG_A_BYTES);
+                const uint64_t d_blo = make_kmajor_sw128_desc(sa + 2 * TG_A_BYTES + TG_B_BYTES);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(b * TG_BN);
+#pragma unroll
+                for (int ks = 0; ks < TG_BK / 8; ++ks) {
+                    const uint64_t ko = (uint64_t)(ks * 32 >> 4);
+                    umma_tf32(d_tmem, d_ahi + ko, d_blo + ko, idesc, ks != 0);
+                    umma_tf32(d_tmem, d_alo + ko, d_bhi + ko, idesc, 1);
+                }
+#pragma unroll
+                for (int ks = 0; ks < TG_BK / 8; ++ks) {
+                    const uint64_t ko = (uint64_t)(ks * 32 >> 4);
+                    umma_tf32(d_tmem, d_ahi + ko, d_bhi + ko, idesc, 1);
+                }
+                umma_commit(bar_sempty + 8 * s);
+                umma_commit(bar_tfull + 8 * b);
+            }
+            __syncwarp();
+        }
+    } else if (warp >= 4 && warp < 4 + WG_CONV_WARPS) {
+        // ===================== converter + transposer =====================
+        const int ct = threadIdx.x - 128;  // 0..255
+        for (int i = 0; i < nk; ++i) {
+            const int r = i % WG_NR, s = i % WG_NS;
+            mbar_wait(bar_rfull + 8 * r, (i / WG_NR) & 1);
+            mbar_wait(bar_sempty + 8 * s, ((i / WG_NS) & 1) ^ 1);
+            const float *rawA = reinterpret_cast<const float *>(raw_base + (size_t)r * WG_RAW_BYTES);
+            const float *rawB = rawA + TG_BK * TG_BM;
+            uint8_t *st = split_base + (size_t)s * TG_STAGE_BYTES;
+#pragma unroll
+            for (int j = 0; j < (TG_BM * 8) / 256; ++j) {        // A: 128 columns x 8 row-quads
+                const int t = ct + j * 256;
+                const int col = t & (TG_BM - 1), q = t / TG_BM;
+                uint4 h, l;
+                split4(rawA[(4 * q + 0) * TG_BM + col], rawA[(4 * q + 1) * TG_BM + col],
+                       rawA[(4 * q + 2) * TG_BM + col], rawA[(4 * q + 3) * TG_BM + col], h, l);
+                const int off = col * 128 + ((q ^ (col & 7)) << 4);
+                *reinterpret_cast<uint4 *>(st + off) = h;
+                *reinterpret_cast<uint4 *>(st + TG_A_BYTES + off) = l;
+            }
+#pragma unroll
+            for (int j = 0; j < (TG_BN * 8) / 256; ++j) {        // B: 160 columns x 8 row-quads
+                const int t = ct + j * 256;
+                const int col = t % TG_BN, q = t / TG_BN;
+                uint4 h, l;
+                split4(rawB[(4 * q + 0) * TG_BN + col], rawB[(4 * q + 1) * TG_BN + col],
+                       rawB[(4 * q + 2) * TG_BN + col], rawB[(4 * q + 3) * TG_BN + col], h, l);
+                const int off = col * 128 + ((q ^ (col & 7)) << 4);
+                *reinterpret_cast<uint4 *>(st + 2 * TG_A_BYTES + off) = h;
+                *reinterpret_cast<uint4 *>(st + 2 * TG_A_BYTES + TG_B_BYTES + off) = l;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(bar_sfull + 8 * s);
+                mbar_arrive(bar_rempty + 8 * r);
+            }
+        }
+    } else if (warp >= 4 + WG_CONV_WARPS) {
+        // ===================== drain + epilogue =====================
+        const int q = warp & 3;
+        const int cpart = (warp - 4 - WG_CONV_WARPS) >> 2;   // 0..3 -> columns [40*cpart, 40*cpart + 40)
+        float acc[40];
+#pragma unroll
+        for (int j = 0; j < 40; ++j) acc[j] = 0.f;
+        for (int i = 0; i < nk; ++i) {
+            const int b = i % TG_NBUF;
+            mbar_wait(bar_tfull + 8 * b, (i / TG_NBUF) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * TG_BN + cpart * 40);
+            uint32_t r0[16], r1[16], r2[8];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(r0[0]), "=r"(r0[1]), "=r"(r0[2]), "=r"(r0[3]), "=r"(r0[4]), "=r"(r0[5]), "=r"(r0[6]), "=r"(r0[7]),
+                  "=r"(r0[8]), "=r"(r0[9]), "=r"(r0[10]), "=r"(r0[11]), "=r"(r0[12]), "=r"(r0[13]), "=r"(r0[14]), "=r"(r0[15])
+                : "r"(taddr));
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                : "=r"(r1[0]), "=r"(r1[1]), "=r"(r1[2]), "=r"(r1[3]), "=r"(r1[4]), "=r"(r1[5]), "=r"(r1[6]), "=r"(r1[7]),
+                  "=r"(r1[8]), "=r"(r1[9]), "=r"(r1[10]), "=r"(r1[11]), "=r"(r1[12]), "=r"(r1[13]), "=r"(r1[14]), "=r"(r1[15])
+                : "r"(taddr + 16u));
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                : "=r"(r2[0]), "=r"(r2[1]), "=r"(r2[2]), "=r"(r2[3]), "=r"(r2[4]), "=r"(r2[5]), "=r"(r2[6]), "=r"(r2[7])
+                : "r"(taddr + 32u));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { acc[j] += __uint_as_float(r0[j]); acc[16 + j] += __uint_as_float(r1[j]); }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[32 + j] += __uint_as_float(r2[j]);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+        }
+        const int m = m0 + q * 32 + lane;            // k_in index (row of gW)
+        const int nb = n0 + cpart * 40;
+        if (m < p.Kin) {
+            float *dst = p.part + ((size_t)blockIdx.z * p.Kin + m) * p.Nout + nb;
+#pragma unroll
+            for (int v = 0; v < 10; ++v)
+                if (nb + 4 * v + 4 <= p.Nout)
+                    *reinterpret_cast<float4 *>(dst + 4 * v) =
+                        make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
 // Split a weight matrix into TF32 hi/lo parts, optionally transposing:
 //   transpose = 0: out[r, c] = split(src[r, c])           (rows x cols) -> (rows x cols)
 //   transpose = 1: out[c, r] = split(src[r, c])           (rows x cols) -> (cols x rows)
@@ -344,16 +553,25 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D fp32 row-major (rows x cols, cols contiguous) tensor map, box = (32 cols, box_rows), SWIZZLE_128B
+// 2-D fp32 row-major (rows x cols, cols contiguous) tensor map.
+//   swizzled : box = (32 cols, box_rows), SWIZZLE_128B    (K-major operand tiles)
+//   plain    : box = (box_cols, box_rows), no swizzle      (raw tiles for the transposing converter)
+static int make_map_ex(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int box_cols, int box_rows,
+                       bool swizzle);
 static int make_map(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int box_rows) {
+    return make_map_ex(map, base, rows, cols, TG_BK, box_rows, true);
+}
+static int make_map_ex(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int box_cols, int box_rows,
+                       bool swizzle) {
     EncodeTiledFn fn = encode_fn();
     PTK_REQUIRE(fn != nullptr, PTK_ERR_CUDA, "cuTensorMapEncodeTiled is unavailable in this driver");
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)cols * 4};
-    cuuint32_t box[2] = {(cuuint32_t)TG_BK, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     PTK_REQUIRE(r == CUDA_SUCCESS, PTK_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld box_rows=%d",
                 (int)r, (long long)rows, (long long)cols, box_rows);
@@ -408,6 +626,61 @@ int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act
     else
         gemm_tf32x3_kernel<false><<<grid, TG_THREADS, smem, st>>>(map_a, map_bhi, map_blo, p);
     PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}
+
+// ---- wgrad host side
+struct WGPlan { int tiles_m, tiles_n, splits, kb_per_split, num_kb; };
+static WGPlan plan_wgrad(int64_t M, int64_t Kin, int64_t Nout) {
+    WGPlan w;
+    w.tiles_m = (int)ceil_div(Kin, TG_BM);
+    w.tiles_n = (int)ceil_div(Nout, TG_BN);
+    w.num_kb = (int)ceil_div(M, TG_BK);
+    int want = sm_count() / (w.tiles_m * w.tiles_n);
+    if (want < 1) want = 1;
+    int max_s = w.num_kb / 4 > 0 ? w.num_kb / 4 : 1;
+    if (want > max_s) want = max_s;
+    w.kb_per_split = (int)ceil_div(w.num_kb, want);
+    w.splits = (int)ceil_div(w.num_kb, w.kb_per_split);
+    return w;
+}
+
+bool wgrad_tf32x3_eligible(const void *X, const void *gH, int64_t M, int64_t Kin, int64_t Nout) {
+    return M >= 32 && Kin >= 32 && Nout >= 16 && (Kin % 4) == 0 && (Nout % 4) == 0 && (((uintptr_t)X) % 16) == 0 &&
+           (((uintptr_t)gH) % 16) == 0;
+}
+
+size_t wgrad_tf32x3_workspace_bytes(int64_t M, int64_t Kin, int64_t Nout) {
+    const WGPlan w = plan_wgrad(M, Kin, Nout);
+    return sizeof(float) * (size_t)w.splits * (size_t)Kin * (size_t)Nout + 256;
+}
+
+// part (splits, Kin, Nout) in `workspace`; returns the number of splits through *n_splits
+int wgrad_tf32x3(const float *X, const float *gH, int64_t M, int64_t Kin, int64_t Nout, void *workspace,
+                 size_t workspace_bytes, float **part_out, int *n_splits, cudaStream_t st) {
+    PTK_REQUIRE(workspace && workspace_bytes >= wgrad_tf32x3_workspace_bytes(M, Kin, Nout), PTK_ERR_WORKSPACE,
+                "wgrad_tf32x3: workspace too small");
+    const WGPlan w = plan_wgrad(M, Kin, Nout);
+    float *part = reinterpret_cast<float *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
+    CUtensorMap map_x, map_g;
+    int rc = make_map_ex(&map_x, X, M, Kin, TG_BM, TG_BK, false);
+    if (rc) return rc;
+    rc = make_map_ex(&map_g, gH, M, Nout, TG_BN, TG_BK, false);
+    if (rc) return rc;
+    WGParams p;
+    p.M = (int)M; p.Kin = (int)Kin; p.Nout = (int)Nout; p.kb_per_split = w.kb_per_split; p.num_kb_total = w.num_kb;
+    p.part = part;
+    const size_t smem = (size_t)WG_NS * TG_STAGE_BYTES + (size_t)WG_NR * WG_RAW_BYTES + 1024;
+    static bool attr_set = false;
+    if (!attr_set) {
+        PTK_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set = true;
+    }
+    dim3 grid((unsigned)w.tiles_m, (unsigned)w.tiles_n, (unsigned)w.splits);
+    wgrad_tf32x3_kernel<<<grid, WG_THREADS, smem, st>>>(map_x, map_g, p);
+    PTK_CHECK_LAUNCH();
+    *part_out = part;
+    *n_splits = w.splits;
     return PTK_OK;
 }
 

@@ -163,7 +163,7 @@ def face_areas_normals(verts_packed, faces_i64):
 # moves 20-layer gradients by 1e-3 -- measured).  Inference forwards and the backward GEMMs,
 # whose errors enter the result smoothly, may use the 3xTF32 tensor-core kernel.
 GEMM_AUTO, GEMM_FFMA, GEMM_TF32X3 = 0, 1, 2
-algo = {"fwd_train": GEMM_FFMA, "fwd_infer": GEMM_AUTO, "dgrad": GEMM_AUTO}
+algo = {"fwd_train": GEMM_FFMA, "fwd_infer": GEMM_AUTO, "dgrad": GEMM_AUTO, "wgrad": GEMM_AUTO}
 
 
 def _linear_fwd(X2, W2, out=None, algo_id=GEMM_FFMA):
@@ -190,13 +190,14 @@ def _linear_dgrad(gH2, W2, act2, algo_id=None):
     return gX
 
 
-def _linear_wgrad(X2, gH2):
+def _linear_wgrad(X2, gH2, algo_id=None):
+    algo_id = algo["wgrad"] if algo_id is None else algo_id
     M, K = X2.shape
     N = gH2.shape[1]
     L = _lib.lib()
     gW = torch.empty(K, N, dtype=torch.float32, device=X2.device)
     ws = _ws(L.ptk_gcn_linear_wgrad_workspace_bytes(M, K, N), X2.device)
-    _lib.check(L.ptk_gcn_linear_wgrad(_p(X2), _p(gH2), M, K, N, _p(gW), _p(ws), ws.numel(), _stream()),
+    _lib.check(L.ptk_gcn_linear_wgrad(_p(X2), _p(gH2), M, K, N, _p(gW), algo_id, _p(ws), ws.numel(), _stream()),
                "ptk_gcn_linear_wgrad")
     return gW
 

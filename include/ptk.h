@@ -149,7 +149,7 @@ int ptk_gcn_linear_dgrad(const float *gH, const float *W, const float *act, int6
                          ptk_stream_t stream);
 size_t ptk_gcn_linear_wgrad_workspace_bytes(int64_t M, int64_t K, int64_t N);
 int ptk_gcn_linear_wgrad(const float *X, const float *gH, int64_t M, int64_t K, int64_t N, float *gW,
-                         void *workspace, size_t workspace_bytes, ptk_stream_t stream);
+                         int algo, void *workspace, size_t workspace_bytes, ptk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (end-to-end path: H2D + kernels + D2H inside the call).

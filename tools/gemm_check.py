@@ -53,6 +53,11 @@ for (M, K, N) in shapes:
             torch.cuda.synchronize()
             ed = rel(gX, refd * (X > 0))
             td = timeit(lambda: ptk_b200.ops._linear_dgrad(G, W, X, algo_id=mode))
+            gW = ptk_b200.ops._linear_wgrad(X, G, algo_id=mode)
+            torch.cuda.synchronize()
+            ew = rel(gW, X.double().t() @ G.double())
+            tw = timeit(lambda: ptk_b200.ops._linear_wgrad(X, G, algo_id=mode))
+            print(f"    wgrad err {ew:.2e} {tw*1e3:8.1f} us {2*M*K*N/tw/1e9:8.1f} TFLOPS")
             print(f"M={M} K={K} N={N} {name:7s} fwd err {e:.2e} {t*1e3:8.1f} us {2*M*K*N/t/1e9:8.1f} TFLOPS | dgrad err {ed:.2e} {td*1e3:8.1f} us {2*M*K*N/td/1e9:8.1f} TFLOPS", flush=True)
         except Exception as ex:
             print(f"M={M} K={K} N={N} {name}: {type(ex).__name__}: {ex}", flush=True)
