@@ -137,18 +137,21 @@ struct NNPlan {
 };
 
 static NNPlan plan_nn(int64_t B, int64_t Pq_max, int64_t Pt_max, int ndir) {
-    const int64_t want = 2LL * sm_count() * 2;  // >= 2 waves at 2 resident CTAs / SM
+    // Aim for >= 4 waves of CTAs (CH_MINB resident per SM) so that the last, partial wave costs little.
+    // Prefer R = 8 queries per thread (fewest shared-memory loads per evaluation) and get the CTA count
+    // from splitting the target range; fall back to fewer queries per thread for tiny clouds.
+    const int64_t want = 4LL * sm_count() * CH_MINB;
     NNPlan p;
-    p.R = 8;
     auto ctas = [&](int R) { return B * ndir * ceil_div(Pq_max, (int64_t)CH_THREADS * R); };
-    if (ctas(8) < want) p.R = 4;
-    if (ctas(4) < want) p.R = 2;
-    int64_t base = ctas(p.R);
+    const int64_t max_split = ceil_div(Pt_max, (int64_t)CH_CHUNK * 16);  // >= 256 targets per split
+    p.R = 8;
+    if (ctas(8) * max_split < want) p.R = 4;
+    if (p.R == 4 && ctas(4) * max_split < want) p.R = 2;
+    const int64_t base = ctas(p.R);
     int64_t ns = base >= want ? 1 : ceil_div(want, base);
-    int64_t max_split = ceil_div(Pt_max, (int64_t)CH_CHUNK * 8);  // >= 128 targets per split
     if (ns > max_split) ns = max_split;
     if (ns < 1) ns = 1;
-    int64_t len = ceil_div(ceil_div(Pt_max, ns), (int64_t)CH_CHUNK) * CH_CHUNK;
+    const int64_t len = ceil_div(ceil_div(Pt_max, ns), (int64_t)CH_CHUNK) * CH_CHUNK;
     p.n_split = (int)ceil_div(Pt_max, len);
     p.split_len = (int)len;
     return p;

@@ -36,6 +36,33 @@ __device__ __forceinline__ void row_gather(const int32_t *__restrict__ col, cons
             my_val = val[e0 + lane];
         }
         int k = 0;
+        for (; k + 8 <= cnt; k += 8) {  // 8 neighbour rows in flight per lane
+            int j[8];
+            float w[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                j[u] = __shfl_sync(0xffffffffu, my_col, k + u);
+                w[u] = __shfl_sync(0xffffffffu, my_val, k + u);
+            }
+            if (active) {
+                if (VEC) {
+                    float4 a[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) a[u] = *reinterpret_cast<const float4 *>(inb + (size_t)j[u] * C + v * 4);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        acc[0] = fmaf(w[u], a[u].x, acc[0]); acc[1] = fmaf(w[u], a[u].y, acc[1]);
+                        acc[2] = fmaf(w[u], a[u].z, acc[2]); acc[3] = fmaf(w[u], a[u].w, acc[3]);
+                    }
+                } else {
+                    float a[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) a[u] = inb[(size_t)j[u] * C + v];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) acc[0] = fmaf(w[u], a[u], acc[0]);
+                }
+            }
+        }
         for (; k + 4 <= cnt; k += 4) {
             int j0 = __shfl_sync(0xffffffffu, my_col, k + 0), j1 = __shfl_sync(0xffffffffu, my_col, k + 1);
             int j2 = __shfl_sync(0xffffffffu, my_col, k + 2), j3 = __shfl_sync(0xffffffffu, my_col, k + 3);
@@ -82,12 +109,26 @@ __device__ __forceinline__ void row_gather(const int32_t *__restrict__ col, cons
 // One warp per (b, i) row.  VEC: lanes own float4 channel groups; else lanes own single channels.
 // Rows with degree > HUB_DEG are skipped here when hubs are handled by gcn_aggregate_hub_kernel.
 template <bool VEC>
+__device__ __forceinline__ void hub_cta(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                        const float *__restrict__ val, const int32_t *__restrict__ hubs, int n_hubs,
+                                        int Nv, const float *__restrict__ in, int C, int L,
+                                        const float *__restrict__ bias, int relu, float *__restrict__ out,
+                                        unsigned hub_block);
+
+// Grid = [hub CTAs | row CTAs]: the hub CTAs have the lowest block ids, so they are scheduled first and
+// their long neighbour lists overlap with the short rows instead of forming a tail.
+template <bool VEC>
 __global__ void __launch_bounds__(AG_THREADS)
 gcn_aggregate_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                     const float *__restrict__ val, int Nv, const float *__restrict__ in,
-                     long long rows, int C, int L, const float *__restrict__ bias, int relu,
-                     float *__restrict__ out, int skip_hubs) {
-    const long long row = (long long)blockIdx.x * AG_WARPS + (threadIdx.x >> 5);
+                     const float *__restrict__ val, const int32_t *__restrict__ hubs, int n_hubs, unsigned hub_ctas,
+                     int Nv, const float *__restrict__ in, long long rows, int C, int L,
+                     const float *__restrict__ bias, int relu, float *__restrict__ out) {
+    if (blockIdx.x < hub_ctas) {
+        hub_cta<VEC>(rowptr, col, val, hubs, n_hubs, Nv, in, C, L, bias, relu, out, blockIdx.x);
+        return;
+    }
+    const int skip_hubs = hub_ctas > 0;
+    const long long row = (long long)(blockIdx.x - hub_ctas) * AG_WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     const int i = (int)(row % Nv);
@@ -143,13 +184,13 @@ gcn_aggregate_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restri
 // One CTA per (b, hub row): the 8 warps split the neighbour list; shared-memory reduction.
 // Only the aggregated channel groups are written (pass-through was done by the row kernel).
 template <bool VEC>
-__global__ void __launch_bounds__(AG_THREADS)
-gcn_aggregate_hub_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                         const float *__restrict__ val, const int32_t *__restrict__ hubs, int n_hubs,
-                         int Nv, const float *__restrict__ in, int C, int L,
-                         const float *__restrict__ bias, int relu, float *__restrict__ out) {
-    const int i = hubs[blockIdx.x % n_hubs];
-    const long long b = blockIdx.x / n_hubs;
+__device__ __forceinline__ void hub_cta(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                                        const float *__restrict__ val, const int32_t *__restrict__ hubs, int n_hubs,
+                                        int Nv, const float *__restrict__ in, int C, int L,
+                                        const float *__restrict__ bias, int relu, float *__restrict__ out,
+                                        unsigned hub_block) {
+    const int i = hubs[hub_block % n_hubs];
+    const long long b = hub_block / n_hubs;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int beg = rowptr[i], end = rowptr[i + 1];
     const int per = (((end - beg) + AG_WARPS - 1) / AG_WARPS + 31) / 32 * 32;
@@ -196,23 +237,43 @@ gcn_aggregate_hub_kernel(const int32_t *__restrict__ rowptr, const int32_t *__re
 
 // gbias[c] = sum_rows g[row, c] (c < L), 0 otherwise.  Deterministic two-stage column sum:
 // stage 1: CTA `k` sums rows k, k+G, ... into part[k, c]; stage 2: one CTA sums the G partials.
-constexpr int BG_PARTS = 296;
-__global__ void __launch_bounds__(128)
+constexpr int BG_PARTS = 1184;  // 8 slabs per SM: short dependent-load chains in stage 1
+// CTA k sums its contiguous slab of rows; 8 row lanes x 32 column lanes (128-byte coalesced segments),
+// fixed-order shared-memory reduction over the row lanes.
+__global__ void __launch_bounds__(256)
 bias_grad_stage1(const float *__restrict__ g, long long M, int C, int L, float *__restrict__ part) {
-    for (int c = threadIdx.x; c < L; c += 128) {
-        float acc = 0.f;
-        for (long long r = blockIdx.x; r < M; r += gridDim.x) acc += g[(size_t)r * C + c];
-        part[(size_t)blockIdx.x * L + c] = acc;
-    }
-}
-__global__ void __launch_bounds__(128)
-bias_grad_stage2(const float *__restrict__ part, int nparts, int C, int L, float *__restrict__ gbias) {
-    for (int c = blockIdx.x * 128 + threadIdx.x; c < C; c += gridDim.x * 128) {
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const long long per = (M + gridDim.x - 1) / gridDim.x;
+    const long long r0 = (long long)blockIdx.x * per;
+    const long long r1 = r0 + per < M ? r0 + per : M;
+    for (int cbase = 0; cbase < L; cbase += 32) {
+        const int c = cbase + cx;
         float acc = 0.f;
         if (c < L)
-            for (int p = 0; p < nparts; ++p) acc += part[(size_t)p * L + c];
-        gbias[c] = acc;
+            for (long long r = r0 + ry; r < r1; r += 8) acc += g[(size_t)r * C + c];
+        red[ry][cx] = acc;
+        __syncthreads();
+        if (ry == 0 && c < L) {
+            float t = red[0][cx];
+#pragma unroll
+            for (int y = 1; y < 8; ++y) t += red[y][cx];
+            part[(size_t)blockIdx.x * L + c] = t;
+        }
+        __syncthreads();
     }
+}
+// stage 2: one warp per column; lanes stride over the partials, fixed-order butterfly => deterministic
+__global__ void __launch_bounds__(256)
+bias_grad_stage2(const float *__restrict__ part, int nparts, int C, int L, float *__restrict__ gbias) {
+    const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (c >= C) return;
+    float acc = 0.f;
+    if (c < L)
+        for (int p = lane; p < nparts; p += 32) acc += part[(size_t)p * L + c];
+    acc = warp_sum(acc);
+    if (lane == 0) gbias[c] = acc;
 }
 
 // gpre = (act > 0) ? g : 0  -- ReLU backward for the stand-alone layer / last-layer cases
@@ -246,20 +307,12 @@ extern "C" int ptk_gcn_aggregate(const int32_t *rowptr, const int32_t *col, cons
     cudaStream_t st = as_stream(stream);
     const long long rows = (long long)B * Nv;
     const bool vec = (C % 4 == 0) && ((((uintptr_t)in) | ((uintptr_t)out)) % 16 == 0);
-    const unsigned grid = (unsigned)ceil_div(rows, AG_WARPS);
-    const int skip = (hubs && n_hubs > 0) ? 1 : 0;
-    if (skip) {
-        const unsigned hgrid = (unsigned)(B * n_hubs);
-        if (vec)
-            gcn_aggregate_hub_kernel<true><<<hgrid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, (int)Nv, in, (int)C, (int)L, bias, relu, out);
-        else
-            gcn_aggregate_hub_kernel<false><<<hgrid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, (int)Nv, in, (int)C, (int)L, bias, relu, out);
-        PTK_CHECK_LAUNCH();
-    }
+    const unsigned hub_ctas = (hubs && n_hubs > 0) ? (unsigned)(B * n_hubs) : 0u;
+    const unsigned grid = hub_ctas + (unsigned)ceil_div(rows, AG_WARPS);
     if (vec)
-        gcn_aggregate_kernel<true><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, (int)Nv, in, rows, (int)C, (int)L, bias, relu, out, skip);
+        gcn_aggregate_kernel<true><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, hub_ctas, (int)Nv, in, rows, (int)C, (int)L, bias, relu, out);
     else
-        gcn_aggregate_kernel<false><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, (int)Nv, in, rows, (int)C, (int)L, bias, relu, out, skip);
+        gcn_aggregate_kernel<false><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, hub_ctas, (int)Nv, in, rows, (int)C, (int)L, bias, relu, out);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }
@@ -279,10 +332,10 @@ extern "C" int ptk_gcn_bias_grad(const float *g, int64_t M, int64_t C, int64_t L
     const int nparts = (int)(M < BG_PARTS ? M : BG_PARTS);
     float *part = reinterpret_cast<float *>(workspace);
     if (L > 0) {
-        bias_grad_stage1<<<nparts, 128, 0, st>>>(g, (long long)M, (int)C, (int)L, part);
+        bias_grad_stage1<<<nparts, 256, 0, st>>>(g, (long long)M, (int)C, (int)L, part);
         PTK_CHECK_LAUNCH();
     }
-    bias_grad_stage2<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>(part, nparts, (int)C, (int)L, gbias);
+    bias_grad_stage2<<<(unsigned)ceil_div(C, 8), 256, 0, st>>>(part, nparts, (int)C, (int)L, gbias);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }

@@ -118,6 +118,116 @@ sgemm_kernel(const float *__restrict__ A, long long lda, const float *__restrict
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Forward-specialised exact-FP32 kernel: H (M x N) = X (M x K) . W (K x N), all row-major, K % 4 == 0,
+// N % 4 == 0, 16-byte aligned.  CTA tile BM x 160 x 16 with BM in {128, 112, 96} chosen per problem so
+// that the grid is a whole number of waves (N = 300 -> two 160-wide column tiles, 6 % padding instead of
+// the 22 % of 128-wide tiles); 8 x 10 register micro-tiles (80 FFMA per 5 shared-memory loads); 128-bit
+// global loads, register-staged double buffering.  Each output is one k-sequential FMA chain starting
+// from 0 -- the arithmetic of a scalar FP32 loop (see ops.py: why the training forward needs that).
+constexpr int FW_BN = 160, FW_BK = 16, FW_PAD = 4;
+
+template <int BM>
+__global__ void __launch_bounds__(BM * 2, 2)
+sgemm_fwd_kernel(const float *__restrict__ A, const float *__restrict__ Bm, float *__restrict__ Cm, int M, int N,
+                 int K) {
+    constexpr int T = BM * 2;
+    __shared__ __align__(16) float As[2][FW_BK][BM + FW_PAD];
+    __shared__ __align__(16) float Bs[2][FW_BK][FW_BN];
+    const int tid = threadIdx.x;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * FW_BN;
+    const int tx = tid % 16, ty = tid / 16;
+
+    float4 ra[2];
+    // A: global -> registers (transposed into shared memory later); B: cp.async straight into shared
+    // memory (16-byte copies, zero-filled out of range) so it costs no staging registers.
+    auto g2r = [&](int k0, int nbuf) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = tid + i * T;
+            const int r = idx >> 2, kq = idx & 3;
+            const int m = m0 + r, k = k0 + kq * 4;
+            ra[i] = (m < M && k < K) ? __ldg(reinterpret_cast<const float4 *>(A + (size_t)m * K + k))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < (FW_BK * 40 + T - 1) / T; ++i) {
+            const int idx = tid + i * T;
+            if (idx < FW_BK * 40) {
+                const int kk = idx / 40, c4 = idx % 40;
+                const int k = k0 + kk, n = n0 + c4 * 4;
+                const bool ok = k < K && n < N;
+                const float *src = ok ? Bm + (size_t)k * N + n : Bm;
+                const unsigned dst = (unsigned)__cvta_generic_to_shared(&Bs[nbuf][kk][c4 * 4]);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(ok ? 16 : 0) : "memory");
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    auto r2s = [&](int buf) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int idx = tid + i * T;
+            const int r = idx >> 2, kq = idx & 3;
+            As[buf][kq * 4 + 0][r] = ra[i].x;
+            As[buf][kq * 4 + 1][r] = ra[i].y;
+            As[buf][kq * 4 + 2][r] = ra[i].z;
+            As[buf][kq * 4 + 3][r] = ra[i].w;
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    };
+
+    float acc[8][10];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) acc[i][j] = 0.f;
+
+    g2r(0, 0);
+    r2s(0);
+    __syncthreads();
+    int buf = 0;
+    for (int k0 = 0; k0 < K; k0 += FW_BK) {
+        const bool more = k0 + FW_BK < K;
+        if (more) g2r(k0 + FW_BK, buf ^ 1);
+#pragma unroll
+        for (int k = 0; k < FW_BK; ++k) {
+            const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 4]);
+            const float4 a1 = *reinterpret_cast<const float4 *>(&As[buf][k][BM / 2 + ty * 4]);
+            const float4 b0 = *reinterpret_cast<const float4 *>(&Bs[buf][k][tx * 4]);
+            const float4 b1 = *reinterpret_cast<const float4 *>(&Bs[buf][k][64 + tx * 4]);
+            const float2 b2 = *reinterpret_cast<const float2 *>(&Bs[buf][k][128 + tx * 2]);
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[10] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y};
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 10; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+        }
+        if (more) {
+            r2s(buf ^ 1);
+            __syncthreads();
+            buf ^= 1;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (i < 4 ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4));
+        if (m >= M) continue;
+        float *row = Cm + (size_t)m * N;
+        const int na = n0 + tx * 4, nb = n0 + 64 + tx * 4, nc = n0 + 128 + tx * 2;
+        if (na + 3 < N) *reinterpret_cast<float4 *>(row + na) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        if (nb + 3 < N) *reinterpret_cast<float4 *>(row + nb) = make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+        if (nc + 1 < N) *reinterpret_cast<float2 *>(row + nc) = make_float2(acc[i][8], acc[i][9]);
+    }
+}
+
+template <int BM>
+static void launch_fwd(const float *X, const float *W, float *H, int64_t M, int64_t K, int64_t N, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(N, FW_BN), (unsigned)ceil_div(M, BM));
+    sgemm_fwd_kernel<BM><<<grid, BM * 2, 0, st>>>(X, W, H, (int)M, (int)N, (int)K);
+}
+
 // second stage of the split wgrad: out[e] = sum_s part[s, e] in ascending s (deterministic)
 __global__ void splitk_reduce_kernel(const float *__restrict__ part, int nsplit, long long elems,
                                      float *__restrict__ out) {
@@ -167,6 +277,24 @@ extern "C" int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int
     if (g_fwd_mode != 1 && tf32x3_eligible(X, H, M, K, N))
         return gemm_tf32x3(X, W, /*b_is_kn=*/1, nullptr, M, K, N, H, workspace, workspace_bytes, as_stream(stream));
     PTK_REQUIRE(g_fwd_mode != 2, PTK_ERR_SHAPE, "gcn_linear_fwd: shape not eligible for the tensor-core path");
+    if ((K % 4) == 0 && (N % 4) == 0 && N >= 64 && (((uintptr_t)X | (uintptr_t)W | (uintptr_t)H) % 16) == 0 &&
+        M < (1LL << 31) && ceil_div(M, 96) <= 65535) {
+        // pick the row-tile height that wastes the least in the last wave (2 resident CTAs per SM)
+        const int64_t slots = 2LL * sm_count();
+        const int64_t nt = ceil_div(N, FW_BN);
+        int best = 128;
+        int64_t best_cost = -1;
+        const int cands[3] = {128, 112, 96};
+        for (int c = 0; c < 3; ++c) {
+            const int64_t cost = ceil_div(ceil_div(M, cands[c]) * nt, slots) * cands[c];
+            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = cands[c]; }
+        }
+        if (best == 128) launch_fwd<128>(X, W, H, M, K, N, as_stream(stream));
+        else if (best == 112) launch_fwd<112>(X, W, H, M, K, N, as_stream(stream));
+        else launch_fwd<96>(X, W, H, M, K, N, as_stream(stream));
+        PTK_CHECK_LAUNCH();
+        return PTK_OK;
+    }
     dim3 grid((unsigned)ceil_div(N, GL_BN), (unsigned)ceil_div(M, GL_BM));
     sgemm_kernel<true, false, false, false><<<grid, GL_THREADS, 0, as_stream(stream)>>>(
         X, K, W, N, H, N, M, N, K, 0, nullptr);
