@@ -115,20 +115,26 @@ __device__ __forceinline__ void hub_cta(const int32_t *__restrict__ rowptr, cons
                                         const float *__restrict__ bias, int relu, float *__restrict__ out,
                                         unsigned hub_block);
 
-// Grid = [hub CTAs | row CTAs]: the hub CTAs have the lowest block ids, so they are scheduled first and
-// their long neighbour lists overlap with the short rows instead of forming a tail.
+// Hub CTAs and row CTAs share one launch; hub CTAs are interleaved at a regular stride (block b is a hub
+// CTA when b % stride == 0) so that their long neighbour lists start early, overlap with the short rows
+// and never monopolise the SMs.
 template <bool VEC>
 __global__ void __launch_bounds__(AG_THREADS)
 gcn_aggregate_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                      const float *__restrict__ val, const int32_t *__restrict__ hubs, int n_hubs, unsigned hub_ctas,
-                     int Nv, const float *__restrict__ in, long long rows, int C, int L,
+                     unsigned hub_stride, int Nv, const float *__restrict__ in, long long rows, int C, int L,
                      const float *__restrict__ bias, int relu, float *__restrict__ out) {
-    if (blockIdx.x < hub_ctas) {
-        hub_cta<VEC>(rowptr, col, val, hubs, n_hubs, Nv, in, C, L, bias, relu, out, blockIdx.x);
-        return;
+    unsigned hubs_before = 0;  // hub CTAs with a block id below this one
+    if (hub_ctas > 0) {
+        const unsigned slot = blockIdx.x / hub_stride;
+        if (blockIdx.x % hub_stride == 0 && slot < hub_ctas) {
+            hub_cta<VEC>(rowptr, col, val, hubs, n_hubs, Nv, in, C, L, bias, relu, out, slot);
+            return;
+        }
+        hubs_before = slot + 1 < hub_ctas ? slot + 1 : hub_ctas;
     }
     const int skip_hubs = hub_ctas > 0;
-    const long long row = (long long)(blockIdx.x - hub_ctas) * AG_WARPS + (threadIdx.x >> 5);
+    const long long row = (long long)(blockIdx.x - hubs_before) * AG_WARPS + (threadIdx.x >> 5);
     if (row >= rows) return;
     const int lane = threadIdx.x & 31;
     const int i = (int)(row % Nv);
@@ -309,10 +315,11 @@ extern "C" int ptk_gcn_aggregate(const int32_t *rowptr, const int32_t *col, cons
     const bool vec = (C % 4 == 0) && ((((uintptr_t)in) | ((uintptr_t)out)) % 16 == 0);
     const unsigned hub_ctas = (hubs && n_hubs > 0) ? (unsigned)(B * n_hubs) : 0u;
     const unsigned grid = hub_ctas + (unsigned)ceil_div(rows, AG_WARPS);
+    const unsigned hub_stride = hub_ctas > 0 ? (grid / hub_ctas > 0 ? grid / hub_ctas : 1u) : 1u;
     if (vec)
-        gcn_aggregate_kernel<true><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, hub_ctas, (int)Nv, in, rows, (int)C, (int)L, bias, relu, out);
+        gcn_aggregate_kernel<true><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, hub_ctas, hub_stride, (int)Nv, in, rows, (int)C, (int)L, bias, relu, out);
     else
-        gcn_aggregate_kernel<false><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, hub_ctas, (int)Nv, in, rows, (int)C, (int)L, bias, relu, out);
+        gcn_aggregate_kernel<false><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, hub_ctas, hub_stride, (int)Nv, in, rows, (int)C, (int)L, bias, relu, out);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }

@@ -129,9 +129,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const uint32_t bar_tempty = smem_u32(&bars[3 * TG_STAGES + TG_NBUF]);  // TMEM buffer drained (8 warps)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * TG_BM;
-    const int n_base = blockIdx.y * TG_BN;
     const int num_kb = (p.K + TG_BK - 1) / TG_BK;
+    // persistent: CTA c processes tiles c, c + gridDim.x, ...; tile t -> (m-tile t / tiles_n, n-tile t % tiles_n).
+    // All pipeline counters (smem stage, TMEM buffer) run across tiles, so the epilogue stores of one
+    // tile overlap the TMA / MMA work of the next.
+    const int tiles_n = (p.N + TG_BN - 1) / TG_BN;
+    const int num_tiles = ((p.M + TG_BM - 1) / TG_BM) * tiles_n;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -160,21 +163,27 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % TG_STAGES;
-                const uint32_t ph = (kb / TG_STAGES) & 1;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                const uint32_t sa = smem_u32(smem + (size_t)s * TG_STAGE_BYTES);
-                mbar_expect_tx(bar_full + 8 * s, TG_A_BYTES + 2 * TG_B_BYTES);
-                tma_load_2d(sa, &map_a, bar_full + 8 * s, kb * TG_BK, m0);
-                tma_load_2d(sa + 2 * TG_A_BYTES, &map_bhi, bar_full + 8 * s, kb * TG_BK, n_base);
-                tma_load_2d(sa + 2 * TG_A_BYTES + TG_B_BYTES, &map_blo, bar_full + 8 * s, kb * TG_BK, n_base);
+            int it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int m0 = (tile / tiles_n) * TG_BM, n_base = (tile % tiles_n) * TG_BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % TG_STAGES;
+                    const uint32_t ph = (it / TG_STAGES) & 1;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    const uint32_t sa = smem_u32(smem + (size_t)s * TG_STAGE_BYTES);
+                    mbar_expect_tx(bar_full + 8 * s, TG_A_BYTES + 2 * TG_B_BYTES);
+                    tma_load_2d(sa, &map_a, bar_full + 8 * s, kb * TG_BK, m0);
+                    tma_load_2d(sa + 2 * TG_A_BYTES, &map_bhi, bar_full + 8 * s, kb * TG_BK, n_base);
+                    tma_load_2d(sa + 2 * TG_A_BYTES + TG_B_BYTES, &map_blo, bar_full + 8 * s, kb * TG_BK, n_base);
+                }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = make_idesc_tf32(TG_BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int total_kb = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) total_kb += num_kb;
+        for (int kb = 0; kb < total_kb; ++kb) {
             const int s = kb % TG_STAGES, b = kb % TG_NBUF;
             mbar_wait(bar_full + 8 * s, (kb / TG_STAGES) & 1);        // B tiles landed
             mbar_wait(bar_conv + 8 * s, (kb / TG_STAGES) & 1);        // A split done
@@ -210,7 +219,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     } else if (warp >= 4 && warp < 8) {
         // ===================== converter warps =====================
         const int ct = threadIdx.x - 128;  // 0..127
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int total_kb = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) total_kb += num_kb;
+        for (int kb = 0; kb < total_kb; ++kb) {
             const int s = kb % TG_STAGES;
             mbar_wait(bar_full + 8 * s, (kb / TG_STAGES) & 1);
             float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * TG_STAGE_BYTES);
@@ -235,6 +246,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // ===================== drain + epilogue warps =====================
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int half = (warp - 8) >> 2;       // column half: [0,80) or [80,160)
+        int it = 0;                             // running chunk index across tiles
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * TG_BM, n_base = (tile % tiles_n) * TG_BN;
         const int row = m0 + q * 32 + lane;
         float acc[80];
 #pragma unroll
@@ -260,9 +274,9 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     if (nb0 + j < p.N && am[j] > 0.f) mbits[j >> 5] |= 1u << (j & 31);
             }
         }
-        for (int kb = 0; kb < num_kb; ++kb) {
-            const int b = kb % TG_NBUF;
-            mbar_wait(bar_tfull + 8 * b, (kb / TG_NBUF) & 1);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+            const int b = it % TG_NBUF;
+            mbar_wait(bar_tfull + 8 * b, (it / TG_NBUF) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * TG_BN + half * 80);
 #pragma unroll
@@ -302,6 +316,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     if (nb + j < p.N) dst[j] = acc[j];
             }
         }
+        }  // tile loop
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -614,7 +629,8 @@ int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act
     if (dbg < 0) { const char *e = getenv("PTK_TG_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.dbg = dbg;
     const size_t smem = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024;
-    dim3 grid((unsigned)ceil_div(M, TG_BM), (unsigned)ceil_div(N, TG_BN));
+    const int64_t num_tiles = ceil_div(M, TG_BM) * ceil_div(N, TG_BN);
+    dim3 grid((unsigned)(num_tiles < sm_count() ? num_tiles : sm_count()));
     static bool attr_set = false;
     if (!attr_set) {
         PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
