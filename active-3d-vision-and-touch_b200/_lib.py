@@ -8,6 +8,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libptk_b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ptk.h")
 
+CHAMFER_FILTER, CHAMFER_EXACT = 0, 1
 PTK_OK, PTK_ERR_SHAPE, PTK_ERR_ALIGN, PTK_ERR_ARCH, PTK_ERR_CUDA, PTK_ERR_WORKSPACE = 0, -1, -2, -3, -4, -5
 
 _vp, _i64, _i32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t
@@ -18,6 +19,9 @@ SIGNATURES = {
     "ptk_last_error": (C.c_char_p, []),
     "ptk_device_info": (C.c_int, [C.c_int] + [C.POINTER(C.c_int)] * 6),
     "ptk_chamfer_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "ptk_chamfer_set_algo": (C.c_int, [C.c_int]),
+    "ptk_chamfer_get_algo": (C.c_int, []),
+    "ptk_chamfer_rescued": (C.c_int, [_vp, _i64, _i64, _i64, C.POINTER(_i64), _vp]),
     "ptk_knn1_fwd": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _sz, _vp]),
     "ptk_chamfer_fwd": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ptk_chamfer_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),

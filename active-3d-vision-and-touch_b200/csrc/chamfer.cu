@@ -23,14 +23,56 @@
 //     the low word makes the lowest index win ties -- deterministic.
 //   * a second small kernel unpacks the keys and does the fused mean reduction in a fixed order
 //     (deterministic, no float atomics).
-#include "chamfer_kernel.cuh"
+//   * default algorithm (PTK_CHAMFER_FILTER): the scan above is run on the 3-FFMA expansion
+//     |t|^2 - 2 q.t with packed FFMA2 instructions as a FILTER (chamfer_kernel2.cuh); the recorded
+//     chunk is re-evaluated with the defining arithmetic and the few queries whose runner-up chunk is
+//     within the proven error bound are re-scanned exactly (chamfer_nn_exact2_kernel, list mode).
+//     Results are bit-identical to PTK_CHAMFER_EXACT (the 6-op scan, kept selectable for checks).
+#include "chamfer_kernel2.cuh"
 
 namespace ptk {
 
 // library configuration of the kernel template (tuned with tools/chamfer_tune.cu)
 constexpr int CH_THREADS = 128;
 constexpr int CH_CHUNK = 16;
-constexpr int CH_MINB = 3;
+constexpr int CH_MINB = 3;   // exact scan
+constexpr int CH_MINB_F = 4; // filter scan
+constexpr int CH_TT_F = 2048;
+
+static int g_chamfer_algo = PTK_CHAMFER_FILTER;
+
+// workspace: [PairAux B][keys_x B*P1][keys_y B*P2][rescue_x B*P1][rescue_y B*P2][flag_x B*P1][flag_y B*P2][count 2B]
+struct ChamferWs {
+    PairAux *aux;
+    u64 *keys_x, *keys_y;
+    int *rescue_x, *rescue_y;
+    unsigned int *flag_x, *flag_y, *count;
+};
+
+static size_t chamfer_ws_bytes(int64_t B, int64_t P1, int64_t P2) {
+    return sizeof(PairAux) * (size_t)B + (size_t)B * (size_t)(P1 + P2) * (8 + 4 + 4) + 8 * (size_t)B;
+}
+
+static ChamferWs carve(void *workspace, int64_t B, int64_t P1, int64_t P2) {
+    ChamferWs w;
+    char *p = reinterpret_cast<char *>(workspace);
+    w.aux = reinterpret_cast<PairAux *>(p);
+    p += sizeof(PairAux) * (size_t)B;
+    w.keys_x = reinterpret_cast<u64 *>(p);
+    p += 8 * (size_t)B * P1;
+    w.keys_y = reinterpret_cast<u64 *>(p);
+    p += 8 * (size_t)B * P2;
+    w.rescue_x = reinterpret_cast<int *>(p);
+    p += 4 * (size_t)B * P1;
+    w.rescue_y = reinterpret_cast<int *>(p);
+    p += 4 * (size_t)B * P2;
+    w.flag_x = reinterpret_cast<unsigned int *>(p);
+    p += 4 * (size_t)B * P1;
+    w.flag_y = reinterpret_cast<unsigned int *>(p);
+    p += 4 * (size_t)B * P2;
+    w.count = reinterpret_cast<unsigned int *>(p);
+    return w;
+}
 
 // Unpack keys -> (dist, idx) and reduce the per-cloud means in a fixed order.
 // grid = B, block = 512.  cham may be NULL (plain knn).
@@ -136,11 +178,11 @@ struct NNPlan {
     int split_len;  // targets per split (multiple of CH_CHUNK)
 };
 
-static NNPlan plan_nn(int64_t B, int64_t Pq_max, int64_t Pt_max, int ndir) {
+static NNPlan plan_nn(int64_t B, int64_t Pq_max, int64_t Pt_max, int ndir, int minb) {
     // Aim for >= 4 waves of CTAs (CH_MINB resident per SM) so that the last, partial wave costs little.
     // Prefer R = 8 queries per thread (fewest shared-memory loads per evaluation) and get the CTA count
     // from splitting the target range; fall back to fewer queries per thread for tiny clouds.
-    const int64_t want = 4LL * sm_count() * CH_MINB;
+    const int64_t want = 4LL * sm_count() * minb;
     NNPlan p;
     auto ctas = [&](int R) { return B * ndir * ceil_div(Pq_max, (int64_t)CH_THREADS * R); };
     const int64_t max_split = ceil_div(Pt_max, (int64_t)CH_CHUNK * 16);  // >= 256 targets per split
@@ -157,35 +199,56 @@ static NNPlan plan_nn(int64_t B, int64_t Pq_max, int64_t Pt_max, int ndir) {
     return p;
 }
 
-static int launch_nn(const float *x, const float *y, int64_t B, int64_t P1, int64_t P2,
-                     unsigned long long *keys_x, unsigned long long *keys_y, int dir_only,
-                     cudaStream_t st) {
+static int launch_nn(const float *x, const float *y, int64_t B, int64_t P1, int64_t P2, const ChamferWs &w,
+                     int dir_only, cudaStream_t st) {
     const int ndir = dir_only >= 0 ? 1 : 2;
     const int64_t Pq = dir_only == 0 ? P1 : (dir_only == 1 ? P2 : (P1 > P2 ? P1 : P2));
     const int64_t Pt = dir_only == 0 ? P2 : (dir_only == 1 ? P1 : (P1 > P2 ? P1 : P2));
-    NNPlan p = plan_nn(B, Pq, Pt, ndir);
+    const bool filter = g_chamfer_algo == PTK_CHAMFER_FILTER;
+    NNPlan p = plan_nn(B, Pq, Pt, ndir, filter ? CH_MINB_F : CH_MINB);
+    u64 *keys_x = dir_only == 1 ? nullptr : w.keys_x;
+    u64 *keys_y = dir_only == 0 ? nullptr : w.keys_y;
     if (p.n_split > 1) {
-        if (keys_x) PTK_CHECK_CUDA(cudaMemsetAsync(keys_x, 0xff, sizeof(unsigned long long) * B * P1, st));
-        if (keys_y) PTK_CHECK_CUDA(cudaMemsetAsync(keys_y, 0xff, sizeof(unsigned long long) * B * P2, st));
+        if (keys_x) PTK_CHECK_CUDA(cudaMemsetAsync(keys_x, 0xff, sizeof(u64) * B * P1, st));
+        if (keys_y) PTK_CHECK_CUDA(cudaMemsetAsync(keys_y, 0xff, sizeof(u64) * B * P2, st));
+        if (filter)  // flag_x and flag_y are adjacent
+            PTK_CHECK_CUDA(cudaMemsetAsync(w.flag_x, 0, sizeof(unsigned int) * B * (P1 + P2), st));
     }
     dim3 grid((unsigned)ceil_div(Pq, (int64_t)CH_THREADS * p.R), (unsigned)p.n_split,
               (unsigned)(B * ndir));
     PTK_REQUIRE(grid.z <= 65535 && grid.y <= 65535, PTK_ERR_SHAPE,
                 "chamfer: batch %lld too large for one launch (max 32767 clouds)", (long long)B);
-    switch (p.R) {
-        case 8:
-            chamfer_nn_kernel<8, CH_CHUNK, CH_THREADS, CH_MINB><<<grid, CH_THREADS, 0, st>>>(x, y, (int)P1, (int)P2, p.split_len,
-                                                               p.n_split, keys_x, keys_y, dir_only);
-            break;
-        case 4:
-            chamfer_nn_kernel<4, CH_CHUNK, CH_THREADS, CH_MINB><<<grid, CH_THREADS, 0, st>>>(x, y, (int)P1, (int)P2, p.split_len,
-                                                               p.n_split, keys_x, keys_y, dir_only);
-            break;
-        default:
-            chamfer_nn_kernel<2, CH_CHUNK, CH_THREADS, CH_MINB><<<grid, CH_THREADS, 0, st>>>(x, y, (int)P1, (int)P2, p.split_len,
-                                                               p.n_split, keys_x, keys_y, dir_only);
-            break;
+    const int iP1 = (int)P1, iP2 = (int)P2;
+    if (filter) {
+        chamfer_bounds_kernel<<<(unsigned)B, 1024, 0, st>>>(x, y, iP1, iP2, w.aux, w.count);
+        PTK_CHECK_LAUNCH();
+#define PTK_FILTER(RR)                                                                                         \
+    chamfer_nn_filter_kernel<RR, CH_CHUNK, CH_THREADS, CH_MINB_F, CH_TT_F, true><<<grid, CH_THREADS, 0, st>>>(  \
+        x, y, iP1, iP2, p.split_len, p.n_split, w.aux, w.keys_x, w.keys_y, dir_only, w.rescue_x, w.rescue_y,   \
+        w.count, w.flag_x, w.flag_y)
+        switch (p.R) {
+            case 8: PTK_FILTER(8); break;
+            case 4: PTK_FILTER(4); break;
+            default: PTK_FILTER(2); break;
+        }
+#undef PTK_FILTER
+        PTK_CHECK_LAUNCH();
+        // rescue pass over the queued (ambiguous) queries; CTAs beyond the list length exit at once
+        dim3 rgrid((unsigned)ceil_div(Pq, (int64_t)CH_THREADS * 8), (unsigned)p.n_split, (unsigned)(B * ndir));
+        chamfer_nn_exact2_kernel<8, CH_CHUNK, CH_THREADS, CH_MINB><<<rgrid, CH_THREADS, 0, st>>>(
+            x, y, iP1, iP2, p.split_len, p.n_split, w.keys_x, w.keys_y, dir_only, w.rescue_x, w.rescue_y, w.count);
+        PTK_CHECK_LAUNCH();
+        return PTK_OK;
     }
+#define PTK_EXACT(RR)                                                                            \
+    chamfer_nn_exact2_kernel<RR, CH_CHUNK, CH_THREADS, CH_MINB><<<grid, CH_THREADS, 0, st>>>(     \
+        x, y, iP1, iP2, p.split_len, p.n_split, w.keys_x, w.keys_y, dir_only, nullptr, nullptr, nullptr)
+    switch (p.R) {
+        case 8: PTK_EXACT(8); break;
+        case 4: PTK_EXACT(4); break;
+        default: PTK_EXACT(2); break;
+    }
+#undef PTK_EXACT
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }
@@ -196,7 +259,34 @@ using namespace ptk;
 
 extern "C" size_t ptk_chamfer_workspace_bytes(int64_t B, int64_t P1, int64_t P2) {
     if (B <= 0 || P1 <= 0 || P2 <= 0) return 0;
-    return sizeof(unsigned long long) * (size_t)B * (size_t)(P1 + P2);
+    return chamfer_ws_bytes(B, P1, P2);
+}
+
+extern "C" int ptk_chamfer_set_algo(int algo) {
+    PTK_REQUIRE(algo == PTK_CHAMFER_FILTER || algo == PTK_CHAMFER_EXACT, PTK_ERR_SHAPE,
+                "chamfer_set_algo: unknown algorithm %d", algo);
+    g_chamfer_algo = algo;
+    return PTK_OK;
+}
+
+extern "C" int ptk_chamfer_get_algo(void) { return g_chamfer_algo; }
+
+extern "C" int ptk_chamfer_rescued(const void *workspace, int64_t B, int64_t P1, int64_t P2,
+                                   int64_t *n_rescued, ptk_stream_t stream) {
+    PTK_REQUIRE(workspace && n_rescued && B > 0 && P1 > 0 && P2 > 0, PTK_ERR_SHAPE, "chamfer_rescued: bad argument");
+    const ChamferWs w = carve(const_cast<void *>(workspace), B, P1, P2);
+    cudaStream_t st = as_stream(stream);
+    unsigned int *h = nullptr;
+    PTK_CHECK_CUDA(cudaMallocHost(&h, sizeof(unsigned int) * 2 * B));
+    cudaError_t e = cudaMemcpyAsync(h, w.count, sizeof(unsigned int) * 2 * B, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    int64_t n = 0;
+    if (e == cudaSuccess)
+        for (int64_t i = 0; i < 2 * B; ++i) n += h[i];
+    cudaFreeHost(h);
+    PTK_CHECK_CUDA(e);
+    *n_rescued = g_chamfer_algo == PTK_CHAMFER_FILTER ? n : 0;
+    return PTK_OK;
 }
 
 static int check_clouds(const void *x, const void *y, int64_t B, int64_t P1, int64_t P2) {
@@ -214,13 +304,14 @@ extern "C" int ptk_knn1_fwd(const float *p1, const float *p2, int64_t B, int64_t
                             ptk_stream_t stream) {
     int rc = check_clouds(p1, p2, B, P1, P2);
     if (rc) return rc;
-    PTK_REQUIRE(workspace && workspace_bytes >= sizeof(unsigned long long) * (size_t)B * (size_t)P1,
-                PTK_ERR_WORKSPACE, "knn1: workspace too small");
+    PTK_REQUIRE(workspace && workspace_bytes >= chamfer_ws_bytes(B, P1, P2), PTK_ERR_WORKSPACE,
+                "knn1: workspace too small (%zu < %zu)", workspace_bytes, chamfer_ws_bytes(B, P1, P2));
+    PTK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, PTK_ERR_ALIGN, "knn1: workspace must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
-    auto *keys = reinterpret_cast<unsigned long long *>(workspace);
-    rc = launch_nn(p1, p2, B, P1, P2, keys, nullptr, 0, st);
+    const ChamferWs w = carve(workspace, B, P1, P2);
+    rc = launch_nn(p1, p2, B, P1, P2, w, 0, st);
     if (rc) return rc;
-    chamfer_finalize_kernel<<<(unsigned)B, 512, 0, st>>>(keys, nullptr, (int)P1, (int)P2, dist, idx,
+    chamfer_finalize_kernel<<<(unsigned)B, 512, 0, st>>>(w.keys_x, nullptr, (int)P1, (int)P2, dist, idx,
                                                          nullptr, nullptr, nullptr);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
@@ -236,12 +327,13 @@ extern "C" int ptk_chamfer_fwd(const float *x, const float *y, int64_t B, int64_
     PTK_REQUIRE(workspace && workspace_bytes >= ptk_chamfer_workspace_bytes(B, P1, P2),
                 PTK_ERR_WORKSPACE, "chamfer_fwd: workspace too small (%zu < %zu)", workspace_bytes,
                 ptk_chamfer_workspace_bytes(B, P1, P2));
+    PTK_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 15) == 0, PTK_ERR_ALIGN,
+                "chamfer_fwd: workspace must be 16-byte aligned");
     cudaStream_t st = as_stream(stream);
-    auto *keys_x = reinterpret_cast<unsigned long long *>(workspace);
-    auto *keys_y = keys_x + (size_t)B * P1;
-    rc = launch_nn(x, y, B, P1, P2, keys_x, keys_y, -1, st);
+    const ChamferWs w = carve(workspace, B, P1, P2);
+    rc = launch_nn(x, y, B, P1, P2, w, -1, st);
     if (rc) return rc;
-    chamfer_finalize_kernel<<<(unsigned)B, 512, 0, st>>>(keys_x, keys_y, (int)P1, (int)P2, dist_x,
+    chamfer_finalize_kernel<<<(unsigned)B, 512, 0, st>>>(w.keys_x, w.keys_y, (int)P1, (int)P2, dist_x,
                                                          idx_x, dist_y, idx_y, cham);
     PTK_CHECK_LAUNCH();
     return PTK_OK;

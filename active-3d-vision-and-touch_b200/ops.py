@@ -37,6 +37,32 @@ def _ws(nbytes, device):
 
 
 # ------------------------------------------------------------------------------------- Chamfer / KNN
+def set_chamfer_algo(name):
+    """'filter' (default: 3-FFMA expansion filter + exact recheck) or 'exact' (6-op scan); same results."""
+    algo = {"filter": _lib.CHAMFER_FILTER, "exact": _lib.CHAMFER_EXACT}[name]
+    _lib.check(_lib.lib().ptk_chamfer_set_algo(algo), "ptk_chamfer_set_algo")
+
+
+def chamfer_rescued(x, y):
+    """Diagnostics: run the forward NN scan on (x, y) and return how many of the B*(P1+P2) queries the
+    filter could not decide (near or exact ties across chunks) and handed to the exact rescue scan."""
+    _need_cuda(x, y)
+    x, y = _f32c(x), _f32c(y)
+    B, P1, _ = x.shape
+    P2 = y.shape[1]
+    L = _lib.lib()
+    idx_x = torch.empty(B, P1, dtype=torch.int32, device=x.device)
+    idx_y = torch.empty(B, P2, dtype=torch.int32, device=x.device)
+    cham = torch.empty(B, dtype=torch.float32, device=x.device)
+    ws = _ws(L.ptk_chamfer_workspace_bytes(B, P1, P2), x.device)
+    n = C.c_int64(0)
+    with torch.cuda.device(x.device):
+        _lib.check(L.ptk_chamfer_fwd(_p(x), _p(y), B, P1, P2, None, _p(idx_x), None, _p(idx_y), _p(cham),
+                                     _p(ws), ws.numel(), _stream()), "ptk_chamfer_fwd")
+        _lib.check(L.ptk_chamfer_rescued(_p(ws), B, P1, P2, C.byref(n), _stream()), "ptk_chamfer_rescued")
+    return int(n.value)
+
+
 class _Chamfer(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, y):
@@ -91,7 +117,7 @@ def knn1(p1, p2):
     L = _lib.lib()
     dist = torch.empty(B, P1, dtype=torch.float32, device=p1.device)
     idx = torch.empty(B, P1, dtype=torch.int32, device=p1.device)
-    ws = _ws(8 * B * P1, p1.device)
+    ws = _ws(L.ptk_chamfer_workspace_bytes(B, P1, P2), p1.device)
     with torch.cuda.device(p1.device):
         _lib.check(L.ptk_knn1_fwd(_p(p1), _p(p2), B, P1, P2, _p(dist), _p(idx), _p(ws), ws.numel(), _stream()),
                    "ptk_knn1_fwd")

@@ -56,7 +56,19 @@ int ptk_device_info(int device, int *sm_count, int *clock_khz, int *l2_bytes, in
  *   PyTorch3D's CUDA kernel executes), strict '<' scanning targets in ascending order: the lowest
  *   index wins exact ties.  cham[b] = mean_i dist_x[b,i] + mean_j dist_y[b,j].
  * ---------------------------------------------------------------------------------------------- */
-size_t ptk_chamfer_workspace_bytes(int64_t B, int64_t P1, int64_t P2);
+size_t ptk_chamfer_workspace_bytes(int64_t B, int64_t P1, int64_t P2); /* 16-byte aligned workspace */
+
+/* Nearest-neighbour scan algorithm (process-wide; both give bit-identical results):
+ *   PTK_CHAMFER_FILTER (default)  3-FFMA expansion filter on packed FP32x2 + exact recheck/rescue
+ *   PTK_CHAMFER_EXACT             the defining 6-op arithmetic for every (query, target) pair */
+#define PTK_CHAMFER_FILTER 0
+#define PTK_CHAMFER_EXACT 1
+int ptk_chamfer_set_algo(int algo);
+int ptk_chamfer_get_algo(void);
+/* Diagnostics (synchronises `stream`): number of queries of the last forward that used `workspace`
+ * whose filter result was ambiguous and went through the exact rescue scan. */
+int ptk_chamfer_rescued(const void *workspace, int64_t B, int64_t P1, int64_t P2, int64_t *n_rescued,
+                        ptk_stream_t stream);
 
 /* One direction: for every p1[b,i] its nearest p2[b,j].  dist (B,P1) and/or idx (B,P1) may be NULL. */
 int ptk_knn1_fwd(const float *p1, const float *p2, int64_t B, int64_t P1, int64_t P2, float *dist,

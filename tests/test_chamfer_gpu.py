@@ -78,6 +78,79 @@ def test_duplicate_points_and_grid_ties(oracle):
     assert rel_err(cham, ocham) < TOL
 
 
+def _clouds(kind, rng, B, P1, P2):
+    """Adversarial inputs for the expansion filter (chamfer_kernel2.cuh)."""
+    if kind == "far_from_origin":      # translation to the box centre must absorb the offset
+        c = np.array([1000.0, -250.0, 40.0], np.float32)
+        return (c + 0.01 * rng.standard_normal((B, P1, 3))).astype(np.float32), \
+               (c + 0.01 * rng.standard_normal((B, P2, 3))).astype(np.float32)
+    if kind == "tiled_x4":             # data_loaders.py:80-87 tiles short clouds: exact duplicates far apart
+        base = rng.random((B, P2 // 4, 3), np.float32)
+        return rng.random((B, P1, 3), np.float32), np.concatenate([base] * 4, 1)
+    if kind == "thin_rod":             # config-1-like: tiny NN distances compared with the extent
+        x = rng.random((B, P1, 3), np.float32) * np.array([0.004, 0.01, 0.19], np.float32)
+        y = rng.random((B, P2, 3), np.float32) * np.array([0.004, 0.01, 0.19], np.float32)
+        return x.astype(np.float32), y.astype(np.float32)
+    if kind == "huge_values":          # squares overflow: filter must switch itself off
+        return (rng.standard_normal((B, P1, 3)) * 1e19).astype(np.float32), \
+               (rng.standard_normal((B, P2, 3)) * 1e19).astype(np.float32)
+    if kind == "tiny_values":          # squares underflow
+        return (rng.standard_normal((B, P1, 3)) * 1e-20).astype(np.float32), \
+               (rng.standard_normal((B, P2, 3)) * 1e-20).astype(np.float32)
+    if kind == "one_outlier":          # a single far point inflates the radius (and the threshold)
+        x = rng.random((B, P1, 3), np.float32); y = rng.random((B, P2, 3), np.float32)
+        x[:, 0] = 1e4
+        return x, y
+    if kind == "identical":            # x == y: every query has distance 0 to itself
+        x = rng.random((B, P1, 3), np.float32)
+        return x, x.copy()
+    raise KeyError(kind)
+
+
+@pytest.mark.parametrize("kind", ["far_from_origin", "tiled_x4", "thin_rod", "huge_values", "tiny_values",
+                                  "one_outlier", "identical"])
+@pytest.mark.parametrize("B,P1,P2", [(2, 1500, 2000), (1, 4000, 4000)])
+def test_filter_adversarial_vs_oracle(oracle, kind, B, P1, P2):
+    rng = np.random.default_rng(sum(map(ord, kind)) + P1)
+    if kind == "identical":
+        P2 = P1
+    x, y = _clouds(kind, rng, B, P1, P2)
+    cham, ix, iy = run(x, y)
+    ocham, odx, oix, ody, oiy = oracle.chamfer_fwd(x, y, use_fma=True)
+    assert np.array_equal(ix, oix) and np.array_equal(iy, oiy)
+    d, i = ptk_b200.ops.knn1(torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda())
+    assert np.array_equal(d.cpu().numpy(), odx) and np.array_equal(i.cpu().numpy(), oix)  # distances bit-exact
+    if np.isfinite(ocham).all():
+        assert rel_err(cham, ocham) < TOL
+
+
+def test_non_finite_inputs_take_the_exact_path(oracle):
+    rng = np.random.default_rng(11)
+    x = rng.random((2, 700, 3), np.float32); y = rng.random((2, 900, 3), np.float32)
+    x[0, 5, 1] = np.nan; y[0, 17, 0] = np.inf; y[1, 3, 2] = -np.inf
+    _, ix, iy = run(x, y)
+    _, _, oix, _, oiy = oracle.chamfer_fwd(x, y, use_fma=True)
+    assert np.array_equal(ix, oix) and np.array_equal(iy, oiy)
+
+
+def test_filter_and_exact_algorithms_agree_bitwise():
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand(8, 5000, 3, device="cuda", generator=g) - 0.5
+    y = torch.rand(8, 7000, 3, device="cuda", generator=g) - 0.5
+    try:
+        ptk_b200.ops.set_chamfer_algo("exact")
+        c0, ix0, iy0 = ptk_b200.ops.chamfer(x, y)
+        d0, i0 = ptk_b200.ops.knn1(x, y)
+    finally:
+        ptk_b200.ops.set_chamfer_algo("filter")
+    c1, ix1, iy1 = ptk_b200.ops.chamfer(x, y)
+    d1, i1 = ptk_b200.ops.knn1(x, y)
+    assert torch.equal(ix0, ix1) and torch.equal(iy0, iy1) and torch.equal(c0, c1)
+    assert torch.equal(d0, d1) and torch.equal(i0, i1)
+    n = ptk_b200.ops.chamfer_rescued(x, y)
+    assert 0 < n < 0.05 * 8 * 12000   # uniform clouds: ~1 % of the queries need the exact rescue
+
+
 def test_only_y_needs_grad(oracle):
     # autoencoder case (reconstruction/autoencoder/train.py:145-151): sampled cloud detached
     rng = np.random.default_rng(3)
