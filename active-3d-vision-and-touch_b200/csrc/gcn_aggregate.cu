@@ -13,6 +13,8 @@
 // (degree > HUB_DEG: the touch-chart centre vertices, degree 1153 -- utils.py:95-98,126-128) are
 // processed by a whole CTA (8 warps split the neighbour list, shared-memory reduction) so that
 // they do not become the tail of the launch.
+#include <stdlib.h>
+
 #include "ptk_common.cuh"
 
 namespace ptk {
@@ -241,6 +243,288 @@ __device__ __forceinline__ void hub_cta(const int32_t *__restrict__ rowptr, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tile kernel (the fast path: C % 4 == 0, at most 96 aggregated float4 groups).
+//
+// ncu on the one-warp-per-row kernel above (B=256, N=1949, C=300, L=99): DRAM traffic equals the
+// algorithmic bytes, but only 35 % of the HBM rate is reached -- 511 warp instructions per row, mostly
+// index arithmetic, shuffles and 64-bit divisions, and a serial rowptr -> col -> neighbour load chain.
+// This kernel removes both:
+//   * a CTA owns TV consecutive vertices and BG consecutive batch elements.  The graph is the same for
+//     every batch element, so each warp stages the (byte offset, weight) list of its row ONCE in its
+//     private shared-memory strip and replays it for the BG batch elements with 128-bit broadcast loads;
+//   * per neighbour: 1/4 LDS.128 x2, one address add, one LDG.128, four FFMA; eight neighbour rows in
+//     flight per lane, the pass-through part of the row is requested before the gather starts;
+//   * the 8 warps of a CTA work on neighbouring rows of the same batch element at the same time, so the
+//     neighbour rows they share (19-vertex charts) are served by L1;
+//   * rows of degree > HUB_DEG are left to dedicated hub CTAs at the front of the grid (8 warps split the
+//     neighbour list, fixed-order shared-memory reduction => deterministic).
+constexpr int AT_STRIP = 128;  // staged neighbours per warp (= HUB_DEG: a non-hub row fits)
+
+template <int NG>
+__device__ __forceinline__ void strip_gather(const uint32_t *__restrict__ s_off, const float *__restrict__ s_w,
+                                             int n4, const char *const (&base)[NG], float (&acc)[NG][4]) {
+    // n4: staged entries, a multiple of 4 (padding has weight 0 and a valid offset).  base[n] already
+    // includes the lane's channel-group offset; lanes beyond the last aggregated group are clamped onto it
+    // (same cache lines, result discarded), which keeps the loop free of divergent branches.
+    int k = 0;
+    for (; k + 8 <= n4; k += 8) {
+        const uint4 o0 = *reinterpret_cast<const uint4 *>(s_off + k), o1 = *reinterpret_cast<const uint4 *>(s_off + k + 4);
+        const float4 w0 = *reinterpret_cast<const float4 *>(s_w + k), w1 = *reinterpret_cast<const float4 *>(s_w + k + 4);
+        const uint32_t off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
+        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int n = 0; n < NG; ++n) {
+            float4 a[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) a[u] = *reinterpret_cast<const float4 *>(base[n] + off[u]);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                acc[n][0] = fmaf(w[u], a[u].x, acc[n][0]); acc[n][1] = fmaf(w[u], a[u].y, acc[n][1]);
+                acc[n][2] = fmaf(w[u], a[u].z, acc[n][2]); acc[n][3] = fmaf(w[u], a[u].w, acc[n][3]);
+            }
+        }
+    }
+    if (k < n4) {
+        const uint4 o0 = *reinterpret_cast<const uint4 *>(s_off + k);
+        const float4 w0 = *reinterpret_cast<const float4 *>(s_w + k);
+        const uint32_t off[4] = {o0.x, o0.y, o0.z, o0.w};
+        const float w[4] = {w0.x, w0.y, w0.z, w0.w};
+#pragma unroll
+        for (int n = 0; n < NG; ++n) {
+            float4 a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = *reinterpret_cast<const float4 *>(base[n] + off[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                acc[n][0] = fmaf(w[u], a[u].x, acc[n][0]); acc[n][1] = fmaf(w[u], a[u].y, acc[n][1]);
+                acc[n][2] = fmaf(w[u], a[u].z, acc[n][2]); acc[n][3] = fmaf(w[u], a[u].w, acc[n][3]);
+            }
+        }
+    }
+}
+
+// Stage entries [e0, e0+cnt) of a row into the warp's strip (cnt <= AT_STRIP), padded to a multiple of 4.
+__device__ __forceinline__ int strip_stage(const int32_t *__restrict__ col, const float *__restrict__ val, int e0,
+                                           int cnt, uint32_t row_bytes, uint32_t *s_off, float *s_w) {
+    const int lane = threadIdx.x & 31;
+    const int n4 = (cnt + 3) & ~3;
+    __syncwarp();
+    for (int e = lane; e < n4; e += 32) {
+        const bool real = e < cnt;
+        s_off[e] = (uint32_t)col[e0 + (real ? e : 0)] * row_bytes;
+        s_w[e] = real ? val[e0 + e] : 0.f;
+    }
+    __syncwarp();
+    return n4;
+}
+
+// Epilogue of one output row: aggregated groups (+bias, boundary group mixes in the pass-through channels).
+template <int NG>
+__device__ __forceinline__ void row_epilogue(const float (&acc)[NG][4], const bool (&on)[NG], const float *__restrict__ self,
+                                             float *__restrict__ o, const float *__restrict__ bias, int L, int relu) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int n = 0; n < NG; ++n) {
+        if (!on[n]) continue;
+        const int c0 = (lane + 32 * n) * 4;
+        float r[4] = {acc[n][0], acc[n][1], acc[n][2], acc[n][3]};
+        if (bias) {
+            const float4 bv = *reinterpret_cast<const float4 *>(bias + c0);
+            r[0] += bv.x; r[1] += bv.y; r[2] += bv.z; r[3] += bv.w;
+        }
+        if (c0 + 4 > L) {  // boundary group: channels >= L pass through
+            const float4 s = *reinterpret_cast<const float4 *>(self + c0);
+            const float sv[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (c0 + k >= L) r[k] = sv[k];
+        }
+        if (relu) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r[k] = fmaxf(r[k], 0.f);
+        }
+        __stcs(reinterpret_cast<float4 *>(o + c0), make_float4(r[0], r[1], r[2], r[3]));
+    }
+}
+
+__device__ __forceinline__ float4 relu4(float4 s, int relu) {
+    if (relu) {
+        s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f);
+    }
+    return s;
+}
+
+template <int NG>
+__global__ void __launch_bounds__(AG_THREADS, 4)
+gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                          const float *__restrict__ val, const int32_t *__restrict__ hubs, int n_hubs,
+                          unsigned hub_ctas, int Nv, const float *__restrict__ in, int B, int C, int L,
+                          const float *__restrict__ bias, int relu, float *__restrict__ out, int TV, int BG,
+                          int n_tiles) {
+    __shared__ __align__(16) uint32_t s_off[AG_WARPS][AT_STRIP];
+    __shared__ __align__(16) float s_w[AG_WARPS][AT_STRIP];
+    __shared__ __align__(16) float s_part[AG_WARPS][NG * 32 * 4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ngroups = C >> 2;
+    const int gath = (L + 3) >> 2;
+    const uint32_t row_bytes = (uint32_t)C * 4u;
+    bool on[NG];
+    uint32_t voff[NG];  // byte offset of the lane's channel group (clamped to the last aggregated group)
+#pragma unroll
+    for (int n = 0; n < NG; ++n) {
+        on[n] = lane + 32 * n < gath;
+        voff[n] = (uint32_t)min(lane + 32 * n, gath - 1) * 16u;
+    }
+    const size_t bstride = (size_t)Nv * C;  // floats per batch element
+
+    if (blockIdx.x < hub_ctas) {
+        // ---- one (batch element, hub row): the warps split the neighbour list
+        const int i = hubs[blockIdx.x % n_hubs];
+        const int b = blockIdx.x / n_hubs;
+        const int beg = rowptr[i], end = rowptr[i + 1];
+        const int per = (((end - beg) + AG_WARPS - 1) / AG_WARPS + 3) & ~3;
+        const int wbeg = min(end, beg + warp * per), wend = min(end, wbeg + per);
+        const char *base[NG];
+#pragma unroll
+        for (int n = 0; n < NG; ++n) base[n] = reinterpret_cast<const char *>(in + b * bstride) + voff[n];
+        const float *self = in + b * bstride + (size_t)i * C;
+        float *o = out + b * bstride + (size_t)i * C;
+        float acc[NG][4];
+#pragma unroll
+        for (int n = 0; n < NG; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+        for (int e0 = wbeg; e0 < wend; e0 += AT_STRIP) {
+            const int n4 = strip_stage(col, val, e0, min(AT_STRIP, wend - e0), row_bytes, s_off[warp], s_w[warp]);
+            strip_gather<NG>(s_off[warp], s_w[warp], n4, base, acc);
+        }
+#pragma unroll
+        for (int n = 0; n < NG; ++n)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s_part[warp][(n * 32 + lane) * 4 + k] = acc[n][k];
+        __syncthreads();
+        if (warp == 0) {
+#pragma unroll
+            for (int n = 0; n < NG; ++n)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    float t = 0.f;
+                    for (int w = 0; w < AG_WARPS; ++w) t += s_part[w][(n * 32 + lane) * 4 + k];
+                    acc[n][k] = t;
+                }
+            row_epilogue<NG>(acc, on, self, o, bias, L, relu);
+        } else {
+            for (int v = gath + (warp - 1) * 32 + lane; v < ngroups; v += (AG_WARPS - 1) * 32)
+                __stcs(reinterpret_cast<float4 *>(o + v * 4), relu4(__ldcs(reinterpret_cast<const float4 *>(self + v * 4)), relu));
+        }
+        return;
+    }
+
+    const unsigned t = blockIdx.x - hub_ctas;
+    const int i0 = (int)(t % (unsigned)n_tiles) * TV;
+    const int b0 = (int)(t / (unsigned)n_tiles) * BG;
+    const int nb = min(B, b0 + BG) - b0;
+    const int i1 = min(Nv, i0 + TV);
+    const int npass = ngroups - gath;  // pure pass-through groups
+    const bool pass0 = lane < npass, pass1 = 32 + lane < npass;
+    const int pv0 = (gath + lane) * 4, pv1 = (gath + 32 + lane) * 4;  // float offsets inside the row
+    for (int i = i0 + warp; i < i1; i += AG_WARPS) {
+        const int beg = rowptr[i], end = rowptr[i + 1];
+        const int deg = end - beg;
+        if (hub_ctas > 0 && deg > HUB_DEG) continue;  // done by a hub CTA
+        int n4 = 0;
+        if (deg <= AT_STRIP) n4 = strip_stage(col, val, beg, deg, row_bytes, s_off[warp], s_w[warp]);
+        const float *inb = in + b0 * bstride;
+        const float *self = inb + (size_t)i * C;
+        float *o = out + b0 * bstride + (size_t)i * C;
+        for (int bb = 0; bb < nb; ++bb, inb += bstride, self += bstride, o += bstride) {
+            // request the pass-through part of the row first (up to two groups per lane stay in registers)
+            float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+            if (pass0) p0 = __ldcs(reinterpret_cast<const float4 *>(self + pv0));
+            if (pass1) p1 = __ldcs(reinterpret_cast<const float4 *>(self + pv1));
+            const char *base[NG];
+#pragma unroll
+            for (int n = 0; n < NG; ++n) base[n] = reinterpret_cast<const char *>(inb) + voff[n];
+            float acc[NG][4];
+#pragma unroll
+            for (int n = 0; n < NG; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+            if (deg <= AT_STRIP) {
+                strip_gather<NG>(s_off[warp], s_w[warp], n4, base, acc);
+            } else {  // long row without a hub list: re-stage chunk by chunk
+                for (int e0 = beg; e0 < end; e0 += AT_STRIP) {
+                    const int m4 = strip_stage(col, val, e0, min(AT_STRIP, end - e0), row_bytes, s_off[warp], s_w[warp]);
+                    strip_gather<NG>(s_off[warp], s_w[warp], m4, base, acc);
+                }
+            }
+            row_epilogue<NG>(acc, on, self, o, bias, L, relu);
+            if (pass0) __stcs(reinterpret_cast<float4 *>(o + pv0), relu4(p0, relu));
+            if (pass1) __stcs(reinterpret_cast<float4 *>(o + pv1), relu4(p1, relu));
+            for (int v = gath + 64 + lane; v < ngroups; v += 32)
+                __stcs(reinterpret_cast<float4 *>(o + v * 4), relu4(__ldcs(reinterpret_cast<const float4 *>(self + v * 4)), relu));
+        }
+    }
+}
+
+// Narrow rows (C <= 8, e.g. the 3-channel last layer): one thread per output row, hub rows by one warp each.
+template <int CM>
+__global__ void __launch_bounds__(256)
+gcn_aggregate_narrow_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                            const float *__restrict__ val, const int32_t *__restrict__ hubs, int n_hubs,
+                            unsigned hub_ctas, int Nv, const float *__restrict__ in, long long rows, int B, int C, int L,
+                            const float *__restrict__ bias, int relu, float *__restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    if (blockIdx.x < hub_ctas) {
+        const long long hw = (long long)blockIdx.x * AG_WARPS + (threadIdx.x >> 5);  // (b, hub) pairs
+        if (hw >= (long long)B * n_hubs) return;
+        const int i = hubs[hw % n_hubs];
+        const long long b = hw / n_hubs;
+        const float *inb = in + (size_t)b * Nv * C;
+        float acc[CM];
+#pragma unroll
+        for (int c = 0; c < CM; ++c) acc[c] = 0.f;
+        for (int e = rowptr[i] + lane; e < rowptr[i + 1]; e += 32) {
+            const float w = val[e];
+            const float *src = inb + (size_t)col[e] * C;
+#pragma unroll
+            for (int c = 0; c < CM; ++c)
+                if (c < L) acc[c] = fmaf(w, src[c], acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < CM; ++c) acc[c] = warp_sum(acc[c]);
+        if (lane == 0) {
+            const size_t row = (size_t)b * Nv + i;
+#pragma unroll
+            for (int c = 0; c < CM; ++c)
+                if (c < C) {
+                    float t = c < L ? acc[c] + (bias ? bias[c] : 0.f) : in[row * C + c];
+                    out[row * C + c] = relu ? fmaxf(t, 0.f) : t;
+                }
+        }
+        return;
+    }
+    const long long row = (long long)(blockIdx.x - hub_ctas) * 256 + threadIdx.x;
+    if (row >= rows) return;
+    const int i = (int)(row % Nv);
+    const float *inb = in + (size_t)(row - i) * C;
+    const int beg = rowptr[i], end = rowptr[i + 1];
+    if (hub_ctas > 0 && end - beg > HUB_DEG) return;
+    float acc[CM];
+#pragma unroll
+    for (int c = 0; c < CM; ++c) acc[c] = 0.f;
+    for (int e = beg; e < end; ++e) {
+        const float w = val[e];
+        const float *src = inb + (size_t)col[e] * C;
+#pragma unroll
+        for (int c = 0; c < CM; ++c)
+            if (c < L) acc[c] = fmaf(w, src[c], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < CM; ++c)
+        if (c < C) {
+            float t = c < L ? acc[c] + (bias ? bias[c] : 0.f) : in[(size_t)row * C + c];
+            out[(size_t)row * C + c] = relu ? fmaxf(t, 0.f) : t;
+        }
+}
+
 // gbias[c] = sum_rows g[row, c] (c < L), 0 otherwise.  Deterministic two-stage column sum:
 // stage 1: CTA `k` sums rows k, k+G, ... into part[k, c]; stage 2: one CTA sums the G partials.
 constexpr int BG_PARTS = 1184;  // 8 slabs per SM: short dependent-load chains in stage 1
@@ -312,11 +596,47 @@ extern "C" int ptk_gcn_aggregate(const int32_t *rowptr, const int32_t *col, cons
     PTK_REQUIRE(in != out, PTK_ERR_SHAPE, "gcn_aggregate: in-place aggregation is not supported");
     cudaStream_t st = as_stream(stream);
     const long long rows = (long long)B * Nv;
-    const bool vec = (C % 4 == 0) && ((((uintptr_t)in) | ((uintptr_t)out)) % 16 == 0);
-    const unsigned hub_ctas = (hubs && n_hubs > 0) ? (unsigned)(B * n_hubs) : 0u;
+    const bool vec = (C % 4 == 0) && ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)bias)) % 16 == 0);
+    const bool have_hubs = hubs && n_hubs > 0;
+    const int gath = (int)((L + 3) / 4);
+    PTK_REQUIRE(B <= 0x7fffffff && Nv * C * 4 <= 0xffffffffLL, PTK_ERR_SHAPE, "gcn_aggregate: one batch element must be < 4 GiB");
+    if (vec && gath >= 1 && gath <= 96) {
+        // tile kernel: TV vertices x BG batch elements per CTA, sized for >= ~6 CTAs per SM slot
+        const unsigned hub_ctas = have_hubs ? (unsigned)(B * n_hubs) : 0u;
+        // TV = 8 (one row per warp) keeps few batch elements in flight at a time: the rows a batch element
+        // gathers stay in L2 until all its tiles are done.  BG amortises the staging of the row structure.
+        int TV = 8, BG = 4;
+        const long long slots = 4LL * sm_count() * 4;
+        while (BG > 1 && ceil_div(Nv, TV) * ceil_div(B, BG) < slots) BG >>= 1;
+        if (const char *e = getenv("PTK_AGG_TV")) TV = atoi(e) > 0 ? atoi(e) : TV;  // tuning overrides
+        if (const char *e = getenv("PTK_AGG_BG")) BG = atoi(e) > 0 ? atoi(e) : BG;
+        const int n_tiles = (int)ceil_div(Nv, TV);
+        const unsigned grid = hub_ctas + (unsigned)(n_tiles * ceil_div(B, BG));
+#define PTK_TILE(NGv)                                                                                              \
+    gcn_aggregate_tile_kernel<NGv><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, hub_ctas, (int)Nv, \
+                                                                in, (int)B, (int)C, (int)L, bias, relu, out, TV, BG, n_tiles)
+        if (gath <= 32) PTK_TILE(1);
+        else if (gath <= 64) PTK_TILE(2);
+        else PTK_TILE(3);
+#undef PTK_TILE
+        PTK_CHECK_LAUNCH();
+        return PTK_OK;
+    }
+    if (C <= 8) {
+        const unsigned hub_ctas = have_hubs ? (unsigned)ceil_div(B * n_hubs, AG_WARPS) : 0u;
+        const unsigned grid = hub_ctas + (unsigned)ceil_div(rows, 256);
+        if (C <= 4)
+            gcn_aggregate_narrow_kernel<4><<<grid, 256, 0, st>>>(rowptr, col, val, hubs, n_hubs, hub_ctas, (int)Nv, in, rows, (int)B, (int)C, (int)L, bias, relu, out);
+        else
+            gcn_aggregate_narrow_kernel<8><<<grid, 256, 0, st>>>(rowptr, col, val, hubs, n_hubs, hub_ctas, (int)Nv, in, rows, (int)B, (int)C, (int)L, bias, relu, out);
+        PTK_CHECK_LAUNCH();
+        return PTK_OK;
+    }
+    const bool vec_old = (C % 4 == 0) && ((((uintptr_t)in) | ((uintptr_t)out)) % 16 == 0);
+    const unsigned hub_ctas = have_hubs ? (unsigned)(B * n_hubs) : 0u;
     const unsigned grid = hub_ctas + (unsigned)ceil_div(rows, AG_WARPS);
     const unsigned hub_stride = hub_ctas > 0 ? (grid / hub_ctas > 0 ? grid / hub_ctas : 1u) : 1u;
-    if (vec)
+    if (vec_old)
         gcn_aggregate_kernel<true><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, hub_ctas, hub_stride, (int)Nv, in, rows, (int)C, (int)L, bias, relu, out);
     else
         gcn_aggregate_kernel<false><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, hub_ctas, hub_stride, (int)Nv, in, rows, (int)C, (int)L, bias, relu, out);
