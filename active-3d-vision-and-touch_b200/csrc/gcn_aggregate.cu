@@ -355,13 +355,28 @@ __device__ __forceinline__ float4 relu4(float4 s, int relu) {
     return s;
 }
 
+// Hub rows with a shared neighbour set ("common set").  The touch-chart centre vertices are each linked to
+// ALL boundary vertices (utils.py:126-128): the 5 (finger) or 20 (grasp) hub rows of the fused graph read
+// the same ~1150 neighbour rows.  When the host finds such a set S with val[h,j] = alpha[h] * cw[j] on it
+// (graph.py), one hub CTA per batch element computes  y* = sum_{j in S} cw[j] x_j  ONCE, and every hub row
+// becomes  alpha[h] * y* + (its few remaining neighbours, kept in the reduced CSR)  -- 1/n_hubs of the
+// gather traffic.  Rows flagged in row_skip are left to the hub CTAs by the tile CTAs.
+struct AggHubs {
+    const int32_t *hubs;        // hub row ids (n_hubs)
+    int n_hubs;
+    const int32_t *common_col;  // common set (n_common), may be NULL: every hub row is gathered on its own
+    const float *common_w;
+    int n_common;
+    const float *alpha;         // per hub row scale of y* (n_hubs)
+    const uint8_t *row_skip;    // Nv flags, may be NULL: rows of degree > HUB_DEG are the hub rows
+};
+
 template <int NG>
 __global__ void __launch_bounds__(AG_THREADS, 4)
 gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                          const float *__restrict__ val, const int32_t *__restrict__ hubs, int n_hubs,
-                          unsigned hub_ctas, int Nv, const float *__restrict__ in, int B, int C, int L,
-                          const float *__restrict__ bias, int relu, float *__restrict__ out, int TV, int BG,
-                          int n_tiles) {
+                          const float *__restrict__ val, const AggHubs hb, unsigned hub_ctas, int Nv,
+                          const float *__restrict__ in, int B, int C, int L, const float *__restrict__ bias,
+                          int relu, float *__restrict__ out, int TV, int BG, int n_tiles) {
     __shared__ __align__(16) uint32_t s_off[AG_WARPS][AT_STRIP];
     __shared__ __align__(16) float s_w[AG_WARPS][AT_STRIP];
     __shared__ __align__(16) float s_part[AG_WARPS][NG * 32 * 4];
@@ -377,24 +392,58 @@ gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__r
         voff[n] = (uint32_t)min(lane + 32 * n, gath - 1) * 16u;
     }
     const size_t bstride = (size_t)Nv * C;  // floats per batch element
+    const int npass = ngroups - gath;       // pure pass-through groups
+    const bool pass0 = lane < npass, pass1 = 32 + lane < npass;
+    const int pv0 = (gath + lane) * 4, pv1 = (gath + 32 + lane) * 4;  // float offsets inside the row
 
-    if (blockIdx.x < hub_ctas) {
-        // ---- one (batch element, hub row): the warps split the neighbour list
-        const int i = hubs[blockIdx.x % n_hubs];
-        const int b = blockIdx.x / n_hubs;
-        const int beg = rowptr[i], end = rowptr[i + 1];
-        const int per = (((end - beg) + AG_WARPS - 1) / AG_WARPS + 3) & ~3;
-        const int wbeg = min(end, beg + warp * per), wend = min(end, wbeg + per);
+    // One output row of one batch element by one warp.  `acc` arrives initialised (0, or alpha * y*);
+    // the row's (offset, weight) list is in the warp's strip when staged, else it is streamed in chunks.
+    auto do_row = [&](int i, const float *inb, float *outb, int beg, int end, int n4, float (&acc)[NG][4]) {
+        const float *self = inb + (size_t)i * C;
+        float *o = outb + (size_t)i * C;
+        // request the pass-through part of the row first (up to two groups per lane stay in registers)
+        float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
+        if (pass0) p0 = __ldcs(reinterpret_cast<const float4 *>(self + pv0));
+        if (pass1) p1 = __ldcs(reinterpret_cast<const float4 *>(self + pv1));
         const char *base[NG];
 #pragma unroll
-        for (int n = 0; n < NG; ++n) base[n] = reinterpret_cast<const char *>(in + b * bstride) + voff[n];
-        const float *self = in + b * bstride + (size_t)i * C;
-        float *o = out + b * bstride + (size_t)i * C;
+        for (int n = 0; n < NG; ++n) base[n] = reinterpret_cast<const char *>(inb) + voff[n];
+        if (end - beg <= AT_STRIP) {
+            strip_gather<NG>(s_off[warp], s_w[warp], n4, base, acc);
+        } else {  // long row: re-stage chunk by chunk
+            for (int e0 = beg; e0 < end; e0 += AT_STRIP) {
+                const int m4 = strip_stage(col, val, e0, min(AT_STRIP, end - e0), row_bytes, s_off[warp], s_w[warp]);
+                strip_gather<NG>(s_off[warp], s_w[warp], m4, base, acc);
+            }
+        }
+        row_epilogue<NG>(acc, on, self, o, bias, L, relu);
+        if (pass0) __stcs(reinterpret_cast<float4 *>(o + pv0), relu4(p0, relu));
+        if (pass1) __stcs(reinterpret_cast<float4 *>(o + pv1), relu4(p1, relu));
+        for (int v = gath + 64 + lane; v < ngroups; v += 32)
+            __stcs(reinterpret_cast<float4 *>(o + v * 4), relu4(__ldcs(reinterpret_cast<const float4 *>(self + v * 4)), relu));
+    };
+
+    if (blockIdx.x < hub_ctas) {
         float acc[NG][4];
 #pragma unroll
         for (int n = 0; n < NG; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
+        const bool common = hb.n_common > 0;
+        // common mode: CTA = batch element, the warps split the common set;
+        // plain mode:  CTA = (batch element, hub row), the warps split that row's neighbour list
+        const int b = common ? (int)blockIdx.x : (int)(blockIdx.x / hb.n_hubs);
+        const int hrow = common ? -1 : hb.hubs[blockIdx.x % hb.n_hubs];
+        const int32_t *lcol = common ? hb.common_col : col;
+        const float *lval = common ? hb.common_w : val;
+        const int beg = common ? 0 : rowptr[hrow], end = common ? hb.n_common : rowptr[hrow + 1];
+        const int per = (((end - beg) + AG_WARPS - 1) / AG_WARPS + 3) & ~3;
+        const int wbeg = min(end, beg + warp * per), wend = min(end, wbeg + per);
+        const float *inb = in + b * bstride;
+        float *outb = out + b * bstride;
+        const char *base[NG];
+#pragma unroll
+        for (int n = 0; n < NG; ++n) base[n] = reinterpret_cast<const char *>(inb) + voff[n];
         for (int e0 = wbeg; e0 < wend; e0 += AT_STRIP) {
-            const int n4 = strip_stage(col, val, e0, min(AT_STRIP, wend - e0), row_bytes, s_off[warp], s_w[warp]);
+            const int n4 = strip_stage(lcol, lval, e0, min(AT_STRIP, wend - e0), row_bytes, s_off[warp], s_w[warp]);
             strip_gather<NG>(s_off[warp], s_w[warp], n4, base, acc);
         }
 #pragma unroll
@@ -402,19 +451,39 @@ gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__r
 #pragma unroll
             for (int k = 0; k < 4; ++k) s_part[warp][(n * 32 + lane) * 4 + k] = acc[n][k];
         __syncthreads();
-        if (warp == 0) {
+        // fixed-order reduction over the warps (every warp computes the same total: deterministic)
+#pragma unroll
+        for (int n = 0; n < NG; ++n)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float t = 0.f;
+                for (int w = 0; w < AG_WARPS; ++w) t += s_part[w][(n * 32 + lane) * 4 + k];
+                acc[n][k] = t;
+            }
+        if (!common) {
+            if (warp == 0) {
+                row_epilogue<NG>(acc, on, inb + (size_t)hrow * C, outb + (size_t)hrow * C, bias, L, relu);
+            } else {
+                const float *self = inb + (size_t)hrow * C;
+                float *o = outb + (size_t)hrow * C;
+                for (int v = gath + (warp - 1) * 32 + lane; v < ngroups; v += (AG_WARPS - 1) * 32)
+                    __stcs(reinterpret_cast<float4 *>(o + v * 4), relu4(__ldcs(reinterpret_cast<const float4 *>(self + v * 4)), relu));
+            }
+            return;
+        }
+        // acc = y*.  Each warp finishes some of the hub rows: alpha * y* + the reduced row.
+        for (int h = warp; h < hb.n_hubs; h += AG_WARPS) {
+            const int i = hb.hubs[h];
+            const float a = hb.alpha[h];
+            const int rb = rowptr[i], re = rowptr[i + 1];
+            int n4 = 0;
+            if (re - rb <= AT_STRIP) n4 = strip_stage(col, val, rb, re - rb, row_bytes, s_off[warp], s_w[warp]);
+            float r[NG][4];
 #pragma unroll
             for (int n = 0; n < NG; ++n)
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    float t = 0.f;
-                    for (int w = 0; w < AG_WARPS; ++w) t += s_part[w][(n * 32 + lane) * 4 + k];
-                    acc[n][k] = t;
-                }
-            row_epilogue<NG>(acc, on, self, o, bias, L, relu);
-        } else {
-            for (int v = gath + (warp - 1) * 32 + lane; v < ngroups; v += (AG_WARPS - 1) * 32)
-                __stcs(reinterpret_cast<float4 *>(o + v * 4), relu4(__ldcs(reinterpret_cast<const float4 *>(self + v * 4)), relu));
+                for (int k = 0; k < 4; ++k) r[n][k] = a * acc[n][k];
+            do_row(i, inb, outb, rb, re, n4, r);
         }
         return;
     }
@@ -424,42 +493,18 @@ gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__r
     const int b0 = (int)(t / (unsigned)n_tiles) * BG;
     const int nb = min(B, b0 + BG) - b0;
     const int i1 = min(Nv, i0 + TV);
-    const int npass = ngroups - gath;  // pure pass-through groups
-    const bool pass0 = lane < npass, pass1 = 32 + lane < npass;
-    const int pv0 = (gath + lane) * 4, pv1 = (gath + 32 + lane) * 4;  // float offsets inside the row
     for (int i = i0 + warp; i < i1; i += AG_WARPS) {
         const int beg = rowptr[i], end = rowptr[i + 1];
-        const int deg = end - beg;
-        if (hub_ctas > 0 && deg > HUB_DEG) continue;  // done by a hub CTA
+        if (hb.row_skip ? hb.row_skip[i] != 0 : (hub_ctas > 0 && end - beg > HUB_DEG)) continue;  // hub CTA's row
         int n4 = 0;
-        if (deg <= AT_STRIP) n4 = strip_stage(col, val, beg, deg, row_bytes, s_off[warp], s_w[warp]);
+        if (end - beg <= AT_STRIP) n4 = strip_stage(col, val, beg, end - beg, row_bytes, s_off[warp], s_w[warp]);
         const float *inb = in + b0 * bstride;
-        const float *self = inb + (size_t)i * C;
-        float *o = out + b0 * bstride + (size_t)i * C;
-        for (int bb = 0; bb < nb; ++bb, inb += bstride, self += bstride, o += bstride) {
-            // request the pass-through part of the row first (up to two groups per lane stay in registers)
-            float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
-            if (pass0) p0 = __ldcs(reinterpret_cast<const float4 *>(self + pv0));
-            if (pass1) p1 = __ldcs(reinterpret_cast<const float4 *>(self + pv1));
-            const char *base[NG];
-#pragma unroll
-            for (int n = 0; n < NG; ++n) base[n] = reinterpret_cast<const char *>(inb) + voff[n];
+        float *outb = out + b0 * bstride;
+        for (int bb = 0; bb < nb; ++bb, inb += bstride, outb += bstride) {
             float acc[NG][4];
 #pragma unroll
             for (int n = 0; n < NG; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
-            if (deg <= AT_STRIP) {
-                strip_gather<NG>(s_off[warp], s_w[warp], n4, base, acc);
-            } else {  // long row without a hub list: re-stage chunk by chunk
-                for (int e0 = beg; e0 < end; e0 += AT_STRIP) {
-                    const int m4 = strip_stage(col, val, e0, min(AT_STRIP, end - e0), row_bytes, s_off[warp], s_w[warp]);
-                    strip_gather<NG>(s_off[warp], s_w[warp], m4, base, acc);
-                }
-            }
-            row_epilogue<NG>(acc, on, self, o, bias, L, relu);
-            if (pass0) __stcs(reinterpret_cast<float4 *>(o + pv0), relu4(p0, relu));
-            if (pass1) __stcs(reinterpret_cast<float4 *>(o + pv1), relu4(p1, relu));
-            for (int v = gath + 64 + lane; v < ngroups; v += 32)
-                __stcs(reinterpret_cast<float4 *>(o + v * 4), relu4(__ldcs(reinterpret_cast<const float4 *>(self + v * 4)), relu));
+            do_row(i, inb, outb, beg, end, n4, acc);
         }
     }
 }
@@ -585,15 +630,20 @@ extern "C" int ptk_relu_mask(const float *g, const float *act, int64_t n, float 
     return PTK_OK;
 }
 
-extern "C" int ptk_gcn_aggregate(const int32_t *rowptr, const int32_t *col, const float *val,
-                                 const int32_t *hubs, int32_t n_hubs, int64_t Nv, const float *in,
-                                 int64_t B, int64_t C, int64_t L, const float *bias, int relu,
-                                 float *out, ptk_stream_t stream) {
+extern "C" int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, const float *val,
+                                    const int32_t *hubs, int32_t n_hubs, const int32_t *common_col,
+                                    const float *common_w, int32_t n_common, const float *hub_alpha,
+                                    const uint8_t *row_skip, int64_t Nv, const float *in, int64_t B,
+                                    int64_t C, int64_t L, const float *bias, int relu, float *out,
+                                    ptk_stream_t stream) {
     PTK_REQUIRE(rowptr && col && val && in && out, PTK_ERR_SHAPE, "gcn_aggregate: null pointer");
     PTK_REQUIRE(B > 0 && Nv > 0 && C > 0 && L >= 0 && L <= C, PTK_ERR_SHAPE,
                 "gcn_aggregate: bad sizes (B=%lld, Nv=%lld, C=%lld, L=%lld)", (long long)B,
                 (long long)Nv, (long long)C, (long long)L);
     PTK_REQUIRE(in != out, PTK_ERR_SHAPE, "gcn_aggregate: in-place aggregation is not supported");
+    const bool common = n_common > 0;
+    PTK_REQUIRE(!common || (hubs && n_hubs > 0 && common_col && common_w && hub_alpha && row_skip), PTK_ERR_SHAPE,
+                "gcn_aggregate: a common neighbour set needs hubs, common_col, common_w, hub_alpha and row_skip");
     cudaStream_t st = as_stream(stream);
     const long long rows = (long long)B * Nv;
     const bool vec = (C % 4 == 0) && ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)bias)) % 16 == 0);
@@ -601,20 +651,23 @@ extern "C" int ptk_gcn_aggregate(const int32_t *rowptr, const int32_t *col, cons
     const int gath = (int)((L + 3) / 4);
     PTK_REQUIRE(B <= 0x7fffffff && Nv * C * 4 <= 0xffffffffLL, PTK_ERR_SHAPE, "gcn_aggregate: one batch element must be < 4 GiB");
     if (vec && gath >= 1 && gath <= 96) {
-        // tile kernel: TV vertices x BG batch elements per CTA, sized for >= ~6 CTAs per SM slot
-        const unsigned hub_ctas = have_hubs ? (unsigned)(B * n_hubs) : 0u;
+        const unsigned hub_ctas = have_hubs ? (unsigned)(common ? B : B * n_hubs) : 0u;
         // TV = 8 (one row per warp) keeps few batch elements in flight at a time: the rows a batch element
         // gathers stay in L2 until all its tiles are done.  BG amortises the staging of the row structure.
-        int TV = 8, BG = 4;
+        int TV = 8, BG = 8;
         const long long slots = 4LL * sm_count() * 4;
         while (BG > 1 && ceil_div(Nv, TV) * ceil_div(B, BG) < slots) BG >>= 1;
         if (const char *e = getenv("PTK_AGG_TV")) TV = atoi(e) > 0 ? atoi(e) : TV;  // tuning overrides
         if (const char *e = getenv("PTK_AGG_BG")) BG = atoi(e) > 0 ? atoi(e) : BG;
         const int n_tiles = (int)ceil_div(Nv, TV);
         const unsigned grid = hub_ctas + (unsigned)(n_tiles * ceil_div(B, BG));
-#define PTK_TILE(NGv)                                                                                              \
-    gcn_aggregate_tile_kernel<NGv><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, hub_ctas, (int)Nv, \
-                                                                in, (int)B, (int)C, (int)L, bias, relu, out, TV, BG, n_tiles)
+        AggHubs hb;
+        hb.hubs = hubs; hb.n_hubs = have_hubs ? n_hubs : 0;
+        hb.common_col = common_col; hb.common_w = common_w; hb.n_common = common ? n_common : 0;
+        hb.alpha = hub_alpha; hb.row_skip = common ? row_skip : nullptr;
+#define PTK_TILE(NGv)                                                                                        \
+    gcn_aggregate_tile_kernel<NGv><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hb, hub_ctas, (int)Nv, in, \
+                                                                (int)B, (int)C, (int)L, bias, relu, out, TV, BG, n_tiles)
         if (gath <= 32) PTK_TILE(1);
         else if (gath <= 64) PTK_TILE(2);
         else PTK_TILE(3);
@@ -622,6 +675,9 @@ extern "C" int ptk_gcn_aggregate(const int32_t *rowptr, const int32_t *col, cons
         PTK_CHECK_LAUNCH();
         return PTK_OK;
     }
+    PTK_REQUIRE(!common, PTK_ERR_SHAPE,
+                "gcn_aggregate: the common-set form needs the vector path (C %% 4 == 0, 1 <= L, ceil(L/4) <= 96, "
+                "16-byte aligned); pass the unreduced CSR otherwise");
     if (C <= 8) {
         const unsigned hub_ctas = have_hubs ? (unsigned)ceil_div(B * n_hubs, AG_WARPS) : 0u;
         const unsigned grid = hub_ctas + (unsigned)ceil_div(rows, 256);
@@ -642,6 +698,14 @@ extern "C" int ptk_gcn_aggregate(const int32_t *rowptr, const int32_t *col, cons
         gcn_aggregate_kernel<false><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, hub_ctas, hub_stride, (int)Nv, in, rows, (int)C, (int)L, bias, relu, out);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
+}
+
+extern "C" int ptk_gcn_aggregate(const int32_t *rowptr, const int32_t *col, const float *val,
+                                 const int32_t *hubs, int32_t n_hubs, int64_t Nv, const float *in,
+                                 int64_t B, int64_t C, int64_t L, const float *bias, int relu,
+                                 float *out, ptk_stream_t stream) {
+    return ptk_gcn_aggregate_ex(rowptr, col, val, hubs, n_hubs, nullptr, nullptr, 0, nullptr, nullptr, Nv, in, B,
+                                C, L, bias, relu, out, stream);
 }
 
 extern "C" size_t ptk_gcn_bias_grad_workspace_bytes(int64_t M, int64_t L) {

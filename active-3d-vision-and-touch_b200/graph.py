@@ -12,6 +12,69 @@ import numpy as np
 import torch
 
 HUB_DEG = 128  # rows with more neighbours are handled by a whole CTA (csrc/gcn_aggregate.cu)
+COMMON_MIN = 64  # smallest shared neighbour set worth factoring out of the hub rows
+
+
+def factor_hubs(rowptr, col, val, n):
+    """Kernel-side form of one CSR (see ptk_gcn_aggregate_ex in include/ptk.h).
+
+    The touch-chart centre vertices are all linked to the same ~1150 boundary vertices
+    (utils.py:126-128).  If the hub rows (degree > HUB_DEG) share a column set S on which
+    val[h, j] == alpha[h] * w[j] (row-normalised A^: alpha = 1/deg_h, w = 1; its transpose: alpha = 1,
+    w = 1/deg_j), S is split off: the kernel sums it once per batch element.  Returns a dict with the
+    (possibly reduced) CSR, the hub list and -- when factored -- common_col / common_w / alpha / row_skip.
+    """
+    deg = np.diff(rowptr)
+    hubs = np.nonzero(deg > HUB_DEG)[0].astype(np.int32)
+    plain = dict(rowptr=rowptr, col=col, val=val, hubs=hubs, common_col=None, common_w=None, alpha=None,
+                 row_skip=None)
+    if len(hubs) < 2:
+        return plain
+    rows = [(col[rowptr[h]:rowptr[h + 1]], val[rowptr[h]:rowptr[h + 1]]) for h in hubs]
+    common = rows[0][0]
+    for c, _ in rows[1:]:
+        common = np.intersect1d(common, c, assume_unique=True)
+    common = np.setdiff1d(common, hubs, assume_unique=True)  # keep hub-hub links in the rows themselves
+    if len(common) < COMMON_MIN:
+        return plain
+    sub = np.stack([v[np.searchsorted(c, common)] for c, v in rows]).astype(np.float64)  # (n_hubs, |S|)
+    if (sub == 0).any():
+        return plain
+    # rank-1 test: prefer an exact form (all rows constant -> w = 1; all rows equal -> alpha = 1)
+    if (sub == sub[:, :1]).all():
+        alpha, w = sub[:, 0], np.ones(len(common))
+    elif (sub == sub[:1]).all():
+        alpha, w = np.ones(len(hubs)), sub[0]
+    else:
+        w = sub[0]
+        alpha = sub[:, 0] / w[0]
+        if np.abs(np.outer(alpha, w) - sub).max() > 1e-7 * np.abs(sub).max():
+            return plain
+    keep = np.ones(len(col), bool)
+    for h, (c, _) in zip(hubs, rows):
+        keep[rowptr[h] + np.searchsorted(c, common)] = False
+    ndeg = deg.copy()
+    ndeg[hubs] -= len(common)
+    nrowptr = np.zeros(n + 1, np.int32)
+    np.cumsum(ndeg, out=nrowptr[1:])
+    row_skip = np.zeros(n, np.uint8)
+    row_skip[hubs] = 1
+    return dict(rowptr=nrowptr, col=np.ascontiguousarray(col[keep]), val=np.ascontiguousarray(val[keep]), hubs=hubs,
+                common_col=common.astype(np.int32), common_w=w.astype(np.float32), alpha=alpha.astype(np.float32),
+                row_skip=row_skip)
+
+
+class KernelCSR:
+    """Device arrays of one direction (A^ or its transpose) in the form the aggregate kernels take."""
+
+    def __init__(self, f, device):
+        to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device) if a is not None and len(a) else None
+        self.rowptr, self.col, self.val = to(f["rowptr"]), to(f["col"]), to(f["val"])
+        self.hubs = to(f["hubs"])
+        self.n_hubs = int(len(f["hubs"]))
+        self.common_col, self.common_w, self.alpha, self.row_skip = (to(f[k]) for k in
+                                                                      ("common_col", "common_w", "alpha", "row_skip"))
+        self.n_common = 0 if f["common_col"] is None else int(len(f["common_col"]))
 
 
 class Graph:
@@ -40,6 +103,9 @@ class Graph:
         self.hubs = to(hubs) if len(hubs) else None
         self.hubs_t = to(hubs_t) if len(hubs_t) else None
         self.n_hubs, self.n_hubs_t = int(len(hubs)), int(len(hubs_t))
+        # kernel-side forms with the hub rows' shared neighbour set factored out (vector path only)
+        self.fwd_k = KernelCSR(factor_hubs(rowptr, col, val, self.n), self.device)
+        self.bwd_k = KernelCSR(factor_hubs(rowptr_t, col_t, val_t, self.n), self.device)
 
     @staticmethod
     def from_dense(adj):

@@ -233,6 +233,15 @@ def _aggregate(g: Graph, H3, Lc, bias, relu, transpose=False, out=None):
     if Nv != g.n:
         raise ValueError(f"features have {Nv} vertices but the adjacency has {g.n}")
     out = out if out is not None else torch.empty_like(H3)
+    k = g.bwd_k if transpose else g.fwd_k
+    vector_path = Cc % 4 == 0 and 1 <= Lc <= 384 and H3.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0 and \
+        (bias is None or bias.data_ptr() % 16 == 0)
+    if k.n_common > 0 and vector_path:
+        _lib.check(_lib.lib().ptk_gcn_aggregate_ex(_p(k.rowptr), _p(k.col), _p(k.val), _p(k.hubs), k.n_hubs,
+                                                   _p(k.common_col), _p(k.common_w), k.n_common, _p(k.alpha),
+                                                   _p(k.row_skip), Nv, _p(H3), B, Cc, Lc, _p(bias), int(relu),
+                                                   _p(out), _stream()), "ptk_gcn_aggregate_ex")
+        return out
     if transpose:
         rp, col, val, hubs, nh = g.rowptr_t, g.col_t, g.val_t, g.hubs_t, g.n_hubs_t
     else:

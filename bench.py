@@ -105,6 +105,12 @@ def cpu_chamfer_leg(seconds_target, steps=None, warmup=0):
     """Oracle Chamfer fwd+bwd on a bounded sample: `bs` pairs of 10k x 10k per step, all host threads."""
     from oracle import oracle as orc
     orc.build()
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core it can
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    orc.set_num_threads(ncpu)
     threads = orc.num_threads()
     bs = max(2, min(B_PER_GPU, threads))
     rng = np.random.default_rng(0)

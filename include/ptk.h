@@ -127,6 +127,19 @@ int ptk_gcn_aggregate(const int32_t *rowptr, const int32_t *col, const float *va
                       const int32_t *hubs, int32_t n_hubs, int64_t Nv, const float *in, int64_t B,
                       int64_t C, int64_t L, const float *bias, int relu, float *out,
                       ptk_stream_t stream);
+/* Same, with the hub rows factored over a common neighbour set S (ptk_b200/graph.py builds it): for the
+ * rows listed in `hubs`
+ *     out[b,h,:L] = act( hub_alpha[h] * sum_{k<n_common} common_w[k] * in[b,common_col[k],:L]
+ *                        + sum_{e in row h of the (reduced) CSR} val[e] * in[b,col[e],:L] + bias )
+ * so the ~1150 boundary rows every touch-chart centre vertex is linked to (utils.py:126-128) are read once
+ * per batch element instead of once per hub row.  row_skip (Nv bytes) flags the hub rows.  n_common = 0
+ * (all common_* / hub_alpha / row_skip NULL) is exactly ptk_gcn_aggregate.  Needs the vector path
+ * (C % 4 == 0, 16-byte aligned, 1 <= L, L <= 384). */
+int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, const float *val,
+                         const int32_t *hubs, int32_t n_hubs, const int32_t *common_col,
+                         const float *common_w, int32_t n_common, const float *hub_alpha,
+                         const uint8_t *row_skip, int64_t Nv, const float *in, int64_t B, int64_t C,
+                         int64_t L, const float *bias, int relu, float *out, ptk_stream_t stream);
 /* gbias[c] = sum_{rows} g[row,c] for c < L, 0 for L <= c < C  (g is (M,C)); overwrites gbias.
  * Deterministic two-stage column sum; workspace from ptk_gcn_bias_grad_workspace_bytes. */
 size_t ptk_gcn_bias_grad_workspace_bytes(int64_t M, int64_t L);
