@@ -9,7 +9,9 @@
 
 struct ptk_host_ctx {
     int device;
-    cudaStream_t stream;
+    cudaStream_t stream;       // kernels + result copies
+    cudaStream_t copy_stream;  // input copies, so that chunk i+1 uploads while chunk i computes
+    cudaEvent_t ev_in[8];
     void *buf[16];
     size_t cap[16];
 };
@@ -54,8 +56,11 @@ extern "C" ptk_host_ctx *ptk_host_ctx_create(int device) {
     ptk_host_ctx *c = (ptk_host_ctx *)calloc(1, sizeof(ptk_host_ctx));
     if (!c) return nullptr;
     c->device = device;
-    if (cudaSetDevice(device) != cudaSuccess ||
-        cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    bool ok = cudaSetDevice(device) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
+              cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) {
         set_error("host_ctx_create: cannot open device %d: %s", device,
                   cudaGetErrorString(cudaGetLastError()));
         free(c);
@@ -69,6 +74,9 @@ extern "C" void ptk_host_ctx_destroy(ptk_host_ctx *c) {
     cudaSetDevice(c->device);
     for (int i = 0; i < 16; ++i)
         if (c->buf[i]) cudaFree(c->buf[i]);
+    for (int i = 0; i < 8; ++i)
+        if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
+    cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
     free(c);
 }
@@ -88,27 +96,50 @@ extern "C" int ptk_host_chamfer(ptk_host_ctx *c, const float *x, const float *y,
     PTK_TRY(ensure(c, HB_IDXY, ny * 4));
     PTK_TRY(ensure(c, HB_CHAM, (size_t)B * 4));
     float *dx = (float *)c->buf[HB_X], *dy = (float *)c->buf[HB_Y];
-    PTK_CHECK_CUDA(cudaMemcpyAsync(dx, x, nx * 12, cudaMemcpyHostToDevice, st));
-    PTK_CHECK_CUDA(cudaMemcpyAsync(dy, y, ny * 12, cudaMemcpyHostToDevice, st));
-    PTK_TRY(ptk_chamfer_fwd(dx, dy, B, P1, P2, nullptr, (int32_t *)c->buf[HB_IDXX], nullptr,
-                            (int32_t *)c->buf[HB_IDXY], (float *)c->buf[HB_CHAM], c->buf[HB_WS],
-                            c->cap[HB_WS], st));
-    PTK_CHECK_CUDA(cudaMemcpyAsync(cham, c->buf[HB_CHAM], (size_t)B * 4, cudaMemcpyDeviceToHost, st));
-    if (idx_x) PTK_CHECK_CUDA(cudaMemcpyAsync(idx_x, c->buf[HB_IDXX], nx * 4, cudaMemcpyDeviceToHost, st));
-    if (idx_y) PTK_CHECK_CUDA(cudaMemcpyAsync(idx_y, c->buf[HB_IDXY], ny * 4, cudaMemcpyDeviceToHost, st));
+    int32_t *dix = (int32_t *)c->buf[HB_IDXX], *diy = (int32_t *)c->buf[HB_IDXY];
+    float *dcham = (float *)c->buf[HB_CHAM];
+    float *dgc = nullptr, *dgx = nullptr, *dgy = nullptr;
     if (grad_cham) {
         // backward always runs on the device when grad_cham is given; the gradients are copied back
         // only where a host pointer is supplied (a trainer keeps them on the device)
         PTK_TRY(ensure(c, HB_GCHAM, (size_t)B * 4));
         PTK_TRY(ensure(c, HB_GX, nx * 12));
         PTK_TRY(ensure(c, HB_GY, ny * 12));
-        PTK_CHECK_CUDA(cudaMemcpyAsync(c->buf[HB_GCHAM], grad_cham, (size_t)B * 4, cudaMemcpyHostToDevice, st));
-        PTK_TRY(ptk_chamfer_bwd(dx, dy, (int32_t *)c->buf[HB_IDXX], (int32_t *)c->buf[HB_IDXY],
-                                (float *)c->buf[HB_GCHAM], B, P1, P2, (float *)c->buf[HB_GX],
-                                (float *)c->buf[HB_GY], st));
-        if (grad_x) PTK_CHECK_CUDA(cudaMemcpyAsync(grad_x, c->buf[HB_GX], nx * 12, cudaMemcpyDeviceToHost, st));
-        if (grad_y) PTK_CHECK_CUDA(cudaMemcpyAsync(grad_y, c->buf[HB_GY], ny * 12, cudaMemcpyDeviceToHost, st));
+        dgc = (float *)c->buf[HB_GCHAM];
+        dgx = (float *)c->buf[HB_GX];
+        dgy = (float *)c->buf[HB_GY];
+        PTK_CHECK_CUDA(cudaMemcpyAsync(dgc, grad_cham, (size_t)B * 4, cudaMemcpyHostToDevice, st));
     }
+    // Chunked pipeline over whole cloud pairs: the upload of chunk i+1 (copy stream) overlaps the kernels of
+    // chunk i.  A chunk keeps enough CTAs for >= 4 waves (see plan_nn in chamfer.cu) so the scan itself does
+    // not change; at most 8 chunks.
+    const int64_t Pm = P1 > P2 ? P1 : P2;
+    const int64_t ctas_per_pair = 2 * ceil_div(Pm, 1024);
+    int64_t bc_min = ceil_div(4LL * sm_count() * 4, ctas_per_pair);
+    if (bc_min < 1) bc_min = 1;
+    int64_t n_chunks = B / bc_min;
+    if (n_chunks < 1) n_chunks = 1;
+    if (n_chunks > 8) n_chunks = 8;
+    const int64_t bc = ceil_div(B, n_chunks);
+    int ci = 0;
+    for (int64_t b0 = 0; b0 < B; b0 += bc, ++ci) {
+        const int64_t nb = B - b0 < bc ? B - b0 : bc;
+        const size_t ox = (size_t)b0 * P1, oy = (size_t)b0 * P2;
+        PTK_CHECK_CUDA(cudaMemcpyAsync(dx + ox * 3, x + ox * 3, (size_t)nb * P1 * 12, cudaMemcpyHostToDevice, c->copy_stream));
+        PTK_CHECK_CUDA(cudaMemcpyAsync(dy + oy * 3, y + oy * 3, (size_t)nb * P2 * 12, cudaMemcpyHostToDevice, c->copy_stream));
+        PTK_CHECK_CUDA(cudaEventRecord(c->ev_in[ci], c->copy_stream));
+        PTK_CHECK_CUDA(cudaStreamWaitEvent(st, c->ev_in[ci], 0));
+        PTK_TRY(ptk_chamfer_fwd(dx + ox * 3, dy + oy * 3, nb, P1, P2, nullptr, dix + ox, nullptr, diy + oy, dcham + b0,
+                                c->buf[HB_WS], c->cap[HB_WS], st));
+        if (grad_cham)
+            PTK_TRY(ptk_chamfer_bwd(dx + ox * 3, dy + oy * 3, dix + ox, diy + oy, dgc + b0, nb, P1, P2, dgx + ox * 3,
+                                    dgy + oy * 3, st));
+    }
+    PTK_CHECK_CUDA(cudaMemcpyAsync(cham, dcham, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
+    if (idx_x) PTK_CHECK_CUDA(cudaMemcpyAsync(idx_x, dix, nx * 4, cudaMemcpyDeviceToHost, st));
+    if (idx_y) PTK_CHECK_CUDA(cudaMemcpyAsync(idx_y, diy, ny * 4, cudaMemcpyDeviceToHost, st));
+    if (grad_cham && grad_x) PTK_CHECK_CUDA(cudaMemcpyAsync(grad_x, dgx, nx * 12, cudaMemcpyDeviceToHost, st));
+    if (grad_cham && grad_y) PTK_CHECK_CUDA(cudaMemcpyAsync(grad_y, dgy, ny * 12, cudaMemcpyDeviceToHost, st));
     PTK_CHECK_CUDA(cudaStreamSynchronize(st));
     return PTK_OK;
 }

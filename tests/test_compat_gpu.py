@@ -55,6 +55,25 @@ def test_host_abi_chamfer(golden, oracle):
     ctx.close()
 
 
+def test_host_abi_chamfer_chunked_pipeline_matches_device_api():
+    """Enough pairs that ptk_host_chamfer splits the batch into upload/compute chunks: the result must be
+    bit-identical to the single-launch device API."""
+    B, P1, P2 = 900, 2100, 1900
+    rng = np.random.default_rng(4)
+    x = rng.random((B, P1, 3), np.float32)
+    y = rng.random((B, P2, 3), np.float32)
+    gc = rng.random(B).astype(np.float32)
+    ctx = ptk_b200.host.HostContext(0)
+    out = ctx.chamfer(x, y, grad_cham=gc, want_idx=True)
+    ctx.close()
+    xt, yt = torch.from_numpy(x).cuda().requires_grad_(True), torch.from_numpy(y).cuda().requires_grad_(True)
+    cham, ix, iy = ptk_b200.ops.chamfer(xt, yt)
+    (cham * torch.from_numpy(gc).cuda()).sum().backward()
+    assert np.array_equal(out["idx_x"], ix.cpu().numpy()) and np.array_equal(out["idx_y"], iy.cpu().numpy())
+    assert np.array_equal(out["cham"], cham.detach().cpu().numpy())
+    assert rel_err(out["grad_x"], xt.grad.cpu().numpy()) < 1e-6 and rel_err(out["grad_y"], yt.grad.cpu().numpy()) < 1e-6
+
+
 def test_adj_init_on_gpu_and_deformation_like_step(golden, objects_dir):
     """load_mesh_vision -> adj_init -> GCN -> vertex update -> chamfer loss -> backward: the
     sequence of vision/train.py:120-157 with the CNN encoders replaced by random features."""
