@@ -25,6 +25,8 @@
 //     (deterministic, no float atomics).
 //   * default algorithm (PTK_CHAMFER_FILTER): the scan above is run on the 3-FFMA expansion
 //     |t|^2 - 2 q.t with packed FFMA2 instructions as a FILTER (chamfer_kernel2.cuh); the recorded
+//     target tiles are TMA-staged (cp.async.bulk + mbarrier, double buffered) from padded SoA arrays a
+//     small pre-pass writes (chamfer_prep_kernel); the recorded
 //     chunk is re-evaluated with the defining arithmetic and the few queries whose runner-up chunk is
 //     within the proven error bound are re-scanned exactly (chamfer_nn_exact2_kernel, list mode).
 //     Results are bit-identical to PTK_CHAMFER_EXACT (the 6-op scan, kept selectable for checks).
@@ -37,20 +39,23 @@ constexpr int CH_THREADS = 128;
 constexpr int CH_CHUNK = 16;
 constexpr int CH_MINB = 3;   // exact scan
 constexpr int CH_MINB_F = 4; // filter scan
-constexpr int CH_TT_F = 2048;
+constexpr int CH_TT_F = 1024; // targets per TMA tile (double buffered: 2 x 4 x 4 KB)
 
 static int g_chamfer_algo = PTK_CHAMFER_FILTER;
 
-// workspace: [PairAux B][keys_x B*P1][keys_y B*P2][rescue_x B*P1][rescue_y B*P2][flag_x B*P1][flag_y B*P2][count 2B]
+// workspace: [PairAux B][soa_x B*4*P1p][soa_y B*4*P2p][keys_x B*P1][keys_y B*P2][rescue_x B*P1][rescue_y B*P2]
+//            [flag_x B*P1][flag_y B*P2][count 2B]      (P?p = cloud size padded to SOA_PAD points)
 struct ChamferWs {
     PairAux *aux;
+    float *soa_x, *soa_y;
     u64 *keys_x, *keys_y;
     int *rescue_x, *rescue_y;
     unsigned int *flag_x, *flag_y, *count;
 };
 
 static size_t chamfer_ws_bytes(int64_t B, int64_t P1, int64_t P2) {
-    return sizeof(PairAux) * (size_t)B + (size_t)B * (size_t)(P1 + P2) * (8 + 4 + 4) + 8 * (size_t)B;
+    return sizeof(PairAux) * (size_t)B + 16 * (size_t)B * (size_t)(soa_padded((int)P1) + soa_padded((int)P2)) +
+           (size_t)B * (size_t)(P1 + P2) * (8 + 4 + 4) + 8 * (size_t)B;
 }
 
 static ChamferWs carve(void *workspace, int64_t B, int64_t P1, int64_t P2) {
@@ -58,6 +63,10 @@ static ChamferWs carve(void *workspace, int64_t B, int64_t P1, int64_t P2) {
     char *p = reinterpret_cast<char *>(workspace);
     w.aux = reinterpret_cast<PairAux *>(p);
     p += sizeof(PairAux) * (size_t)B;
+    w.soa_x = reinterpret_cast<float *>(p);
+    p += 16 * (size_t)B * soa_padded((int)P1);
+    w.soa_y = reinterpret_cast<float *>(p);
+    p += 16 * (size_t)B * soa_padded((int)P2);
     w.keys_x = reinterpret_cast<u64 *>(p);
     p += 8 * (size_t)B * P1;
     w.keys_y = reinterpret_cast<u64 *>(p);
@@ -222,10 +231,14 @@ static int launch_nn(const float *x, const float *y, int64_t B, int64_t P1, int6
     if (filter) {
         chamfer_bounds_kernel<<<(unsigned)B, 1024, 0, st>>>(x, y, iP1, iP2, w.aux, w.count);
         PTK_CHECK_LAUNCH();
-#define PTK_FILTER(RR)                                                                                         \
-    chamfer_nn_filter_kernel<RR, CH_CHUNK, CH_THREADS, CH_MINB_F, CH_TT_F, true><<<grid, CH_THREADS, 0, st>>>(  \
-        x, y, iP1, iP2, p.split_len, p.n_split, w.aux, w.keys_x, w.keys_y, dir_only, w.rescue_x, w.rescue_y,   \
-        w.count, w.flag_x, w.flag_y)
+        const int Pp = soa_padded(iP1 > iP2 ? iP1 : iP2);
+        chamfer_prep_kernel<<<dim3((unsigned)ceil_div(Pp, 256), (unsigned)(2 * B)), 256, 0, st>>>(x, y, iP1, iP2, w.aux,
+                                                                                                 w.soa_x, w.soa_y);
+        PTK_CHECK_LAUNCH();
+#define PTK_FILTER(RR)                                                                                          \
+    chamfer_nn_filter_tma_kernel<RR, CH_CHUNK, CH_THREADS, CH_MINB_F, CH_TT_F><<<grid, CH_THREADS, 0, st>>>(     \
+        x, y, iP1, iP2, p.split_len, p.n_split, w.aux, w.soa_x, w.soa_y, w.keys_x, w.keys_y, dir_only, w.rescue_x, \
+        w.rescue_y, w.count, w.flag_x, w.flag_y)
         switch (p.R) {
             case 8: PTK_FILTER(8); break;
             case 4: PTK_FILTER(4); break;

@@ -172,7 +172,7 @@ chamfer_nn_filter_kernel(const float *__restrict__ x, const float *__restrict__ 
                          int *__restrict__ rescue_x, int *__restrict__ rescue_y,
                          unsigned int *__restrict__ rescue_count, unsigned int *__restrict__ rescue_flag_x,
                          unsigned int *__restrict__ rescue_flag_y) {
-    static_assert(CHUNK % 4 == 0 && TT % CHUNK == 0, "tile must hold whole chunks");
+    static_assert(CHUNK % 16 == 0 && TT % CHUNK == 0, "tile must hold whole chunks of 16-target bodies");
     const int z = blockIdx.z;
     const int b = dir_only >= 0 ? z : (z >> 1);
     const int dir = dir_only >= 0 ? dir_only : (z & 1);
@@ -238,8 +238,11 @@ chamfer_nn_filter_kernel(const float *__restrict__ x, const float *__restrict__ 
             float m[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) m[r] = INF;
+#pragma unroll 1
+            for (int sub = 0; sub < CHUNK / 16; ++sub) {
 #pragma unroll
-            for (int g = 0; g < CHUNK / 4; ++g) {
+            for (int g4 = 0; g4 < 4; ++g4) {
+                const int g = sub * 4 + g4;
                 if (PACKED) {
                     const ulonglong2 tx = *reinterpret_cast<const ulonglong2 *>(&sx[c * CHUNK + g * 4]);
                     const ulonglong2 ty = *reinterpret_cast<const ulonglong2 *>(&sy[c * CHUNK + g * 4]);
@@ -275,6 +278,7 @@ chamfer_nn_filter_kernel(const float *__restrict__ x, const float *__restrict__ 
                         m[r] = min3f(m[r], a2, a3);
                     }
                 }
+            }
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
@@ -312,6 +316,205 @@ chamfer_nn_filter_kernel(const float *__restrict__ x, const float *__restrict__ 
             keys[qi] = key;
         if (!(sec[r] > best[r] + __fmaf_ru(bd, FILTER_THR_BD, ax.thr))) {
             // with a split target range several CTAs may flag the same query: queue it once
+            if (n_split == 1 || atomicExch(&rflag[qi], 1u) == 0u)
+                rescue[atomicAdd(&rescue_count[2 * b + dir], 1u)] = qi;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA-staged variant of the filter scan.
+//
+// chamfer_prep_kernel writes, once per forward, every cloud as four padded SoA arrays
+// [X | Y | Z | TT] of translated coordinates (TT = |t|^2, padding: 0,0,0,+inf).  The scan then streams
+// target tiles straight into shared memory with cp.async.bulk (TMA, mbarrier complete_tx), double
+// buffered: no staging arithmetic and no load latency inside the scan, one CTA barrier per tile that only
+// waits for warp skew.
+constexpr int SOA_PAD = 64;  // clouds are padded to a multiple of this many points
+
+__host__ __device__ inline int soa_padded(int P) { return (P + SOA_PAD - 1) / SOA_PAD * SOA_PAD; }
+
+// grid (ceil(Ppad_max / 256), 2 * B): blockIdx.y = 2 * b + cloud
+__global__ void __launch_bounds__(256)
+chamfer_prep_kernel(const float *__restrict__ x, const float *__restrict__ y, int P1, int P2,
+                    const PairAux *__restrict__ aux, float *__restrict__ soa_x, float *__restrict__ soa_y) {
+    const int b = blockIdx.y >> 1, cloud = blockIdx.y & 1;
+    const int P = cloud == 0 ? P1 : P2;
+    const int Pp = soa_padded(P);
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= Pp) return;
+    const float *src = (cloud == 0 ? x + (size_t)b * P1 * 3 : y + (size_t)b * P2 * 3);
+    float *dst = (cloud == 0 ? soa_x + (size_t)b * 4 * Pp : soa_y + (size_t)b * 4 * Pp);
+    const PairAux ax = aux[b];
+    float tx = 0.f, ty = 0.f, tz = 0.f, tt = __int_as_float(0x7f800000);
+    if (i < P) {
+        tx = __fsub_rn(src[i * 3 + 0], ax.cx);
+        ty = __fsub_rn(src[i * 3 + 1], ax.cy);
+        tz = __fsub_rn(src[i * 3 + 2], ax.cz);
+        tt = __fmaf_rn(tz, tz, __fmaf_rn(ty, ty, __fmul_rn(tx, tx)));
+    }
+    dst[i] = tx;
+    dst[Pp + i] = ty;
+    dst[2 * Pp + i] = tz;
+    dst[3 * Pp + i] = tt;
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_wait_parity(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+template <int R, int CHUNK, int THREADS, int MINB, int TT>
+__global__ void __launch_bounds__(THREADS, MINB)
+chamfer_nn_filter_tma_kernel(const float *__restrict__ x, const float *__restrict__ y, int P1, int P2,
+                             int split_len, int n_split, const PairAux *__restrict__ aux,
+                             const float *__restrict__ soa_x, const float *__restrict__ soa_y,
+                             u64 *__restrict__ keys_x, u64 *__restrict__ keys_y, int dir_only,
+                             int *__restrict__ rescue_x, int *__restrict__ rescue_y,
+                             unsigned int *__restrict__ rescue_count, unsigned int *__restrict__ rescue_flag_x,
+                             unsigned int *__restrict__ rescue_flag_y) {
+    static_assert(CHUNK % 16 == 0 && TT % CHUNK == 0 && SOA_PAD % CHUNK == 0, "tile must hold whole chunks");
+    const int z = blockIdx.z;
+    const int b = dir_only >= 0 ? z : (z >> 1);
+    const int dir = dir_only >= 0 ? dir_only : (z & 1);
+    const int NQ = dir == 0 ? P1 : P2;
+    const int NT = dir == 0 ? P2 : P1;
+    const int P1p = soa_padded(P1), P2p = soa_padded(P2);
+    const int NQp = dir == 0 ? P1p : P2p, NTp = dir == 0 ? P2p : P1p;
+    const float *__restrict__ Q = dir == 0 ? x + (size_t)b * P1 * 3 : y + (size_t)b * P2 * 3;
+    const float *__restrict__ T = dir == 0 ? y + (size_t)b * P2 * 3 : x + (size_t)b * P1 * 3;
+    const float *__restrict__ QS = dir == 0 ? soa_x + (size_t)b * 4 * P1p : soa_y + (size_t)b * 4 * P2p;
+    const float *__restrict__ TS = dir == 0 ? soa_y + (size_t)b * 4 * P2p : soa_x + (size_t)b * 4 * P1p;
+    u64 *__restrict__ keys = dir == 0 ? keys_x + (size_t)b * P1 : keys_y + (size_t)b * P2;
+
+    const int q0 = blockIdx.x * (THREADS * R);
+    if (q0 >= NQ) return;
+    const int t_begin = blockIdx.y * split_len;
+    if (t_begin >= NT) return;
+    const int t_end = min(NT, t_begin + split_len);
+    const int tid = threadIdx.x;
+    const PairAux ax = aux[b];
+    const float INF = __int_as_float(0x7f800000);
+
+    __shared__ __align__(128) float sbuf[2][4][TT];
+    __shared__ __align__(8) u64 mbar[2];
+    const uint32_t bar0 = smem_addr(&mbar[0]), bar1 = smem_addr(&mbar[1]);
+    const int ntiles = (t_end - t_begin + TT - 1) / TT;
+    auto issue = [&](int it) {  // one thread: request tile `it` into buffer it & 1
+        const int tile = t_begin + it * TT;
+        const int n = min(TT, t_end - tile);
+        const uint32_t bytes = (uint32_t)((n + CHUNK - 1) / CHUNK * CHUNK) * 4u;
+        const uint32_t bar = (it & 1) ? bar1 : bar0;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4u * bytes) : "memory");
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(smem_addr(&sbuf[it & 1][a][0])), "l"(TS + (size_t)a * NTp + tile), "r"(bytes), "r"(bar)
+                         : "memory");
+    };
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar0));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        issue(0);
+        if (ntiles > 1) issue(1);
+    }
+
+    float mqx[R], mqy[R], mqz[R];  // -2 (q - c)
+    float best[R], sec[R];
+    int bchunk[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int qi = min(q0 + r * THREADS + tid, NQ - 1);
+        mqx[r] = -2.0f * QS[qi];
+        mqy[r] = -2.0f * QS[NQp + qi];
+        mqz[r] = -2.0f * QS[2 * NQp + qi];
+        best[r] = INF;
+        sec[r] = INF;
+        bchunk[r] = t_begin / CHUNK;
+    }
+    __syncthreads();  // barrier initialisation visible to every waiter
+
+    for (int it = 0; it < ntiles; ++it) {
+        const int tile = t_begin + it * TT;
+        const int n = min(TT, t_end - tile);
+        const int nchunks = (n + CHUNK - 1) / CHUNK;
+        const int chunk0 = tile / CHUNK;
+        mbar_wait_parity((it & 1) ? bar1 : bar0, (uint32_t)((it >> 1) & 1));
+        const float *sx = sbuf[it & 1][0], *sy = sbuf[it & 1][1], *sz = sbuf[it & 1][2], *st = sbuf[it & 1][3];
+        for (int c = 0; c < nchunks; ++c) {
+            float m[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) m[r] = INF;
+#pragma unroll 1
+            for (int sub = 0; sub < CHUNK / 16; ++sub) {
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    const int o = c * CHUNK + sub * 16 + g4 * 4;
+                    const ulonglong2 tx = *reinterpret_cast<const ulonglong2 *>(&sx[o]);
+                    const ulonglong2 ty = *reinterpret_cast<const ulonglong2 *>(&sy[o]);
+                    const ulonglong2 tz = *reinterpret_cast<const ulonglong2 *>(&sz[o]);
+                    const ulonglong2 tt = *reinterpret_cast<const ulonglong2 *>(&st[o]);
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        const u64 qx2 = pack2(mqx[r], mqx[r]), qy2 = pack2(mqy[r], mqy[r]), qz2 = pack2(mqz[r], mqz[r]);
+                        u64 a = fma2(qx2, tx.x, tt.x);
+                        u64 c2 = fma2(qx2, tx.y, tt.y);
+                        a = fma2(qy2, ty.x, a);
+                        c2 = fma2(qy2, ty.y, c2);
+                        a = fma2(qz2, tz.x, a);
+                        c2 = fma2(qz2, tz.y, c2);
+                        float a0, a1, a2, a3;
+                        unpack2(a, a0, a1);
+                        unpack2(c2, a2, a3);
+                        m[r] = min3f(m[r], a0, a1);
+                        m[r] = min3f(m[r], a2, a3);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                sec[r] = fminf(sec[r], fmaxf(m[r], best[r]));
+                bchunk[r] = m[r] < best[r] ? chunk0 + c : bchunk[r];
+                best[r] = fminf(best[r], m[r]);
+            }
+        }
+        __syncthreads();  // every warp is done with this buffer
+        if (tid == 0 && it + 2 < ntiles) issue(it + 2);
+    }
+
+    int *__restrict__ rescue = dir == 0 ? rescue_x + (size_t)b * P1 : rescue_y + (size_t)b * P2;
+    unsigned int *__restrict__ rflag = dir == 0 ? rescue_flag_x + (size_t)b * P1 : rescue_flag_y + (size_t)b * P2;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int qi = q0 + r * THREADS + tid;
+        if (qi >= NQ) continue;
+        const float qx = Q[(size_t)qi * 3 + 0], qy = Q[(size_t)qi * 3 + 1], qz = Q[(size_t)qi * 3 + 2];
+        const int j0 = bchunk[r] * CHUNK;
+        const int j1 = min(j0 + CHUNK, t_end);
+        float bd = INF;
+        int arg = j0;
+        for (int j = j0; j < j1; ++j) {
+            const float d = sqdist(qx, qy, qz, T[(size_t)j * 3], T[(size_t)j * 3 + 1], T[(size_t)j * 3 + 2]);
+            if (d < bd) {
+                bd = d;
+                arg = j;
+            }
+        }
+        const u64 key = ((u64)__float_as_uint(bd) << 32) | (unsigned int)arg;
+        if (n_split > 1)
+            atomicMin(&keys[qi], key);
+        else
+            keys[qi] = key;
+        if (!(sec[r] > best[r] + __fmaf_ru(bd, FILTER_THR_BD, ax.thr))) {
             if (n_split == 1 || atomicExch(&rflag[qi], 1u) == 0u)
                 rescue[atomicAdd(&rescue_count[2 * b + dir], 1u)] = qi;
         }

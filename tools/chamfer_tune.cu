@@ -157,6 +157,60 @@ void run_filter(const char *name, const float *x, const float *y, int B, int P, 
     fflush(stdout);
 }
 
+template <int R, int CHUNK, int THREADS, int MINB, int TT>
+void run_tma(const char *name, const float *x, const float *y, int B, int P, unsigned long long *kx,
+             unsigned long long *ky, unsigned long long *d_sum, unsigned long long ref, int reps, PairAux *aux) {
+    dim3 grid((P + THREADS * R - 1) / (THREADS * R), 1, B * 2);
+    int split_len = ((P + CHUNK - 1) / CHUNK) * CHUNK;
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+    static int *rescue = nullptr;
+    static unsigned int *rcount = nullptr;
+    static float *soa = nullptr;
+    const int Pp = soa_padded(P);
+    if (!rescue) { CK(cudaMalloc(&rescue, 8 * (size_t)B * P)); CK(cudaMalloc(&rcount, 8 * (size_t)B)); CK(cudaMalloc(&soa, 32 * (size_t)B * Pp)); }
+    float *soa_x = soa, *soa_y = soa + (size_t)B * 4 * Pp;
+    dim3 rgrid((P + 128 * 8 - 1) / (128 * 8), 1, B * 2);
+    dim3 pgrid((Pp + 255) / 256, 2 * B);
+    auto launch = [&]() {
+        chamfer_bounds_kernel<<<B, 1024>>>(x, y, P, P, aux, rcount);
+        chamfer_prep_kernel<<<pgrid, 256>>>(x, y, P, P, aux, soa_x, soa_y);
+        chamfer_nn_filter_tma_kernel<R, CHUNK, THREADS, MINB, TT><<<grid, THREADS>>>(x, y, P, P, split_len, 1, aux, soa_x, soa_y, kx, ky, -1, rescue, rescue + (size_t)B * P, rcount, nullptr, nullptr);
+        chamfer_nn_exact2_kernel<8, 16, 128, 3><<<rgrid, 128>>>(x, y, P, P, split_len, 1, kx, ky, -1, rescue, rescue + (size_t)B * P, rcount);
+    };
+    launch();
+    CK(cudaDeviceSynchronize());
+    unsigned int amb = 0;
+    {
+        std::vector<unsigned int> hc(2 * B);
+        CK(cudaMemcpy(hc.data(), rcount, 8 * (size_t)B, cudaMemcpyDeviceToHost));
+        for (auto v : hc) amb += v;
+    }
+    launch();
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(a));
+    for (int i = 0; i < reps; ++i) launch();
+    CK(cudaEventRecord(b));
+    CK(cudaDeviceSynchronize());
+    float ms;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    ms /= reps;
+    CK(cudaMemset(d_sum, 0, 8));
+    size_t n = (size_t)B * P;
+    checksum<<<(unsigned)((n + 255) / 256), 256>>>(kx, n, d_sum);
+    checksum<<<(unsigned)((n + 255) / 256), 256>>>(ky, n, d_sum);
+    unsigned long long h;
+    CK(cudaMemcpy(&h, d_sum, 8, cudaMemcpyDeviceToHost));
+    cudaFuncAttributes fa;
+    CK(cudaFuncGetAttributes(&fa, chamfer_nn_filter_tma_kernel<R, CHUNK, THREADS, MINB, TT>));
+    double evals = 2.0 * B * (double)P * P;
+    double peak = 128.0 * 148 * 1.965e9 / 3.0;
+    printf("tma     %-21s R=%d chunk=%2d thr=%3d minb=%d regs=%3d ctas=%5u  %8.3f ms  %6.3f Tevals/s  frac3=%.3f  amb=%.4f%%  %s\n", name, R,
+           CHUNK, THREADS, MINB, fa.numRegs, grid.x * grid.z, ms, evals / ms / 1e9, evals / (ms * 1e-3) / peak,
+           100.0 * amb / (2.0 * n), h == ref ? "OK" : "MISMATCH");
+    fflush(stdout);
+}
+
 static const char *g_only = nullptr;
 static bool want(const char *name) { return g_only == nullptr || strstr(name, g_only) != nullptr; }
 
@@ -181,21 +235,19 @@ int main(int argc, char **argv) {
 #define E(R, C, T, M) if (want("E" #R "," #C "," #T "," #M)) run_exact2<R, C, T, M>(#R "," #C "," #T "," #M, x, y, B, P, kx, ky, d_sum, ref, reps)
 #define F(R, C, T, M, TT) if (want("F" #R "," #C "," #T "," #M "," #TT)) run_filter<R, C, T, M, TT, true>(#R "," #C "," #T "," #M "," #TT, x, y, B, P, kx, ky, d_sum, ref, reps, aux, d_amb)
 #define G(R, C, T, M, TT) if (want("G" #R "," #C "," #T "," #M "," #TT)) run_filter<R, C, T, M, TT, false>(#R "," #C "," #T "," #M "," #TT, x, y, B, P, kx, ky, d_sum, ref, reps, aux, d_amb)
+#define T(R, C, T_, M, TT) if (want("T" #R "," #C "," #T_ "," #M "," #TT)) run_tma<R, C, T_, M, TT>(#R "," #C "," #T_ "," #M "," #TT, x, y, B, P, kx, ky, d_sum, ref, reps, aux)
     PairAux *aux;
     unsigned int *d_amb;
     CK(cudaMalloc(&aux, sizeof(PairAux) * B)); CK(cudaMalloc(&d_amb, 4));
     V(8, 16, 128, 3);
-    E(8, 16, 128, 3);
     F(8, 16, 128, 4, 2048);
-    F(8, 16, 128, 3, 2048);
     F(8, 32, 128, 4, 2048);
-    F(8, 16, 128, 5, 2048);
-    F(4, 16, 128, 8, 2048);
-    F(4, 16, 128, 6, 2048);
-    F(4, 16, 256, 4, 2048);
-    F(8, 16, 64, 8, 2048);
-    F(8, 16, 256, 2, 2048);
-    F(8, 16, 128, 4, 1024);
-    G(8, 16, 128, 3, 2048);
+    F(8, 64, 128, 4, 2048);
+    T(8, 16, 128, 4, 1024);
+    T(8, 32, 128, 4, 1024);
+    T(8, 16, 128, 4, 512);
+    T(8, 32, 128, 5, 1024);
+    T(8, 64, 128, 4, 1024);
+    T(8, 32, 256, 2, 1024);
     return 0;
 }
