@@ -532,7 +532,9 @@ template <int R, int CHUNK, int THREADS>
 __device__ __forceinline__ void exact2_body(const float *__restrict__ Q, const float *__restrict__ T, int NT,
                                             int t_begin, int t_end, const int (&qidx)[R], const bool (&valid)[R],
                                             u64 *__restrict__ keys, bool atomic_merge, float *sx, float *sy,
-                                            float *sz) {
+                                            float *sz, int coff = 0, int cstride = 1) {
+    // coff/cstride: this thread only scans chunks coff, coff + cstride, ... of every tile (used when
+    // several warps share one short query list and split the targets; merged by atomicMin)
     const int tid = threadIdx.x;
     const float INF = __int_as_float(0x7f800000);
     u64 qx[R], qy[R], qz[R];
@@ -564,7 +566,7 @@ __device__ __forceinline__ void exact2_body(const float *__restrict__ Q, const f
         __syncthreads();
         const int nchunks = npad / CHUNK;
         const int chunk0 = tile / CHUNK;
-        for (int c = 0; c < nchunks; ++c) {
+        for (int c = coff; c < nchunks; c += cstride) {
             float m[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) m[r] = INF;
@@ -661,6 +663,15 @@ chamfer_nn_exact2_kernel(const float *__restrict__ x, const float *__restrict__ 
     if (list_mode && NL - q0 <= THREADS) {
         int qidx[1];
         bool valid[1];
+        if (NL - q0 <= 32) {
+            // at most one warp of queries: every warp takes all of them and 1/nwarps of the chunks
+            const int e = q0 + (tid & 31);
+            valid[0] = e < NL;
+            qidx[0] = list[min(e, NL - 1)];
+            exact2_body<1, CHUNK, THREADS>(Q, T, NT, t_begin, t_end, qidx, valid, keys, true, sx, sy, sz, tid >> 5,
+                                           THREADS / 32);
+            return;
+        }
         const int e = q0 + tid;
         valid[0] = e < NL;
         qidx[0] = list[min(e, NL - 1)];
