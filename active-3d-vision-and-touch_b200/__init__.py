@@ -12,13 +12,14 @@ Layout
     utils.py, model.py      the reference's own signatures (utility.utils, GCN_layer, GCN)
     host.py                 host-buffer (numpy) entry points = the non-torch end-to-end path
     recon.py                the GCN + Chamfer-loss part of one reconstruction step (Deformation's layout)
+    policy.py               batched candidate scoring of the greedy touch policies (environment.best_step)
     dist.py                 object/batch sharding + NCCL gradient all-reduce / loss gather
     pytorch3d_shim/         the five pytorch3d.* names the reference imports
 """
 import os
 import sys
 
-from . import _lib, dist, graph, host, model, obj_io, ops, recon, utils  # noqa: F401
+from . import _lib, dist, graph, host, model, obj_io, ops, policy, recon, utils  # noqa: F401
 from .model import GCN, GCN_layer  # noqa: F401
 from .utils import batch_sample, chamfer_distance  # noqa: F401
 

@@ -34,6 +34,13 @@ def init_from_env(backend=None):
     return rank, world, local
 
 
+def rank_world():
+    """(rank, world) of the default process group, (0, 1) when torch.distributed is not initialised."""
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(), dist.get_world_size()
+    return 0, 1
+
+
 def shard_bounds(n_items, rank, world):
     """Contiguous block [lo, hi) of `n_items` objects owned by `rank` (sizes differ by at most 1)."""
     base, rem = divmod(int(n_items), int(world))

@@ -124,6 +124,42 @@ def knn1(p1, p2):
     return dist, idx
 
 
+# ------------------------------------------------------------------------------------- vertex max-pool
+class _VertexMax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats):
+        _need_cuda(feats)
+        feats = _f32c(feats)
+        if feats.dim() != 3:
+            raise ValueError(f"Expected (B,N,C) vertex features, got {tuple(feats.shape)}")
+        B, Nv, Cc = feats.shape
+        out = torch.empty(B, Cc, dtype=torch.float32, device=feats.device)
+        arg = torch.empty(B, Cc, dtype=torch.int32, device=feats.device)
+        with torch.cuda.device(feats.device):
+            _lib.check(_lib.lib().ptk_vertex_maxpool_fwd(_p(feats), B, Nv, Cc, _p(out), _p(arg), _stream()),
+                       "ptk_vertex_maxpool_fwd")
+        ctx.save_for_backward(arg)
+        ctx.shape = (B, Nv, Cc)
+        ctx.mark_non_differentiable(arg)
+        return out, arg
+
+    @staticmethod
+    def backward(ctx, g, _ga):
+        (arg,) = ctx.saved_tensors
+        B, Nv, Cc = ctx.shape
+        gin = torch.empty(B, Nv, Cc, dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            _lib.check(_lib.lib().ptk_vertex_maxpool_bwd(_p(_f32c(g)), _p(arg), B, Nv, Cc, _p(gin), _stream()),
+                       "ptk_vertex_maxpool_bwd")
+        return gin
+
+
+def vertex_max(feats):
+    """(B,N,C) -> (values (B,C), vertex index (B,C) int32): `features.max(dim=1)` of the autoencoder's GCN
+    encoder (autoencoder/model.py:91) and the DDQN graph model (DDQN/model.py:128), differentiable."""
+    return _VertexMax.apply(feats)
+
+
 # ------------------------------------------------------------------------------------- surface sampling
 class _Sample(torch.autograd.Function):
     @staticmethod

@@ -406,6 +406,22 @@ def extra_measurements(torch, ptk_b200, dev, hbm_peak, hbm_src):
     uv = torch.rand(2, Bs, 10000, device=dev)
     ms = timeit(lambda: ptk_b200.ops.sample_points(verts, faces32, uf, uv), 20)
     out["sampler"] = {"shape": "B=16 V=1949 F=2464 S=10000", "ms": ms}
+
+    # --- config 4: greedy-policy scoring, 32 environments x 50 candidate actions in one batched pass
+    E, A = 32, 50
+    cand = torch.cat([vision, touch], 1)[:1].repeat(E * A, 1, 1).reshape(E, A, -1, 3)
+    cand = cand * (1.0 + 0.01 * torch.rand(E, A, 1, 1, device=dev))
+    gtp = torch.nn.functional.normalize(torch.randn(E, 10000, 3, device=dev), dim=-1) * 0.25
+    maskp = (torch.rand(E, A, device=dev) < 0.1).to(torch.int64)
+
+    def policy():
+        sc = ptk_b200.policy.score_candidates(cand, adj_info["faces"], gtp, num=10000)
+        return ptk_b200.policy.best_actions(sc, maskp)
+
+    ms = timeit(policy, 3, warm=1)
+    out["policy_scoring"] = {"shape": "BASELINE configs[3]: 32 envs x 50 actions = 1600 candidate meshes (V=1949, F=2464), "
+                                      "3 x 10k-point samplings + Chamfer each, masked arg-min on the device",
+                             "ms": ms, "candidates_per_s": E * A / (ms * 1e-3)}
     return out
 
 

@@ -177,6 +177,18 @@ int ptk_gcn_linear_wgrad(const float *X, const float *gH, int64_t M, int64_t K, 
                          int algo, void *workspace, size_t workspace_bytes, ptk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Max over the vertices: (B,Nv,C) -> out (B,C) and arg (B,C) int32 (may be NULL), lowest vertex id on
+ * ties, NaN propagates.  Replaces `features.max(dim=1)[0]` after the GCN encoder of the autoencoder
+ * (pterotactyl/reconstruction/autoencoder/model.py:91) and `torch.max(x, dim=1)[0]` of the DDQN
+ * Graph_Model (pterotactyl/policies/DDQN/model.py:128).  bwd overwrites grad_in (B,Nv,C):
+ * grad_in[b, arg[b,c], c] = grad_out[b,c], zero elsewhere.
+ * ---------------------------------------------------------------------------------------------- */
+int ptk_vertex_maxpool_fwd(const float *in, int64_t B, int64_t Nv, int64_t C, float *out, int32_t *arg,
+                           ptk_stream_t stream);
+int ptk_vertex_maxpool_bwd(const float *grad_out, const int32_t *arg, int64_t B, int64_t Nv, int64_t C,
+                           float *grad_in, ptk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (end-to-end path: H2D + kernels + D2H inside the call).
  * All pointers are HOST pointers (pinned memory makes the copies asynchronous and faster).
  * ---------------------------------------------------------------------------------------------- */
