@@ -1,0 +1,48 @@
+"""Dev tool: BASELINE configs[4] sweep -- Chamfer fwd and fwd+bwd over cloud sizes and batch sizes on one GPU.
+    python tools/chamfer_sweep.py > profiles/rNN_chamfer_sweep.txt
+Each cell also checks size-independent properties (reported index reproduces the reported distance; symmetry)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import ptk_b200
+
+dev = torch.device("cuda")
+
+def timeit(fn, iters):
+    fn(); torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+print(f"{'P':>7} {'B':>4} {'fwd ms':>10} {'fwd+bwd ms':>11} {'pairs/s':>10} {'Tevals/s':>9} {'rescued %':>9}  checks")
+for P in (1000, 2000, 5000, 10000, 20000, 50000, 100000):
+    for B in (1, 4, 16, 64, 256):
+        if B * P * P > 256 * 20000 * 20000 * 1.1:   # keep the sweep within a few seconds per cell
+            continue
+        g = torch.Generator(device=dev).manual_seed(P + B)
+        x = (torch.rand(B, P, 3, device=dev, generator=g) - 0.5).requires_grad_(True)
+        y = (torch.rand(B, P, 3, device=dev, generator=g) - 0.5).requires_grad_(True)
+        iters = max(2, min(50, int(2e11 / (B * P * P))))
+        def fwd():
+            with torch.no_grad():
+                return ptk_b200.ops.chamfer(x, y)
+        def both():
+            x.grad = y.grad = None
+            c, _, _ = ptk_b200.ops.chamfer(x, y)
+            c.sum().backward()
+        tf, tb = timeit(fwd, iters), timeit(both, iters)
+        cham, ix, iy = fwd()
+        ar = torch.arange(B, device=dev)[:, None]
+        dx = ((x - y[ar, ix.long()]) ** 2).sum(-1).mean(1)
+        dy = ((y - x[ar, iy.long()]) ** 2).sum(-1).mean(1)
+        ok1 = torch.allclose(cham, (dx + dy).detach(), rtol=1e-5)
+        c2, jx, jy = ptk_b200.ops.chamfer(y.detach(), x.detach())
+        ok2 = torch.equal(jx, iy) and torch.equal(jy, ix)
+        q = x[0, :32].detach()
+        ok3 = torch.equal(((q[:, None] - y[0].detach()[None]) ** 2).sum(-1).argmin(1).int(), ix[0, :32])
+        resc = ptk_b200.ops.chamfer_rescued(x.detach(), y.detach()) / (2.0 * B * P)
+        print(f"{P:7d} {B:4d} {tf:10.3f} {tb:11.3f} {B / (tb * 1e-3):10.1f} {2.0 * B * P * P / (tf * 1e-3) / 1e12:9.3f} "
+              f"{100 * resc:9.3f}  {'ok' if (ok1 and ok2 and ok3) else 'FAIL'}", flush=True)
+        del x, y
