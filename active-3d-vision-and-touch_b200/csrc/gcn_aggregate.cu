@@ -374,9 +374,9 @@ struct AggHubs {
 template <int NG>
 __global__ void __launch_bounds__(AG_THREADS, 4)
 gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                          const float *__restrict__ val, const AggHubs hb, unsigned hub_ctas, int Nv,
+                          const float *__restrict__ val, const AggHubs hb, unsigned hub_slots, int Nv,
                           const float *__restrict__ in, int B, int C, int L, const float *__restrict__ bias,
-                          int relu, float *__restrict__ out, int TV, int BG, int n_tiles) {
+                          int relu, float *__restrict__ out, int TV, int BG, int n_tiles, int hubs_first) {
     __shared__ __align__(16) uint32_t s_off[AG_WARPS][AT_STRIP];
     __shared__ __align__(16) float s_w[AG_WARPS][AT_STRIP];
     __shared__ __align__(16) float s_part[AG_WARPS][NG * 32 * 4];
@@ -423,15 +423,37 @@ gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__r
             __stcs(reinterpret_cast<float4 *>(o + v * 4), relu4(__ldcs(reinterpret_cast<const float4 *>(self + v * 4)), relu));
     };
 
-    if (blockIdx.x < hub_ctas) {
+    // Block order: per batch group (BG batch elements) first its hub CTAs, then its tiles -- the boundary rows
+    // the hub CTAs pull into L2 are the ones the group's tiles gather next.
+    // (hubs_first: all hub CTAs lead the grid instead -- better when the whole input is L2-resident and the
+    // only concern is starting the long hub rows early.)
+    const unsigned per_group = hub_slots + (unsigned)n_tiles;
+    unsigned group, local;
+    if (hubs_first) {
+        const unsigned n_groups = ((unsigned)B + BG - 1) / BG;
+        const unsigned lead = hub_slots * n_groups;
+        if (blockIdx.x < lead) {
+            group = blockIdx.x / hub_slots;
+            local = blockIdx.x % hub_slots;
+        } else {
+            group = (blockIdx.x - lead) / (unsigned)n_tiles;
+            local = hub_slots + (blockIdx.x - lead) % (unsigned)n_tiles;
+        }
+    } else {
+        group = blockIdx.x / per_group;
+        local = blockIdx.x % per_group;
+    }
+    const unsigned hub_ctas = hub_slots;  // > 0: rows above HUB_DEG / flagged rows belong to hub CTAs
+    if (local < hub_slots) {
         float acc[NG][4];
 #pragma unroll
         for (int n = 0; n < NG; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
         const bool common = hb.n_common > 0;
         // common mode: CTA = batch element, the warps split the common set;
         // plain mode:  CTA = (batch element, hub row), the warps split that row's neighbour list
-        const int b = common ? (int)blockIdx.x : (int)(blockIdx.x / hb.n_hubs);
-        const int hrow = common ? -1 : hb.hubs[blockIdx.x % hb.n_hubs];
+        const int b = (int)group * BG + (common ? (int)local : (int)(local / hb.n_hubs));
+        if (b >= B) return;
+        const int hrow = common ? -1 : hb.hubs[local % hb.n_hubs];
         const int32_t *lcol = common ? hb.common_col : col;
         const float *lval = common ? hb.common_w : val;
         const int beg = common ? 0 : rowptr[hrow], end = common ? hb.n_common : rowptr[hrow + 1];
@@ -488,9 +510,8 @@ gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__r
         return;
     }
 
-    const unsigned t = blockIdx.x - hub_ctas;
-    const int i0 = (int)(t % (unsigned)n_tiles) * TV;
-    const int b0 = (int)(t / (unsigned)n_tiles) * BG;
+    const int i0 = (int)(local - hub_slots) * TV;
+    const int b0 = (int)group * BG;
     const int nb = min(B, b0 + BG) - b0;
     const int i1 = min(Nv, i0 + TV);
     for (int i = i0 + warp; i < i1; i += AG_WARPS) {
@@ -651,7 +672,6 @@ extern "C" int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, c
     const int gath = (int)((L + 3) / 4);
     PTK_REQUIRE(B <= 0x7fffffff && Nv * C * 4 <= 0xffffffffLL, PTK_ERR_SHAPE, "gcn_aggregate: one batch element must be < 4 GiB");
     if (vec && gath >= 1 && gath <= 96) {
-        const unsigned hub_ctas = have_hubs ? (unsigned)(common ? B : B * n_hubs) : 0u;
         // TV = 8 (one row per warp) keeps few batch elements in flight at a time: the rows a batch element
         // gathers stay in L2 until all its tiles are done.  BG amortises the staging of the row structure.
         int TV = 8, BG = 8;
@@ -660,14 +680,16 @@ extern "C" int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, c
         if (const char *e = getenv("PTK_AGG_TV")) TV = atoi(e) > 0 ? atoi(e) : TV;  // tuning overrides
         if (const char *e = getenv("PTK_AGG_BG")) BG = atoi(e) > 0 ? atoi(e) : BG;
         const int n_tiles = (int)ceil_div(Nv, TV);
-        const unsigned grid = hub_ctas + (unsigned)(n_tiles * ceil_div(B, BG));
+        const unsigned hub_slots = have_hubs ? (unsigned)(common ? BG : BG * n_hubs) : 0u;  // per batch group
+        const unsigned grid = (unsigned)((hub_slots + n_tiles) * ceil_div(B, BG));
+        const int hubs_first = (double)B * Nv * C * 8.0 < 100e6;  // input + output fit the 126 MB L2
         AggHubs hb;
         hb.hubs = hubs; hb.n_hubs = have_hubs ? n_hubs : 0;
         hb.common_col = common_col; hb.common_w = common_w; hb.n_common = common ? n_common : 0;
         hb.alpha = hub_alpha; hb.row_skip = common ? row_skip : nullptr;
 #define PTK_TILE(NGv)                                                                                        \
-    gcn_aggregate_tile_kernel<NGv><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hb, hub_ctas, (int)Nv, in, \
-                                                                (int)B, (int)C, (int)L, bias, relu, out, TV, BG, n_tiles)
+    gcn_aggregate_tile_kernel<NGv><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hb, hub_slots, (int)Nv, in, \
+                                                                (int)B, (int)C, (int)L, bias, relu, out, TV, BG, n_tiles, hubs_first)
         if (gath <= 32) PTK_TILE(1);
         else if (gath <= 64) PTK_TILE(2);
         else PTK_TILE(3);
