@@ -45,3 +45,31 @@ def recon_loss(vertices, faces, gt_points, number_points=10000, loss_coeff=9000.
     cd = utils.chamfer_distance(vertices, faces, gt_points, num=number_points, repeat=3, generator=generator,
                                 uniforms=uniforms)
     return loss_coeff * cd.mean(), cd
+
+
+class GraphedStep:
+    """One training step (forward + loss + backward + optimizer) captured in a CUDA graph and replayed.
+
+    The reference's step (vision/train.py:120-157) is ~600 kernel launches of 5-150 us at batch 16, so launch
+    gaps and Python overhead are a measurable share.  Every ptk_b200 op is capture-safe (no host
+    synchronisation, workspaces from torch's graph-private pool), so the whole step can be replayed from one
+    graph launch.  `step_fn()` must read its inputs from tensors that stay at fixed addresses (copy new batches
+    into them with `.copy_()`), return the loss tensor, and include `optimizer.zero_grad(set_to_none=True)`,
+    `backward()` and `optimizer.step()`; the optimizer has to be built with `capturable=True`.
+    """
+
+    def __init__(self, step_fn, warmup=3):
+        self.step_fn = step_fn
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up off the default stream: lazy initialisation, caches, autotuning
+            for _ in range(warmup):
+                step_fn()
+        torch.cuda.current_stream().wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = step_fn()
+
+    def __call__(self):
+        self.graph.replay()
+        return self.loss

@@ -395,10 +395,27 @@ def extra_measurements(torch, ptk_b200, dev, hbm_peak, hbm_src):
         opt.step()
 
     ms = timeit(step, 5, warm=2)
+    ms_graph = None
+    try:  # the same step replayed from one CUDA graph (launch gaps and Python overhead removed)
+        opt_g = torch.optim.Adam(net.parameters(), lr=3e-4, capturable=True)
+
+        def step_g():
+            opt_g.zero_grad(set_to_none=True)
+            verts = net(vision, touch, lambda it, v: feats[it])
+            loss, _ = ptk_b200.recon.recon_loss(verts, adj_info["faces"], gt, number_points=10000)
+            loss.backward()
+            opt_g.step()
+            return loss
+
+        graphed = ptk_b200.recon.GraphedStep(step_g)
+        ms_graph = timeit(graphed, 10, warm=2)
+    except Exception as exc:
+        out["recon_step_graph_error"] = repr(exc)[:300]
     gemm_flop = 3 * 2 * Bs * (1824 * (448 * 300 + 18 * 300 * 300 + 300 * 3) + 2 * 1949 * (448 * 300 + 18 * 300 * 300 + 300 * 3))
     out["recon_step"] = {"shape": "v_t_p GCN part: B=16, 3 x (448->300x18->3), N=1824/1949/1949, 3 x 10k-point "
                                   "Chamfer loss, fwd+bwd+Adam; synthetic vertex features (CNN/MLP encoders out of scope)",
-                         "ms": ms, "steps_per_s": 1e3 / ms, "gemm_tflops": gemm_flop / (ms * 1e-3) / 1e12}
+                         "ms": ms, "steps_per_s": 1e3 / ms, "gemm_tflops": gemm_flop / (ms * 1e-3) / 1e12,
+                         "ms_cuda_graph": ms_graph, "steps_per_s_cuda_graph": (1e3 / ms_graph) if ms_graph else None}
     # --- sampler (B=16, V=1949, F=2464, S=10000)
     faces32 = adj_info["faces"].to(torch.int32)
     verts = torch.cat([vision, touch], 1)
