@@ -9,6 +9,8 @@
 // TF32/BF16 tensor-core math; this file is the exact-FP32 FFMA implementation: 128x128x16 CTA
 // tiles, 8x8 register micro-tiles (2x2 blocks of 4x4 so that shared-memory reads are 128-bit and
 // conflict-free), register-staged global prefetch of the next k-tile.
+#include <stdlib.h>
+
 #include "ptk_common.cuh"
 
 namespace ptk {
@@ -120,15 +122,15 @@ sgemm_kernel(const float *__restrict__ A, long long lda, const float *__restrict
 
 // ------------------------------------------------------------------------------------------------
 // Forward-specialised exact-FP32 kernel: H (M x N) = X (M x K) . W (K x N), all row-major, K % 4 == 0,
-// N % 4 == 0, 16-byte aligned.  CTA tile BM x 160 x 16 with BM in {128, 112, 96} chosen per problem so
-// that the grid is a whole number of waves (N = 300 -> two 160-wide column tiles, 6 % padding instead of
-// the 22 % of 128-wide tiles); 8 x 10 register micro-tiles (80 FFMA per 5 shared-memory loads); 128-bit
+// N % 4 == 0, 16-byte aligned.  CTA tile BM x 160 x 16, BM = 64 by default (N = 300 -> two 160-wide column
+// tiles, 6 % padding instead of the 22 % of 128-wide tiles); 8 x 10 register micro-tiles held as 8 x 5 packed
+// FP32x2 pairs (40 FFMA2 per 5 shared-memory loads); 128-bit
 // global loads, register-staged double buffering.  Each output is one k-sequential FMA chain starting
 // from 0 -- the arithmetic of a scalar FP32 loop (see ops.py: why the training forward needs that).
 constexpr int FW_BN = 160, FW_BK = 16, FW_PAD = 4;
 
 template <int BM>
-__global__ void __launch_bounds__(BM * 2, 2)
+__global__ void __launch_bounds__(BM * 2, BM <= 32 ? 6 : (BM <= 64 ? 3 : 2))
 sgemm_fwd_kernel(const float *__restrict__ A, const float *__restrict__ Bm, float *__restrict__ Cm, int M, int N,
                  int K) {
     constexpr int T = BM * 2;
@@ -285,18 +287,15 @@ extern "C" int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int
         return gemm_tf32x3(X, W, /*b_is_kn=*/1, nullptr, M, K, N, H, workspace, workspace_bytes, as_stream(stream));
     PTK_REQUIRE(g_fwd_mode != 2, PTK_ERR_SHAPE, "gcn_linear_fwd: shape not eligible for the tensor-core path");
     if ((K % 4) == 0 && (N % 4) == 0 && N >= 64 && (((uintptr_t)X | (uintptr_t)W | (uintptr_t)H) % 16) == 0 &&
-        M < (1LL << 31) && ceil_div(M, 96) <= 65535) {
-        // pick the row-tile height that wastes the least in the last wave (2 resident CTAs per SM)
-        const int64_t slots = 2LL * sm_count();
-        const int64_t nt = ceil_div(N, FW_BN);
-        int best = 128;
-        int64_t best_cost = -1;
-        const int cands[3] = {128, 112, 96};
-        for (int c = 0; c < 3; ++c) {
-            const int64_t cost = ceil_div(ceil_div(M, cands[c]) * nt, slots) * cands[c];
-            if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = cands[c]; }
-        }
-        if (best == 128) launch_fwd<128>(X, W, H, M, K, N, as_stream(stream));
+        M < (1LL << 31) && ceil_div(M, 32) <= 65535) {
+        // BM = 64 (128 threads, 3 CTAs/SM, 168 registers: the 8 x 10 micro-tile fits without spills) measured
+        // fastest at every M that occurs here: 120 us vs 145 us (BM 112/128, spilling at the 128-register cap),
+        // 136 us (BM 32) and cuBLAS FP32 127 us at M=31184, K=N=300.
+        int best = 64;
+        if (const char *e = getenv("PTK_FWD_BM")) best = atoi(e);  // tuning override
+        if (best == 32) launch_fwd<32>(X, W, H, M, K, N, as_stream(stream));
+        else if (best == 64) launch_fwd<64>(X, W, H, M, K, N, as_stream(stream));
+        else if (best == 128) launch_fwd<128>(X, W, H, M, K, N, as_stream(stream));
         else if (best == 112) launch_fwd<112>(X, W, H, M, K, N, as_stream(stream));
         else launch_fwd<96>(X, W, H, M, K, N, as_stream(stream));
         PTK_CHECK_LAUNCH();
