@@ -133,3 +133,90 @@ def test_gcn_batch_independence(golden):
         y = net(x, info)
         y2 = net(x[2:4].contiguous(), info)
     assert torch.equal(y[2:4], y2)
+
+
+def test_full_size_config3_properties(golden):
+    """BASELINE configs[2] size (B=16, N=1949, 20 x 300 GCN): properties that need no oracle run.
+    (1) batch independence: every batch element equals the same element run alone (bit-identical forward);
+    (2) gradient additivity: parameter gradients of the batch equal the sum of per-element gradients;
+    (3) the factored hub rows (graph.factor_hubs) and the plain CSR give the same aggregate."""
+    adj = golden("adjacency")
+    g = Graph.from_csr(adj["p_adj_rowptr"], adj["p_adj_col"], "cuda")
+    info = {"adj": g.dense()}
+    args = types.SimpleNamespace(num_GCN_layers=20, hidden_GCN_size=300, cut=0.33)
+    torch.manual_seed(7)
+    net = ptk_b200.GCN(448, args).cuda()
+    B = 16
+    x = torch.rand(B, g.n, 448, device="cuda")
+    gout = torch.rand(B, g.n, 3, device="cuda")
+    y = net(x, info)
+    (y * gout).sum().backward()
+    gw_batch = [p.grad.clone() for p in net.parameters()]
+    sums = [torch.zeros_like(p) for p in net.parameters()]
+    for b in (0, 7, 15):
+        yb = net(x[b:b + 1].contiguous(), info)
+        assert torch.equal(yb[0], y[b]), b
+    for b in range(B):
+        net.zero_grad(set_to_none=True)
+        yb = net(x[b:b + 1].contiguous(), info)
+        (yb * gout[b:b + 1]).sum().backward()
+        for s, p in zip(sums, net.parameters()):
+            s += p.grad
+    for a, s in zip(gw_batch, sums):
+        assert rel_err(a.cpu().numpy(), s.cpu().numpy()) < TOL
+    # (3) factored vs plain hub handling on a batch that uses the tile kernel
+    H = torch.randn(B, g.n, 300, device="cuda")
+    bias = torch.randn(300, device="cuda")
+    fact = ptk_b200.ops._aggregate(g, H, 99, bias, True)
+    assert g.fwd_k.n_common > 1000
+    plain = torch.empty_like(H)
+    import ctypes as C
+    from ptk_b200 import _lib
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    _lib.check(_lib.lib().ptk_gcn_aggregate(p(g.rowptr), p(g.col), p(g.val), p(g.hubs), g.n_hubs, g.n, p(H), B, 300, 99,
+                                            p(bias), 1, p(plain), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               "ptk_gcn_aggregate")
+    assert rel_err(fact.cpu().numpy(), plain.cpu().numpy()) < 2e-6
+    # (4) linearity of the aggregation in its input
+    H2 = torch.randn_like(H)
+    lhs = ptk_b200.ops._aggregate(g, H + 2.0 * H2, 99, None, False)
+    rhs = ptk_b200.ops._aggregate(g, H, 99, None, False) + 2.0 * ptk_b200.ops._aggregate(g, H2, 99, None, False)
+    assert rel_err(lhs.cpu().numpy(), rhs.cpu().numpy()) < TOL
+
+
+def test_random_graphs_with_and_without_common_hub_sets(oracle):
+    """Generic CSR graphs: random weights (hub rows NOT rank-1 => no factorisation), rows longer than the
+    128-entry strip without a hub list, and a synthetic star graph whose hubs do share a common set."""
+    rng = np.random.default_rng(5)
+    n = 700
+    for case in ("random_weights", "star"):
+        rows = [np.unique(np.append(rng.integers(0, n, rng.integers(1, 12)), i)) for i in range(n)]
+        hubs = [10, 300, 650]
+        common = np.unique(rng.integers(0, n, 400))
+        for h in hubs:
+            rows[h] = np.unique(np.concatenate([rows[h], common]))
+        rowptr = np.zeros(n + 1, np.int32)
+        rowptr[1:] = np.cumsum([len(r) for r in rows])
+        col = np.concatenate(rows).astype(np.int32)
+        if case == "random_weights":
+            val = rng.random(len(col)).astype(np.float32)
+            gr = Graph(rowptr, col, val, n, "cuda")
+            assert gr.fwd_k.n_common == 0          # not rank-1 on the common set: plain hub CTAs
+        else:
+            gr = Graph.from_csr(rowptr, col, "cuda")
+            val = gr.host["val"]
+            assert gr.fwd_k.n_common >= 300      # (the pattern is not symmetric: its transpose has no hub rows)
+        H = rng.standard_normal((3, n, 64)).astype(np.float32)
+        bias = rng.standard_normal(64).astype(np.float32)
+        for L in (64, 21):
+            out = ptk_b200.ops._aggregate(gr, torch.from_numpy(H).cuda(), L, torch.from_numpy(bias).cuda(), True)
+            dense = np.zeros((n, n), np.float64)
+            dense[np.repeat(np.arange(n), np.diff(rowptr)), col] = val
+            want = H.astype(np.float64).copy()
+            want[:, :, :L] = np.einsum("ij,bjc->bic", dense, H[:, :, :L].astype(np.float64)) + bias[:L]
+            want = np.maximum(want, 0)
+            assert rel_err(out.cpu().numpy(), want) < TOL, (case, L)
+            gT = ptk_b200.ops._aggregate(gr, torch.from_numpy(H).cuda(), L, None, False, transpose=True)
+            wantT = H.astype(np.float64).copy()
+            wantT[:, :, :L] = np.einsum("ji,bjc->bic", dense, H[:, :, :L].astype(np.float64))
+            assert rel_err(gT.cpu().numpy(), wantT) < TOL, (case, L)
