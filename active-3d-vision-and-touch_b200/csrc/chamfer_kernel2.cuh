@@ -381,7 +381,7 @@ chamfer_nn_filter_tma_kernel(const float *__restrict__ x, const float *__restric
                              int *__restrict__ rescue_x, int *__restrict__ rescue_y,
                              unsigned int *__restrict__ rescue_count, unsigned int *__restrict__ rescue_flag_x,
                              unsigned int *__restrict__ rescue_flag_y) {
-    static_assert(CHUNK % 16 == 0 && TT % CHUNK == 0 && SOA_PAD % CHUNK == 0, "tile must hold whole chunks");
+    static_assert((CHUNK == 16 || CHUNK == 32 || CHUNK == 64) && TT % CHUNK == 0 && SOA_PAD % CHUNK == 0, "tile must hold whole chunks");
     const int z = blockIdx.z;
     const int b = dir_only >= 0 ? z : (z >> 1);
     const int dir = dir_only >= 0 ? dir_only : (z & 1);
@@ -450,41 +450,44 @@ chamfer_nn_filter_tma_kernel(const float *__restrict__ x, const float *__restric
         const int chunk0 = tile / CHUNK;
         mbar_wait_parity((it & 1) ? bar1 : bar0, (uint32_t)((it >> 1) & 1));
         const float *sx = sbuf[it & 1][0], *sy = sbuf[it & 1][1], *sz = sbuf[it & 1][2], *st = sbuf[it & 1][3];
-        for (int c = 0; c < nchunks; ++c) {
-            float m[R];
+        // 16-target bodies; the per-chunk bookkeeping runs after every CHUNK/16-th body (uniform branch)
+        float m[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) m[r] = INF;
-#pragma unroll 1
-            for (int sub = 0; sub < CHUNK / 16; ++sub) {
+        for (int r = 0; r < R; ++r) m[r] = INF;
+        const int nbodies = nchunks * (CHUNK / 16);
+        for (int sb = 0; sb < nbodies; ++sb) {
 #pragma unroll
-                for (int g4 = 0; g4 < 4; ++g4) {
-                    const int o = c * CHUNK + sub * 16 + g4 * 4;
-                    const ulonglong2 tx = *reinterpret_cast<const ulonglong2 *>(&sx[o]);
-                    const ulonglong2 ty = *reinterpret_cast<const ulonglong2 *>(&sy[o]);
-                    const ulonglong2 tz = *reinterpret_cast<const ulonglong2 *>(&sz[o]);
-                    const ulonglong2 tt = *reinterpret_cast<const ulonglong2 *>(&st[o]);
+            for (int g4 = 0; g4 < 4; ++g4) {
+                const int o = sb * 16 + g4 * 4;
+                const ulonglong2 tx = *reinterpret_cast<const ulonglong2 *>(&sx[o]);
+                const ulonglong2 ty = *reinterpret_cast<const ulonglong2 *>(&sy[o]);
+                const ulonglong2 tz = *reinterpret_cast<const ulonglong2 *>(&sz[o]);
+                const ulonglong2 tt = *reinterpret_cast<const ulonglong2 *>(&st[o]);
 #pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        const u64 qx2 = pack2(mqx[r], mqx[r]), qy2 = pack2(mqy[r], mqy[r]), qz2 = pack2(mqz[r], mqz[r]);
-                        u64 a = fma2(qx2, tx.x, tt.x);
-                        u64 c2 = fma2(qx2, tx.y, tt.y);
-                        a = fma2(qy2, ty.x, a);
-                        c2 = fma2(qy2, ty.y, c2);
-                        a = fma2(qz2, tz.x, a);
-                        c2 = fma2(qz2, tz.y, c2);
-                        float a0, a1, a2, a3;
-                        unpack2(a, a0, a1);
-                        unpack2(c2, a2, a3);
-                        m[r] = min3f(m[r], a0, a1);
-                        m[r] = min3f(m[r], a2, a3);
-                    }
+                for (int r = 0; r < R; ++r) {
+                    const u64 qx2 = pack2(mqx[r], mqx[r]), qy2 = pack2(mqy[r], mqy[r]), qz2 = pack2(mqz[r], mqz[r]);
+                    u64 a = fma2(qx2, tx.x, tt.x);
+                    u64 c2 = fma2(qx2, tx.y, tt.y);
+                    a = fma2(qy2, ty.x, a);
+                    c2 = fma2(qy2, ty.y, c2);
+                    a = fma2(qz2, tz.x, a);
+                    c2 = fma2(qz2, tz.y, c2);
+                    float a0, a1, a2, a3;
+                    unpack2(a, a0, a1);
+                    unpack2(c2, a2, a3);
+                    m[r] = min3f(m[r], a0, a1);
+                    m[r] = min3f(m[r], a2, a3);
                 }
             }
+            if (CHUNK == 16 || (sb & (CHUNK / 16 - 1)) == CHUNK / 16 - 1) {
+                const int cid = chunk0 + sb / (CHUNK / 16);
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                sec[r] = fminf(sec[r], fmaxf(m[r], best[r]));
-                bchunk[r] = m[r] < best[r] ? chunk0 + c : bchunk[r];
-                best[r] = fminf(best[r], m[r]);
+                for (int r = 0; r < R; ++r) {
+                    sec[r] = fminf(sec[r], fmaxf(m[r], best[r]));
+                    bchunk[r] = m[r] < best[r] ? cid : bchunk[r];
+                    best[r] = fminf(best[r], m[r]);
+                    m[r] = INF;
+                }
             }
         }
         __syncthreads();  // every warp is done with this buffer

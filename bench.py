@@ -295,7 +295,10 @@ def run_ours(args):
         "kernel": "chamfer_nn_filter_tma_kernel<8,16,128,4,1024> (the event pair also spans chamfer_bounds_kernel, chamfer_prep_kernel, the "
                   "exact rescue pass chamfer_nn_exact2_kernel and chamfer_finalize_kernel, ~2 % together)",
         "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this exact shape, from the committed
+        # `ncu --set full` capture profiles/r01_ncu_chamfer_filter_v4.txt (143.6 MB + 27.4 MB); the algorithmic
+        # minimum is the two clouds read once (61 MB) + their SoA copies (82 MB) + 41 MB of keys: HBM is idle here
+        "traffic": 170.997e6 if (B, P) == (256, 10000) else None, "traffic_unit": "bytes per launch (ncu)",
         "evals_per_s": evals / (fwd_ms * 1e-3), "ms_per_launch": fwd_ms,
         "rescued_queries_frac": rescued.value / (2.0 * B * P),
         "peak_source": f"derived, MEASURED_PEAKS.json has no FP32 entry: 2 flop x 128 FP32 lanes x {info['sm_count']} SMs x "

@@ -240,14 +240,9 @@ int main(int argc, char **argv) {
     unsigned int *d_amb;
     CK(cudaMalloc(&aux, sizeof(PairAux) * B)); CK(cudaMalloc(&d_amb, 4));
     V(8, 16, 128, 3);
-    F(8, 16, 128, 4, 2048);
-    F(8, 32, 128, 4, 2048);
-    F(8, 64, 128, 4, 2048);
     T(8, 16, 128, 4, 1024);
     T(8, 32, 128, 4, 1024);
-    T(8, 16, 128, 4, 512);
-    T(8, 32, 128, 5, 1024);
     T(8, 64, 128, 4, 1024);
-    T(8, 32, 256, 2, 1024);
+    T(8, 32, 128, 3, 1024);
     return 0;
 }

@@ -1,5 +1,5 @@
 #!/bin/bash
-# One GPU-box pass: parity tests, bench, ncu launch list, ncu full capture of the dominant kernel, dev profiles.
+# One GPU-box pass: parity tests, bench, ncu launch list, ncu full captures of the dominant kernels, dev profiles.
 # Usage (from the repo root, under gpurun): bash tools/gpu_round.sh <tag>
 TAG=${1:-r01}
 OUT=gpurun_out
@@ -13,8 +13,11 @@ timeout 900 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err
 timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $OUT/${TAG}_bench_ref.json 2>> $OUT/${TAG}_bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 3 --warmup 3 --no-cpu --no-extra > $OUT/${TAG}_bench_under_ncu.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:chamfer_nn -s 3 -c 2 -f -o $OUT/${TAG}_chamfer \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:chamfer_nn_filter -s 3 -c 1 -f -o $OUT/${TAG}_chamfer \
     python bench.py --steps 3 --warmup 3 --no-cpu --no-extra > $OUT/${TAG}_ncu_chamfer.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:gcn_aggregate_tile -s 6 -c 1 -f -o $OUT/${TAG}_agg \
+    python tools/agg_bench.py 256 2 > $OUT/${TAG}_ncu_agg.log 2>&1
 timeout 600 python tools/recon_profile.py 16 > $OUT/${TAG}_recon_profile.txt 2>&1
 timeout 600 python tools/gemm_check.py 31184,300,300 31184,448,300 > $OUT/${TAG}_gemm_check.txt 2>&1
+timeout 600 python tools/agg_bench.py 256 20 > $OUT/${TAG}_agg_bench.txt 2>&1
 tail -3 $OUT/${TAG}_pytest_gpu.log; cat $OUT/${TAG}_smoke.log | tail -2; cat $OUT/${TAG}_bench.json; tail -5 $OUT/${TAG}_bench.err
