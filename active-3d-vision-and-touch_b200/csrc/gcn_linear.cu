@@ -249,7 +249,7 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ part, int nsplit,
 
 // tensor-core path (gemm_tf32x3.cu)
 bool tf32x3_eligible(const void *A, const void *D, int64_t M, int64_t K, int64_t N);
-size_t tf32x3_workspace_bytes(int64_t K, int64_t N);
+size_t tf32x3_workspace_bytes(int64_t M, int64_t K, int64_t N);
 int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act, int64_t M, int64_t K, int64_t N,
                 float *D, void *workspace, size_t workspace_bytes, cudaStream_t st);
 
@@ -271,9 +271,8 @@ static int check_gemm(const void *a, const void *b, const void *c, int64_t M, in
 }
 
 extern "C" size_t ptk_gcn_linear_workspace_bytes(int64_t M, int64_t K, int64_t N) {
-    (void)M;
-    if (K <= 0 || N <= 0) return 0;
-    return tf32x3_workspace_bytes(K, N);
+    if (M <= 0 || K <= 0 || N <= 0) return 0;
+    return tf32x3_workspace_bytes(M, K, N);
 }
 
 extern "C" int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int64_t K, int64_t N,

@@ -109,7 +109,8 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
 struct TGParams {
     int M, N, K;          // D is M x N, reduction K
     float *D;
-    const float *act;     // optional ReLU mask source, same shape as D
+    const uint32_t *mask; // optional ReLU mask of D, packed: bit (c & 31) of word [row * wpr + (c >> 5)] = act[row, c] > 0
+    int wpr;              // mask words per row = ceil(N / 32)
     int dbg;              // development switches (PTK_TG_DEBUG): 1 = skip A split, 2 = skip drain loads, 4 = skip MMAs
 };
 
@@ -256,23 +257,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // ReLU mask of this thread's 80 outputs, fetched while the pipeline fills (bit j: act > 0)
         uint32_t mbits[3] = {0u, 0u, 0u};
         if (MASK && row < p.M) {
+            // 80 mask bits of this thread's outputs from the packed row mask (4 word loads instead of 20 strided
+            // 16-byte loads of the activation itself: the epilogue is one thread per row)
             const int nb0 = n_base + half * 80;
-            const float *am = p.act + (size_t)row * p.N + nb0;
-            if ((p.N & 3) == 0) {
+            const int w0 = nb0 >> 5, sh = nb0 & 31;
+            const uint32_t *mr = p.mask + (size_t)row * p.wpr;
+            uint32_t w[4];
 #pragma unroll
-                for (int v = 0; v < 20; ++v) {
-                    if (nb0 + 4 * v + 4 <= p.N) {
-                        const float4 a = __ldg(reinterpret_cast<const float4 *>(am + 4 * v));
-                        const uint32_t m4 = (a.x > 0.f ? 1u : 0u) | (a.y > 0.f ? 2u : 0u) | (a.z > 0.f ? 4u : 0u) |
-                                            (a.w > 0.f ? 8u : 0u);
-                        mbits[(4 * v) >> 5] |= m4 << ((4 * v) & 31);
-                    }
-                }
-            } else {
+            for (int i = 0; i < 4; ++i) w[i] = (w0 + i < p.wpr) ? __ldg(mr + w0 + i) : 0u;
 #pragma unroll
-                for (int j = 0; j < 80; ++j)
-                    if (nb0 + j < p.N && am[j] > 0.f) mbits[j >> 5] |= 1u << (j & 31);
-            }
+            for (int i = 0; i < 3; ++i) mbits[i] = __funnelshift_r(w[i], w[i + 1], sh);
         }
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
             const int b = it % TG_NBUF;
@@ -593,21 +587,51 @@ static int make_map_ex(CUtensorMap *map, const float *base, int64_t rows, int64_
     return PTK_OK;
 }
 
+// bits[row * wpr + j] bit i = act[row, 32 j + i] > 0 (0 beyond N).  One warp per row, coalesced.
+__global__ void __launch_bounds__(256)
+relu_bits_kernel(const float *__restrict__ act, long long M, int N, int wpr, uint32_t *__restrict__ bits) {
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= M) return;
+    const float *a = act + (size_t)row * N;
+    uint32_t mine = 0u;
+    for (int j = 0; j < wpr; ++j) {
+        const int c = 32 * j + lane;
+        const uint32_t word = __ballot_sync(0xffffffffu, c < N && a[c] > 0.f);
+        if ((j & 31) == lane) mine = word;
+        if ((j & 31) == 31 || j == wpr - 1) {  // flush up to 32 words with one coalesced store
+            const int j0 = j & ~31;
+            if (j0 + lane <= j) bits[(size_t)row * wpr + j0 + lane] = mine;
+        }
+    }
+}
+
 bool tf32x3_eligible(const void *A, const void *D, int64_t M, int64_t K, int64_t N) {
     // TMA needs 16-byte aligned bases and row pitches; tiny reductions / outputs stay on the SIMT path
     return M >= 1 && K >= 32 && N >= 16 && (K % 4) == 0 && (((uintptr_t)A) % 16) == 0 && (((uintptr_t)D) % 16) == 0;
 }
 
-size_t tf32x3_workspace_bytes(int64_t K, int64_t N) { return 2 * sizeof(float) * (size_t)K * (size_t)N + 256; }
+// split B (hi, lo) + the packed ReLU mask of D (M rows x ceil(N/32) words; D has max(K, N) columns at most:
+// the same function sizes forward (D = M x N) and dgrad (D = M x K) workspaces)
+size_t tf32x3_workspace_bytes(int64_t M, int64_t K, int64_t N) {
+    const int64_t cols = K > N ? K : N;
+    return 2 * sizeof(float) * (size_t)K * (size_t)N + 512 + sizeof(uint32_t) * (size_t)M * (size_t)ceil_div(cols, 32);
+}
 
 // D (M x N) = A (M x K) . Bsrc, where Bsrc is either (K x N) row-major [b_is_kn = 1: transposed during the
 // split] or (N x K) row-major [b_is_kn = 0].  act (optional): D masked by act > 0.
 int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act, int64_t M, int64_t K, int64_t N,
                 float *D, void *workspace, size_t workspace_bytes, cudaStream_t st) {
-    PTK_REQUIRE(workspace && workspace_bytes >= tf32x3_workspace_bytes(K, N), PTK_ERR_WORKSPACE,
+    PTK_REQUIRE(workspace && workspace_bytes >= tf32x3_workspace_bytes(M, K, N), PTK_ERR_WORKSPACE,
                 "gemm_tf32x3: workspace too small");
     float *b_hi = reinterpret_cast<float *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float *b_lo = b_hi + (size_t)K * N;
+    uint32_t *mask = reinterpret_cast<uint32_t *>(((uintptr_t)(b_lo + (size_t)K * N) + 255) & ~(uintptr_t)255);
+    const int wpr = (int)ceil_div(N, 32);
+    if (act) {
+        relu_bits_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(act, (long long)M, (int)N, wpr, mask);
+        PTK_CHECK_LAUNCH();
+    }
     const long long elems = (long long)K * N;
     if (b_is_kn)
         split_tf32_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, st>>>(Bsrc, (int)K, (int)N, 1, b_hi, b_lo);
@@ -624,7 +648,7 @@ int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act
     if (rc) return rc;
 
     TGParams p;
-    p.M = (int)M; p.N = (int)N; p.K = (int)K; p.D = D; p.act = act;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K; p.D = D; p.mask = act ? mask : nullptr; p.wpr = wpr;
     static int dbg = -1;
     if (dbg < 0) { const char *e = getenv("PTK_TG_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.dbg = dbg;
