@@ -237,6 +237,63 @@ static void launch_fwd(const float *X, const float *W, float *H, int64_t M, int6
     sgemm_fwd_kernel<BM><<<grid, BM * 2, 0, st>>>(X, W, H, (int)M, (int)N, (int)K);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Skinny layers (N <= 4: the 300 -> 3 output layer of every GCN, vision/model.py:296-301).  As GEMMs they are
+// matrix-vector shaped and HBM/L2-bound; the tiled kernels above spend 80 us on them, these take ~10 us.
+//   forward : one warp per row, 128-bit loads of X, W (K x N) in shared memory, warp reduction
+//   wgrad   : a CTA sums a slab of rows for every k (thread = k), partials reduced by splitk_reduce_kernel
+// (The output layer has no activation behind it, so the k-sequential rounding of the exact forward kernel is
+// not needed here.)
+constexpr int SK_MAXN = 4;
+
+__global__ void __launch_bounds__(256)
+skinny_fwd_kernel(const float *__restrict__ X, const float *__restrict__ W, float *__restrict__ H, long long M, int K,
+                  int N) {
+    extern __shared__ __align__(16) float sk_w[];  // [K][4]
+    for (int e = threadIdx.x; e < K * SK_MAXN; e += 256) {
+        const int k = e >> 2, n = e & 3;
+        sk_w[e] = n < N ? W[(size_t)k * N + n] : 0.f;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const float4 *x4 = reinterpret_cast<const float4 *>(X + (size_t)row * K);
+    float acc[SK_MAXN] = {0.f, 0.f, 0.f, 0.f};
+    for (int q = lane; q < K / 4; q += 32) {
+        const float4 x = __ldg(x4 + q);
+        const float xv[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float4 w = *reinterpret_cast<const float4 *>(&sk_w[(q * 4 + j) * SK_MAXN]);
+            acc[0] = fmaf(xv[j], w.x, acc[0]); acc[1] = fmaf(xv[j], w.y, acc[1]);
+            acc[2] = fmaf(xv[j], w.z, acc[2]); acc[3] = fmaf(xv[j], w.w, acc[3]);
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < SK_MAXN; ++n) acc[n] = warp_sum(acc[n]);
+    if (lane < N) H[(size_t)row * N + lane] = lane == 0 ? acc[0] : (lane == 1 ? acc[1] : (lane == 2 ? acc[2] : acc[3]));
+}
+
+// part[blockIdx.x][k][n] = sum over the CTA's rows of X[m,k] * gH[m,n]
+__global__ void __launch_bounds__(1024)
+skinny_wgrad_kernel(const float *__restrict__ X, const float *__restrict__ gH, float *__restrict__ part, long long M,
+                    int K, int N, long long rows_per_cta) {
+    const long long r0 = (long long)blockIdx.x * rows_per_cta;
+    const long long r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
+    for (int k = threadIdx.x; k < K; k += blockDim.x) {
+        float acc[SK_MAXN] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+        for (long long m = r0; m < r1; ++m) {
+            const float x = X[(size_t)m * K + k];
+#pragma unroll
+            for (int n = 0; n < SK_MAXN; ++n)
+                if (n < N) acc[n] = fmaf(x, __ldg(gH + (size_t)m * N + n), acc[n]);
+        }
+        for (int n = 0; n < N; ++n) part[((size_t)blockIdx.x * K + k) * N + n] = acc[n];
+    }
+}
+
 // second stage of the split wgrad: out[e] = sum_s part[s, e] in ascending s (deterministic)
 __global__ void splitk_reduce_kernel(const float *__restrict__ part, int nsplit, long long elems,
                                      float *__restrict__ out) {
@@ -300,6 +357,12 @@ extern "C" int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int
         PTK_CHECK_LAUNCH();
         return PTK_OK;
     }
+    if (N <= SK_MAXN && (K % 4) == 0 && ((uintptr_t)X % 16) == 0 && (size_t)K * SK_MAXN * 4 <= 48 * 1024) {
+        skinny_fwd_kernel<<<(unsigned)ceil_div(M, 8), 256, (size_t)K * SK_MAXN * sizeof(float), as_stream(stream)>>>(
+            X, W, H, (long long)M, (int)K, (int)N);
+        PTK_CHECK_LAUNCH();
+        return PTK_OK;
+    }
     dim3 grid((unsigned)ceil_div(N, GL_BN), (unsigned)ceil_div(M, GL_BM));
     sgemm_kernel<true, false, false, false><<<grid, GL_THREADS, 0, as_stream(stream)>>>(
         X, K, W, N, H, N, M, N, K, 0, nullptr);
@@ -330,7 +393,14 @@ extern "C" int ptk_gcn_linear_dgrad(const float *gH, const float *W, const float
     return PTK_OK;
 }
 
+static int skinny_wgrad_ctas(int64_t M) {
+    const int64_t want = 3LL * sm_count();  // three 320-thread CTAs per SM keep enough loads in flight
+    const int64_t n = M / 16 < want ? M / 16 : want;
+    return (int)(n > 0 ? n : 1);
+}
+
 static int wgrad_splits(int64_t M, int64_t K, int64_t N) {
+    if (N <= SK_MAXN) return skinny_wgrad_ctas(M);
     const int64_t tiles = ceil_div(K, GL_BM) * ceil_div(N, GL_BN);
     int64_t want = ceil_div(2LL * sm_count() * 2, tiles);
     int64_t max_s = ceil_div(M, 4 * GL_BK);
@@ -365,6 +435,19 @@ extern "C" int ptk_gcn_linear_wgrad(const float *X, const float *gH, int64_t M, 
         return PTK_OK;
     }
     PTK_REQUIRE(algo != 2, PTK_ERR_SHAPE, "gcn_linear_wgrad: shape not eligible for the tensor-core path");
+    if (N <= SK_MAXN) {
+        const int ctas = skinny_wgrad_ctas(M);
+        const long long rows_per_cta = (long long)ceil_div(M, ctas);
+        float *part = reinterpret_cast<float *>(workspace);
+        cudaStream_t st = as_stream(stream);
+        const int threads = (int)(K >= 1024 ? 1024 : ceil_div(K, 32) * 32);
+        skinny_wgrad_kernel<<<ctas, threads, 0, st>>>(X, gH, part, (long long)M, (int)K, (int)N, rows_per_cta);
+        PTK_CHECK_LAUNCH();
+        const long long elems = (long long)K * N;
+        splitk_reduce_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, st>>>(part, ctas, elems, gW);
+        PTK_CHECK_LAUNCH();
+        return PTK_OK;
+    }
     // gW (K x N) = X^T . gH : GEMM with m=K, n=N, k=M; A[m=k_in][k=row] = X[row*K + k_in]
     const int ns = wgrad_splits(M, K, N);
     const int64_t kper = ceil_div(ceil_div(M, ns), GL_BK) * GL_BK;

@@ -20,7 +20,7 @@ vision = torch.from_numpy(meshes["vision_verts"]).to(dev)[None].repeat(Bs, 1, 1)
 touch = torch.rand(Bs, 125, 3, device=dev) * 0.02 + 0.2
 feats = [torch.rand(Bs, 1824, 448, device=dev), torch.rand(Bs, 1949, 448, device=dev), torch.rand(Bs, 1949, 448, device=dev)]
 gt = torch.nn.functional.normalize(torch.randn(Bs, 10000, 3, device=dev), dim=-1) * 0.25
-opt = torch.optim.Adam(net.parameters(), lr=3e-4)
+opt = torch.optim.Adam(net.parameters(), lr=3e-4, fused=True)
 def step():
     opt.zero_grad(set_to_none=True)
     verts = net(vision, touch, lambda it, v: feats[it])
