@@ -376,14 +376,16 @@ __global__ void __launch_bounds__(AG_THREADS, 4)
 gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                           const float *__restrict__ val, const AggHubs hb, unsigned hub_slots, int Nv,
                           const float *__restrict__ in, int B, int C, int L, const float *__restrict__ bias,
-                          int relu, float *__restrict__ out, int TV, int BG, int n_tiles, int hubs_first) {
+                          int relu, float *__restrict__ out, int TV, int BG, int n_tiles, int hubs_first, int ldi,
+                          int ldo) {
+    // ldi / ldo: row strides (floats) of in / out; C channels are handled ([0, L) aggregated, [L, C) passed through)
     __shared__ __align__(16) uint32_t s_off[AG_WARPS][AT_STRIP];
     __shared__ __align__(16) float s_w[AG_WARPS][AT_STRIP];
     __shared__ __align__(16) float s_part[AG_WARPS][NG * 32 * 4];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ngroups = C >> 2;
     const int gath = (L + 3) >> 2;
-    const uint32_t row_bytes = (uint32_t)C * 4u;
+    const uint32_t row_bytes = (uint32_t)ldi * 4u;
     bool on[NG];
     uint32_t voff[NG];  // byte offset of the lane's channel group (clamped to the last aggregated group)
 #pragma unroll
@@ -391,7 +393,7 @@ gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__r
         on[n] = lane + 32 * n < gath;
         voff[n] = (uint32_t)min(lane + 32 * n, gath - 1) * 16u;
     }
-    const size_t bstride = (size_t)Nv * C;  // floats per batch element
+    const size_t bstride = (size_t)Nv * ldi, bstride_o = (size_t)Nv * ldo;  // floats per batch element
     const int npass = ngroups - gath;       // pure pass-through groups
     const bool pass0 = lane < npass, pass1 = 32 + lane < npass;
     const int pv0 = (gath + lane) * 4, pv1 = (gath + 32 + lane) * 4;  // float offsets inside the row
@@ -399,8 +401,8 @@ gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__r
     // One output row of one batch element by one warp.  `acc` arrives initialised (0, or alpha * y*);
     // the row's (offset, weight) list is in the warp's strip when staged, else it is streamed in chunks.
     auto do_row = [&](int i, const float *inb, float *outb, int beg, int end, int n4, float (&acc)[NG][4]) {
-        const float *self = inb + (size_t)i * C;
-        float *o = outb + (size_t)i * C;
+        const float *self = inb + (size_t)i * ldi;
+        float *o = outb + (size_t)i * ldo;
         // request the pass-through part of the row first (up to two groups per lane stay in registers)
         float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1 = p0;
         if (pass0) p0 = __ldcs(reinterpret_cast<const float4 *>(self + pv0));
@@ -427,6 +429,8 @@ gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__r
     // the hub CTAs pull into L2 are the ones the group's tiles gather next.
     // (hubs_first: all hub CTAs lead the grid instead -- better when the whole input is L2-resident and the
     // only concern is starting the long hub rows early.)
+    // (A persistent-CTA variant -- a few CTAs per SM walking the work items -- was measured slower at every batch
+    // size: 314 vs 278 us at B=256, no gain at B=16.)
     const unsigned per_group = hub_slots + (unsigned)n_tiles;
     unsigned group, local;
     if (hubs_first) {
@@ -460,7 +464,7 @@ gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__r
         const int per = (((end - beg) + AG_WARPS - 1) / AG_WARPS + 3) & ~3;
         const int wbeg = min(end, beg + warp * per), wend = min(end, wbeg + per);
         const float *inb = in + b * bstride;
-        float *outb = out + b * bstride;
+        float *outb = out + b * bstride_o;
         const char *base[NG];
 #pragma unroll
         for (int n = 0; n < NG; ++n) base[n] = reinterpret_cast<const char *>(inb) + voff[n];
@@ -484,10 +488,10 @@ gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__r
             }
         if (!common) {
             if (warp == 0) {
-                row_epilogue<NG>(acc, on, inb + (size_t)hrow * C, outb + (size_t)hrow * C, bias, L, relu);
+                row_epilogue<NG>(acc, on, inb + (size_t)hrow * ldi, outb + (size_t)hrow * ldo, bias, L, relu);
             } else {
-                const float *self = inb + (size_t)hrow * C;
-                float *o = outb + (size_t)hrow * C;
+                const float *self = inb + (size_t)hrow * ldi;
+                float *o = outb + (size_t)hrow * ldo;
                 for (int v = gath + (warp - 1) * 32 + lane; v < ngroups; v += (AG_WARPS - 1) * 32)
                     __stcs(reinterpret_cast<float4 *>(o + v * 4), relu4(__ldcs(reinterpret_cast<const float4 *>(self + v * 4)), relu));
             }
@@ -520,8 +524,8 @@ gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__r
         int n4 = 0;
         if (end - beg <= AT_STRIP) n4 = strip_stage(col, val, beg, end - beg, row_bytes, s_off[warp], s_w[warp]);
         const float *inb = in + b0 * bstride;
-        float *outb = out + b0 * bstride;
-        for (int bb = 0; bb < nb; ++bb, inb += bstride, outb += bstride) {
+        float *outb = out + b0 * bstride_o;
+        for (int bb = 0; bb < nb; ++bb, inb += bstride, outb += bstride_o) {
             float acc[NG][4];
 #pragma unroll
             for (int n = 0; n < NG; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
@@ -656,21 +660,26 @@ extern "C" int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, c
                                     const float *common_w, int32_t n_common, const float *hub_alpha,
                                     const uint8_t *row_skip, int64_t Nv, const float *in, int64_t B,
                                     int64_t C, int64_t L, const float *bias, int relu, float *out,
-                                    ptk_stream_t stream) {
+                                    int64_t ldi, int64_t ldo, ptk_stream_t stream) {
+    if (ldi <= 0) ldi = C;
+    if (ldo <= 0) ldo = C;
     PTK_REQUIRE(rowptr && col && val && in && out, PTK_ERR_SHAPE, "gcn_aggregate: null pointer");
     PTK_REQUIRE(B > 0 && Nv > 0 && C > 0 && L >= 0 && L <= C, PTK_ERR_SHAPE,
                 "gcn_aggregate: bad sizes (B=%lld, Nv=%lld, C=%lld, L=%lld)", (long long)B,
                 (long long)Nv, (long long)C, (long long)L);
     PTK_REQUIRE(in != out, PTK_ERR_SHAPE, "gcn_aggregate: in-place aggregation is not supported");
+    PTK_REQUIRE(ldi >= C && ldo >= C, PTK_ERR_SHAPE, "gcn_aggregate: row strides must be >= C");
+    const bool strided = ldi != C || ldo != C;
     const bool common = n_common > 0;
     PTK_REQUIRE(!common || (hubs && n_hubs > 0 && common_col && common_w && hub_alpha && row_skip), PTK_ERR_SHAPE,
                 "gcn_aggregate: a common neighbour set needs hubs, common_col, common_w, hub_alpha and row_skip");
     cudaStream_t st = as_stream(stream);
     const long long rows = (long long)B * Nv;
-    const bool vec = (C % 4 == 0) && ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)bias)) % 16 == 0);
+    const bool vec = (C % 4 == 0) && (ldi % 4 == 0) && (ldo % 4 == 0) &&
+                     ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)bias)) % 16 == 0);
     const bool have_hubs = hubs && n_hubs > 0;
     const int gath = (int)((L + 3) / 4);
-    PTK_REQUIRE(B <= 0x7fffffff && Nv * C * 4 <= 0xffffffffLL, PTK_ERR_SHAPE, "gcn_aggregate: one batch element must be < 4 GiB");
+    PTK_REQUIRE(B <= 0x7fffffff && Nv * ldi * 4 <= 0xffffffffLL, PTK_ERR_SHAPE, "gcn_aggregate: one batch element must be < 4 GiB");
     if (vec && gath >= 1 && gath <= 96) {
         // TV = 8 (one row per warp) keeps few batch elements in flight at a time: the rows a batch element
         // gathers stay in L2 until all its tiles are done.  BG amortises the staging of the row structure.
@@ -682,14 +691,15 @@ extern "C" int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, c
         const int n_tiles = (int)ceil_div(Nv, TV);
         const unsigned hub_slots = have_hubs ? (unsigned)(common ? BG : BG * n_hubs) : 0u;  // per batch group
         const unsigned grid = (unsigned)((hub_slots + n_tiles) * ceil_div(B, BG));
-        const int hubs_first = (double)B * Nv * C * 8.0 < 100e6;  // input + output fit the 126 MB L2
+        const int hubs_first = (double)B * Nv * (ldi + ldo) * 4.0 < 100e6;  // input + output fit the 126 MB L2
         AggHubs hb;
         hb.hubs = hubs; hb.n_hubs = have_hubs ? n_hubs : 0;
         hb.common_col = common_col; hb.common_w = common_w; hb.n_common = common ? n_common : 0;
         hb.alpha = hub_alpha; hb.row_skip = common ? row_skip : nullptr;
 #define PTK_TILE(NGv)                                                                                        \
     gcn_aggregate_tile_kernel<NGv><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hb, hub_slots, (int)Nv, in, \
-                                                                (int)B, (int)C, (int)L, bias, relu, out, TV, BG, n_tiles, hubs_first)
+                                                                (int)B, (int)C, (int)L, bias, relu, out, TV, BG, n_tiles, hubs_first, \
+                                                                (int)ldi, (int)ldo)
         if (gath <= 32) PTK_TILE(1);
         else if (gath <= 64) PTK_TILE(2);
         else PTK_TILE(3);
@@ -697,6 +707,7 @@ extern "C" int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, c
         PTK_CHECK_LAUNCH();
         return PTK_OK;
     }
+    PTK_REQUIRE(!strided, PTK_ERR_SHAPE, "gcn_aggregate: row strides need the vector path (C, ldi, ldo %% 4 == 0, 1 <= L <= 384)");
     PTK_REQUIRE(!common, PTK_ERR_SHAPE,
                 "gcn_aggregate: the common-set form needs the vector path (C %% 4 == 0, 1 <= L, ceil(L/4) <= 96, "
                 "16-byte aligned); pass the unreduced CSR otherwise");
@@ -727,7 +738,7 @@ extern "C" int ptk_gcn_aggregate(const int32_t *rowptr, const int32_t *col, cons
                                  int64_t B, int64_t C, int64_t L, const float *bias, int relu,
                                  float *out, ptk_stream_t stream) {
     return ptk_gcn_aggregate_ex(rowptr, col, val, hubs, n_hubs, nullptr, nullptr, 0, nullptr, nullptr, Nv, in, B,
-                                C, L, bias, relu, out, stream);
+                                C, L, bias, relu, out, 0, 0, stream);
 }
 
 extern "C" size_t ptk_gcn_bias_grad_workspace_bytes(int64_t M, int64_t L) {

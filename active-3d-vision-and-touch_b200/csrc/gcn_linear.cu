@@ -132,7 +132,10 @@ constexpr int FW_BN = 160, FW_BK = 16, FW_PAD = 4;
 template <int BM>
 __global__ void __launch_bounds__(BM * 2, BM <= 32 ? 6 : (BM <= 64 ? 3 : 2))
 sgemm_fwd_kernel(const float *__restrict__ A, const float *__restrict__ Bm, float *__restrict__ Cm, int M, int N,
-                 int K) {
+                 int K, int ld1, int nsplit, float *__restrict__ C2, int ld2, int relu2) {
+    // Output: columns n < nsplit -> Cm[m * ld1 + n]; columns n >= nsplit -> C2[m * ld2 + n], optionally ReLU'd
+    // (the fused GCN-layer form: the propagated slice goes to a compact scratch for the aggregation, the
+    // pass-through slice straight into the layer output).  Plain GEMM: nsplit = N, ld1 = N.
     constexpr int T = BM * 2;
     __shared__ __align__(16) float As[2][FW_BK][BM + FW_PAD];
     __shared__ __align__(16) float Bs[2][FW_BK][FW_BN];
@@ -223,18 +226,45 @@ sgemm_fwd_kernel(const float *__restrict__ A, const float *__restrict__ Bm, floa
     for (int i = 0; i < 8; ++i) {
         const int m = m0 + (i < 4 ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4));
         if (m >= M) continue;
-        float *row = Cm + (size_t)m * N;
+        float *row1 = Cm + (size_t)m * ld1;
+        float *row2 = C2 + (size_t)m * ld2;
         const int na = n0 + tx * 4, nb = n0 + 64 + tx * 4, nc = n0 + 128 + tx * 2;
-        if (na + 3 < N) *reinterpret_cast<ulonglong2 *>(row + na) = make_ulonglong2(acc[i][0], acc[i][1]);
-        if (nb + 3 < N) *reinterpret_cast<ulonglong2 *>(row + nb) = make_ulonglong2(acc[i][2], acc[i][3]);
-        if (nc + 1 < N) *reinterpret_cast<unsigned long long *>(row + nc) = acc[i][4];
+        auto relu_pair = [&](unsigned long long v) {
+            if (!relu2) return v;
+            float lo = __uint_as_float((unsigned)v), hi = __uint_as_float((unsigned)(v >> 32));
+            lo = fmaxf(lo, 0.f);
+            hi = fmaxf(hi, 0.f);
+            return ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
+        };
+        auto put4 = [&](int n, unsigned long long a, unsigned long long b) {
+            if (n + 3 >= N) return;
+            if (n < nsplit)
+                *reinterpret_cast<ulonglong2 *>(row1 + n) = make_ulonglong2(a, b);
+            else
+                *reinterpret_cast<ulonglong2 *>(row2 + n) = make_ulonglong2(relu_pair(a), relu_pair(b));
+        };
+        put4(na, acc[i][0], acc[i][1]);
+        put4(nb, acc[i][2], acc[i][3]);
+        if (nc + 1 < N) {
+            if (nc < nsplit)
+                *reinterpret_cast<unsigned long long *>(row1 + nc) = acc[i][4];
+            else
+                *reinterpret_cast<unsigned long long *>(row2 + nc) = relu_pair(acc[i][4]);
+        }
     }
 }
 
 template <int BM>
-static void launch_fwd(const float *X, const float *W, float *H, int64_t M, int64_t K, int64_t N, cudaStream_t st) {
+static void launch_fwd(const float *X, const float *W, float *H, int64_t M, int64_t K, int64_t N, cudaStream_t st,
+                       int ld1 = 0, int nsplit = -1, float *C2 = nullptr, int ld2 = 0, int relu2 = 0) {
     dim3 grid((unsigned)ceil_div(N, FW_BN), (unsigned)ceil_div(M, BM));
-    sgemm_fwd_kernel<BM><<<grid, BM * 2, 0, st>>>(X, W, H, (int)M, (int)N, (int)K);
+    if (nsplit < 0) {
+        nsplit = (int)N;
+        ld1 = (int)N;
+        C2 = H;
+        ld2 = (int)N;
+    }
+    sgemm_fwd_kernel<BM><<<grid, BM * 2, 0, st>>>(X, W, H, (int)M, (int)N, (int)K, ld1, nsplit, C2, ld2, relu2);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -366,6 +396,21 @@ extern "C" int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int
     dim3 grid((unsigned)ceil_div(N, GL_BN), (unsigned)ceil_div(M, GL_BM));
     sgemm_kernel<true, false, false, false><<<grid, GL_THREADS, 0, as_stream(stream)>>>(
         X, K, W, N, H, N, M, N, K, 0, nullptr);
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}
+
+extern "C" int ptk_gcn_linear_fwd_split(const float *X, const float *W, int64_t M, int64_t K, int64_t N,
+                                        int64_t n_split, float *head, float *out, int relu, ptk_stream_t stream) {
+    int rc = check_gemm(X, W, out, M, K, N);
+    if (rc) return rc;
+    PTK_REQUIRE(head && n_split > 0 && n_split < N && (n_split % 4) == 0, PTK_ERR_SHAPE,
+                "gcn_linear_fwd_split: n_split must be a multiple of 4 inside (0, N)");
+    PTK_REQUIRE((K % 4) == 0 && (N % 4) == 0 && N >= 64 && M < (1LL << 31) && ceil_div(M, 64) <= 65535, PTK_ERR_SHAPE,
+                "gcn_linear_fwd_split: needs K %% 4 == 0, N %% 4 == 0, N >= 64");
+    PTK_REQUIRE((((uintptr_t)X | (uintptr_t)W | (uintptr_t)head | (uintptr_t)out) % 16) == 0, PTK_ERR_ALIGN,
+                "gcn_linear_fwd_split: pointers must be 16-byte aligned");
+    launch_fwd<64>(X, W, head, M, K, N, as_stream(stream), (int)n_split, (int)n_split, out, (int)N, relu);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }

@@ -276,7 +276,7 @@ def _aggregate(g: Graph, H3, Lc, bias, relu, transpose=False, out=None):
         _lib.check(_lib.lib().ptk_gcn_aggregate_ex(_p(k.rowptr), _p(k.col), _p(k.val), _p(k.hubs), k.n_hubs,
                                                    _p(k.common_col), _p(k.common_w), k.n_common, _p(k.alpha),
                                                    _p(k.row_skip), Nv, _p(H3), B, Cc, Lc, _p(bias), int(relu),
-                                                   _p(out), _stream()), "ptk_gcn_aggregate_ex")
+                                                   _p(out), 0, 0, _stream()), "ptk_gcn_aggregate_ex")
         return out
     if transpose:
         rp, col, val, hubs, nh = g.rowptr_t, g.col_t, g.val_t, g.hubs_t, g.n_hubs_t
@@ -284,6 +284,31 @@ def _aggregate(g: Graph, H3, Lc, bias, relu, transpose=False, out=None):
         rp, col, val, hubs, nh = g.rowptr, g.col, g.val, g.hubs, g.n_hubs
     _lib.check(_lib.lib().ptk_gcn_aggregate(_p(rp), _p(col), _p(val), _p(hubs), nh, Nv, _p(H3), B, Cc, Lc,
                                             _p(bias), int(relu), _p(out), _stream()), "ptk_gcn_aggregate")
+    return out
+
+
+def _fused_layer_ok(K, N, Lc, relu):
+    """Shapes the fused forward (ptk_gcn_linear_fwd_split + strided aggregate) covers: a 'cut' layer whose
+    propagated slice, rounded up to whole float4 groups, is a proper prefix of a >= 64-wide output."""
+    Lp = (Lc + 3) // 4 * 4
+    return relu and K % 4 == 0 and N % 4 == 0 and N >= 64 and 1 <= Lc and Lp < N and Lp <= 384
+
+
+def _fused_layer_fwd(g: Graph, X2, W2, Lc, bias, B, Nv, head_buf):
+    """One GCN_layer.forward (vision/model.py:351-363) in two kernels: the exact FFMA2 GEMM writes the
+    propagated slice H[:, :Lp] into the compact `head_buf` and relu(H[:, Lp:]) straight into the layer
+    output; the aggregation gathers from the head and fills out[:, :, :Lp]."""
+    M, K = X2.shape
+    N = W2.shape[1]
+    Lp = (Lc + 3) // 4 * 4
+    out = torch.empty(B, Nv, N, dtype=torch.float32, device=X2.device)
+    L = _lib.lib()
+    _lib.check(L.ptk_gcn_linear_fwd_split(_p(X2), _p(W2), M, K, N, Lp, _p(head_buf), _p(out), 1, _stream()),
+               "ptk_gcn_linear_fwd_split")
+    k = g.fwd_k
+    _lib.check(L.ptk_gcn_aggregate_ex(_p(k.rowptr), _p(k.col), _p(k.val), _p(k.hubs), k.n_hubs, _p(k.common_col),
+                                      _p(k.common_w), k.n_common, _p(k.alpha), _p(k.row_skip), Nv, _p(head_buf), B,
+                                      Lp, Lc, _p(bias), 1, _p(out), Lp, N, _stream()), "ptk_gcn_aggregate_ex")
     return out
 
 
@@ -361,11 +386,19 @@ class _GCNStack(torch.autograd.Function):
                 K = acts[-1].shape[2]
                 W2 = _f32c(Ws[l]).reshape(K, -1)
                 N = W2.shape[1]
+                bias = _f32c(bs[l])
+                if fwd_algo == GEMM_FFMA and _fused_layer_ok(K, N, Ls[l], relus[l]) and bias.data_ptr() % 16 == 0:
+                    Lp = (Ls[l] + 3) // 4 * 4
+                    head = Hbuf.get(("head", Lp))
+                    if head is None:
+                        head = Hbuf[("head", Lp)] = torch.empty(B * Nv, Lp, dtype=torch.float32, device=X.device)
+                    acts.append(_fused_layer_fwd(graph, acts[-1].reshape(B * Nv, K), W2, Ls[l], bias, B, Nv, head))
+                    continue
                 H = Hbuf.get(N)
                 if H is None:
                     H = Hbuf[N] = torch.empty(B * Nv, N, dtype=torch.float32, device=X.device)
                 _linear_fwd(acts[-1].reshape(B * Nv, K), W2, out=H, algo_id=fwd_algo)
-                acts.append(_aggregate(graph, H.reshape(B, Nv, N), Ls[l], _f32c(bs[l]), relus[l]))
+                acts.append(_aggregate(graph, H.reshape(B, Nv, N), Ls[l], bias, relus[l]))
         ctx.save_for_backward(*acts, *[_f32c(w) for w in Ws])
         ctx.graph, ctx.Ls, ctx.relus, ctx.n = graph, Ls, relus, n
         ctx.wshapes = [w.shape for w in Ws]

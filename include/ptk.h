@@ -134,12 +134,15 @@ int ptk_gcn_aggregate(const int32_t *rowptr, const int32_t *col, const float *va
  * so the ~1150 boundary rows every touch-chart centre vertex is linked to (utils.py:126-128) are read once
  * per batch element instead of once per hub row.  row_skip (Nv bytes) flags the hub rows.  n_common = 0
  * (all common_* / hub_alpha / row_skip NULL) is exactly ptk_gcn_aggregate.  Needs the vector path
- * (C % 4 == 0, 16-byte aligned, 1 <= L, L <= 384). */
+ * (C % 4 == 0, 16-byte aligned, 1 <= L, L <= 384).
+ * ldi / ldo: row strides (floats) of in / out, 0 = C.  With ptk_gcn_linear_fwd_split this is the fused
+ * layer: in = the compact (B,Nv,n_split) head the GEMM wrote, C = n_split, ldo = layer width. */
 int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, const float *val,
                          const int32_t *hubs, int32_t n_hubs, const int32_t *common_col,
                          const float *common_w, int32_t n_common, const float *hub_alpha,
                          const uint8_t *row_skip, int64_t Nv, const float *in, int64_t B, int64_t C,
-                         int64_t L, const float *bias, int relu, float *out, ptk_stream_t stream);
+                         int64_t L, const float *bias, int relu, float *out, int64_t ldi, int64_t ldo,
+                         ptk_stream_t stream);
 /* gbias[c] = sum_{rows} g[row,c] for c < L, 0 for L <= c < C  (g is (M,C)); overwrites gbias.
  * Deterministic two-stage column sum; workspace from ptk_gcn_bias_grad_workspace_bytes. */
 size_t ptk_gcn_bias_grad_workspace_bytes(int64_t M, int64_t L);
@@ -169,6 +172,13 @@ size_t ptk_gcn_linear_workspace_bytes(int64_t M, int64_t K, int64_t N); /* fwd a
 #define PTK_GEMM_TF32X3 2
 int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int64_t K, int64_t N, float *H, int algo,
                        void *workspace, size_t workspace_bytes, ptk_stream_t stream);
+/* Fused GCN-layer forward GEMM (exact-FP32 kernel): H = X.W is never materialised as one matrix --
+ * columns [0, n_split) go to `head` (M, n_split) for ptk_gcn_aggregate_ex, columns [n_split, N) are
+ * ReLU'd (relu != 0) and written straight into `out` (M, N): GCN_layer.forward's `cat(adj @ H[:, :L],
+ * H[:, L:])` + activation (vision/model.py:355-363) without the round trip of the pass-through slice.
+ * n_split = L rounded up to a multiple of 4; needs K % 4 == 0, N % 4 == 0, N >= 64, 16-byte alignment. */
+int ptk_gcn_linear_fwd_split(const float *X, const float *W, int64_t M, int64_t K, int64_t N, int64_t n_split,
+                             float *head, float *out, int relu, ptk_stream_t stream);
 int ptk_gcn_linear_dgrad(const float *gH, const float *W, const float *act, int64_t M, int64_t K,
                          int64_t N, float *gX, int algo, void *workspace, size_t workspace_bytes,
                          ptk_stream_t stream);
