@@ -11,7 +11,7 @@ struct ptk_host_ctx {
     int device;
     cudaStream_t stream;       // kernels + result copies
     cudaStream_t copy_stream;  // input copies, so that chunk i+1 uploads while chunk i computes
-    cudaEvent_t ev_in[8];
+    cudaEvent_t ev_in[9];
     void *buf[16];
     size_t cap[16];
 };
@@ -59,7 +59,7 @@ extern "C" ptk_host_ctx *ptk_host_ctx_create(int device) {
     bool ok = cudaSetDevice(device) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) == cudaSuccess &&
               cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) == cudaSuccess;
-    for (int i = 0; ok && i < 8; ++i) ok = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < 9; ++i) ok = cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming) == cudaSuccess;
     if (!ok) {
         set_error("host_ctx_create: cannot open device %d: %s", device,
                   cudaGetErrorString(cudaGetLastError()));
@@ -74,7 +74,7 @@ extern "C" void ptk_host_ctx_destroy(ptk_host_ctx *c) {
     cudaSetDevice(c->device);
     for (int i = 0; i < 16; ++i)
         if (c->buf[i]) cudaFree(c->buf[i]);
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 9; ++i)
         if (c->ev_in[i]) cudaEventDestroy(c->ev_in[i]);
     cudaStreamDestroy(c->copy_stream);
     cudaStreamDestroy(c->stream);
@@ -111,19 +111,31 @@ extern "C" int ptk_host_chamfer(ptk_host_ctx *c, const float *x, const float *y,
         PTK_CHECK_CUDA(cudaMemcpyAsync(dgc, grad_cham, (size_t)B * 4, cudaMemcpyHostToDevice, st));
     }
     // Chunked pipeline over whole cloud pairs: the upload of chunk i+1 (copy stream) overlaps the kernels of
-    // chunk i.  A chunk keeps enough CTAs for >= 4 waves (see plan_nn in chamfer.cu) so the scan itself does
-    // not change; at most 8 chunks.
+    // chunk i.  The first chunk is small (B/8) so that little of its upload is exposed; the others keep enough
+    // CTAs for >= 4 waves (see plan_nn in chamfer.cu) so the scan itself does not change; at most 8 chunks.
     const int64_t Pm = P1 > P2 ? P1 : P2;
     const int64_t ctas_per_pair = 2 * ceil_div(Pm, 1024);
     int64_t bc_min = ceil_div(4LL * sm_count() * 4, ctas_per_pair);
     if (bc_min < 1) bc_min = 1;
-    int64_t n_chunks = B / bc_min;
-    if (n_chunks < 1) n_chunks = 1;
-    if (n_chunks > 8) n_chunks = 8;
-    const int64_t bc = ceil_div(B, n_chunks);
-    int ci = 0;
-    for (int64_t b0 = 0; b0 < B; b0 += bc, ++ci) {
-        const int64_t nb = B - b0 < bc ? B - b0 : bc;
+    int64_t bounds[10];
+    int nchunks = 0;
+    bounds[0] = 0;
+    if (B >= 2 * bc_min) {
+        const int64_t first = B / 8 > 0 ? B / 8 : 1;
+        int64_t rest_chunks = (B - first) / bc_min;
+        if (rest_chunks < 1) rest_chunks = 1;
+        if (rest_chunks > 7) rest_chunks = 7;
+        const int64_t bc = ceil_div(B - first, rest_chunks);
+        bounds[++nchunks] = first;
+        while (bounds[nchunks] < B) {
+            const int64_t nxt = bounds[nchunks] + bc < B ? bounds[nchunks] + bc : B;
+            bounds[++nchunks] = nxt;
+        }
+    } else {
+        bounds[++nchunks] = B;
+    }
+    for (int ci = 0; ci < nchunks; ++ci) {
+        const int64_t b0 = bounds[ci], nb = bounds[ci + 1] - bounds[ci];
         const size_t ox = (size_t)b0 * P1, oy = (size_t)b0 * P2;
         PTK_CHECK_CUDA(cudaMemcpyAsync(dx + ox * 3, x + ox * 3, (size_t)nb * P1 * 12, cudaMemcpyHostToDevice, c->copy_stream));
         PTK_CHECK_CUDA(cudaMemcpyAsync(dy + oy * 3, y + oy * 3, (size_t)nb * P2 * 12, cudaMemcpyHostToDevice, c->copy_stream));
