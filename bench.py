@@ -31,6 +31,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# NCCL prints "NCCL version ..." on stdout at NCCL_DEBUG=VERSION/INFO; stdout must carry exactly one JSON line
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO") and not os.environ.get("PTK_KEEP_NCCL_DEBUG"):
+    os.environ["NCCL_DEBUG"] = "WARN"
 
 P = 10000           # points per cloud
 B_PER_GPU = 256     # cloud pairs per GPU per step
