@@ -559,12 +559,25 @@ __device__ __forceinline__ void exact2_body(const float *__restrict__ Q, const f
         __syncthreads();
         const int npad = ((n + CHUNK - 1) / CHUNK) * CHUNK;
         const float *__restrict__ src = T + (size_t)tile * 3;
-        for (int e = tid; e < npad * 3; e += THREADS) {
-            float v = e < n * 3 ? src[e] : INF;
-            int p = e / 3;
-            int c = e - p * 3;
-            float *dst = c == 0 ? sx : (c == 1 ? sy : sz);
-            dst[p] = v;
+        // eight loads in flight per thread: in list mode only a few CTAs are resident and this staging is
+        // latency-bound (ncu: 255 us rescue pass, long-scoreboard stalls) unless the loads are batched
+        for (int e0 = 0; e0 < npad * 3; e0 += THREADS * 8) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * THREADS + tid;
+                v[u] = e < n * 3 ? src[e] : INF;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * THREADS + tid;
+                if (e < npad * 3) {
+                    const int p = e / 3;
+                    const int c = e - p * 3;
+                    float *dst = c == 0 ? sx : (c == 1 ? sy : sz);
+                    dst[p] = v[u];
+                }
+            }
         }
         __syncthreads();
         const int nchunks = npad / CHUNK;

@@ -185,6 +185,11 @@ def run_ours(args):
     import ptk_b200
     from ptk_b200 import _lib
 
+    # Everything libraries print while the job runs (NCCL banner, warnings) goes to stderr: stdout carries exactly
+    # the one JSON line.  File descriptor 1 is restored right before that line is printed.
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank, world, local = ptk_b200.dist.init_from_env()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
@@ -337,6 +342,8 @@ def run_ours(args):
         "clocks": clocks, "e2e": e2e, "gpu_launches": 7 * K * world,
         "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
     }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
