@@ -106,3 +106,42 @@ def test_pytorch3d_shim_imports():
     from pytorch3d.io.obj_io import load_obj, save_obj  # noqa: F401
     w0, w1, w2 = _rand_barycentric_coords(2, 5, torch.float32, "cpu")
     assert torch.allclose(w0 + w1 + w2, torch.ones(2, 5))
+
+
+def test_factor_hubs_is_exact_on_the_real_graphs_and_falls_back_otherwise(golden):
+    """graph.factor_hubs: the reduced CSR + alpha * w on the common set reproduces the adjacency exactly for the
+    fused touch graphs (forward and transpose), leaves hub-free graphs alone, and refuses non-rank-1 hub rows."""
+    import numpy as np
+    from ptk_b200.graph import Graph, factor_hubs
+    adj = golden("adjacency")
+
+    def dense(rowptr, col, val, n):
+        a = np.zeros((n, n), np.float64)
+        a[np.repeat(np.arange(n), np.diff(rowptr)), col] = val
+        return a
+
+    for tag, n_hubs in (("p", 5), ("g", 20)):
+        g = Graph.from_csr(adj[f"{tag}_adj_rowptr"], adj[f"{tag}_adj_col"], "cpu")
+        h = g.host
+        for rp, col, val in ((h["rowptr"], h["col"], h["val"]), (h["rowptr_t"], h["col_t"], h["val_t"])):
+            f = factor_hubs(rp, col, val, g.n)
+            assert len(f["hubs"]) == n_hubs and len(f["common_col"]) > 1000
+            assert f["row_skip"].sum() == n_hubs and (np.diff(f["rowptr"])[f["hubs"]] < 64).all()
+            rec = dense(f["rowptr"], f["col"], f["val"], g.n)
+            for hub, a in zip(f["hubs"], f["alpha"]):
+                rec[hub, f["common_col"]] += np.float64(a) * f["common_w"].astype(np.float64)
+            assert np.array_equal(rec.astype(np.float32), dense(rp, col, val, g.n).astype(np.float32))
+    g0 = Graph.from_csr(adj["p_origional_rowptr"], adj["p_origional_col"], "cpu")
+    assert g0.fwd_k.n_common == 0 and g0.fwd_k.n_hubs == 0
+    # hub rows whose weights are not rank-1 on the shared columns must not be factored
+    rng = np.random.default_rng(0)
+    n = 400
+    rows = [np.unique(np.append(rng.integers(0, n, 5), i)) for i in range(n)]
+    shared = np.arange(100, 300)
+    for hub in (3, 50):
+        rows[hub] = np.unique(np.concatenate([rows[hub], shared]))
+    rowptr = np.zeros(n + 1, np.int32)
+    rowptr[1:] = np.cumsum([len(r) for r in rows])
+    col = np.concatenate(rows).astype(np.int32)
+    f = factor_hubs(rowptr, col, rng.random(len(col)).astype(np.float32), n)
+    assert f["common_col"] is None and len(f["hubs"]) == 2
