@@ -286,6 +286,13 @@ def run_ours(args):
            "d2h_bytes_per_step": B * 4, "steps": ke, "ms_per_step": 1e3 * e2e_s / ke,
            "api": "ptk_host_chamfer (C ABI, pinned host buffers; backward on device, loss read back)"}
 
+    recon = None
+    if not args.no_extra:
+        try:
+            recon = recon_step_measurement(torch, ptk_b200, dev, rank, world)
+        except Exception as exc:  # secondary numbers must never lose the headline
+            recon = {"error": repr(exc)[:300]}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -325,6 +332,8 @@ def run_ours(args):
 
     extra = {"fwd_ms": fwd_ms, "bwd_ms": bwd_ms, "bwd_hbm_gbs": (2 * B * P) * (12 + 4 + 12 + 12 + 12) / (bwd_ms * 1e-3) / 1e9,
              "device": torch.cuda.get_device_name(dev), "sm_count": info["sm_count"]}
+    if recon is not None:
+        extra["recon_step"] = recon
     if not args.no_extra:
         try:
             extra.update(extra_measurements(torch, ptk_b200, dev, hbm_peak, hbm_src))
@@ -348,6 +357,92 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def recon_step_measurement(torch, ptk_b200, dev, rank, world):
+    """BASELINE configs[2]-shaped reconstruction step on EVERY rank (weak scaling, 16 objects per GPU): 3 GCN passes
+    (448 -> 300 x 18 -> 3, N = 1824/1949/1949) + 3 x 10k-point Chamfer loss + backward + Adam; for world > 1 the
+    parameter gradients go through the bucketed NCCL all-reduce that overlaps the backward (ptk_b200.dist).
+    The CNN/MLP vertex-feature encoders are out of scope: vertex features are synthetic."""
+    import types
+    import torch.distributed as dist
+    from ptk_b200.graph import Graph
+    gold = os.path.join(ROOT, "tests", "golden")
+    adj = dict(np.load(os.path.join(gold, "adjacency.npz")))
+    meshes = dict(np.load(os.path.join(gold, "meshes.npz")))
+    args = types.SimpleNamespace(use_img=True, use_touch=True, finger=True, num_grasps=5, num_GCN_layers=20,
+                                 hidden_GCN_size=300, cut=0.33)
+    to = lambda a, dt: torch.from_numpy(a).to(dev, dt)
+    g = Graph.from_csr(adj["p_adj_rowptr"], adj["p_adj_col"], dev)
+    adj_info = {"origional": Graph.from_csr(adj["p_origional_rowptr"], adj["p_origional_col"], dev).dense(),
+                "adj": g.dense(), "faces": to(adj["p_faces"], torch.int64)}
+    torch.manual_seed(0)                                   # identical initial weights on every rank
+    net = ptk_b200.recon.ChartDeformer(adj_info, args, 448).to(dev)
+    Bs = 16
+    gen = torch.Generator(device=dev).manual_seed(100 + rank)   # every rank owns different objects
+    vision = to(meshes["vision_verts"], torch.float32)[None].repeat(Bs, 1, 1)
+    touch = torch.rand(Bs, 125, 3, device=dev, generator=gen) * 0.02 + 0.2
+    feats = [torch.rand(Bs, 1824, 448, device=dev, generator=gen), torch.rand(Bs, 1949, 448, device=dev, generator=gen),
+             torch.rand(Bs, 1949, 448, device=dev, generator=gen)]
+    gt = torch.nn.functional.normalize(torch.randn(Bs, 10000, 3, device=dev, generator=gen), dim=-1) * 0.25
+    opt = torch.optim.Adam(net.parameters(), lr=3e-4, fused=True)
+    reducer = ptk_b200.dist.GradReducer(net.parameters(), bucket_mb=4)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        reducer.reset()
+        verts = net(vision, touch, lambda it, v: feats[it])
+        loss, _ = ptk_b200.recon.recon_loss(verts, adj_info["faces"], gt, number_points=10000)
+        (loss / world).backward()                          # mean over the global batch; gradients reduced with SUM
+        reducer.finish()
+        opt.step()
+        return loss
+
+    def timeit(fn, iters, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / iters
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    ms = timeit(step, 5, 2)
+    out = {"shape": "v_t_p GCN part: 16 objects per GPU, 3 x (448->300x18->3), N=1824/1949/1949, 3 x 10k-point "
+                    "Chamfer loss, fwd+bwd+Adam; synthetic vertex features (CNN/MLP encoders out of scope)",
+           "n_gpus": world, "ms": ms, "steps_per_s": 1e3 / ms, "objects_per_s": world * Bs * 1e3 / ms,
+           "grad_allreduce": (f"{len(reducer.buckets)} NCCL buckets overlapped with backward" if world > 1 else "none (1 GPU)")}
+    gemm_flop = 3 * 2 * Bs * (1824 * (448 * 300 + 18 * 300 * 300 + 300 * 3) + 2 * 1949 * (448 * 300 + 18 * 300 * 300 + 300 * 3))
+    out["gemm_tflops_per_gpu"] = gemm_flop / (ms * 1e-3) / 1e12
+    if world == 1:
+        try:  # the same step replayed from one CUDA graph (launch gaps and Python overhead removed)
+            opt_g = torch.optim.Adam(net.parameters(), lr=3e-4, fused=True, capturable=True)
+
+            def step_g():
+                opt_g.zero_grad(set_to_none=True)
+                verts = net(vision, touch, lambda it, v: feats[it])
+                loss, _ = ptk_b200.recon.recon_loss(verts, adj_info["faces"], gt, number_points=10000)
+                loss.backward()
+                opt_g.step()
+                return loss
+
+            graphed = ptk_b200.recon.GraphedStep(step_g)
+            msg = timeit(graphed, 10, 2)
+            out["ms_cuda_graph"] = msg
+            out["steps_per_s_cuda_graph"] = 1e3 / msg
+        except Exception as exc:
+            out["cuda_graph_error"] = repr(exc)[:300]
+    return out
 
 
 def extra_measurements(torch, ptk_b200, dev, hbm_peak, hbm_src):
@@ -384,51 +479,15 @@ def extra_measurements(torch, ptk_b200, dev, hbm_peak, hbm_src):
                             "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg}
     del H, o
 
-    # --- config-3-shaped reconstruction step: 3 GCN passes (448->300x18->3) + 10k-point Chamfer loss x3 + backward
+    # (the config-3-shaped reconstruction step is measured by recon_step_measurement() on every rank)
     args = types.SimpleNamespace(use_img=True, use_touch=True, finger=True, num_grasps=5, num_GCN_layers=20,
                                  hidden_GCN_size=300, cut=0.33)
     to = lambda a, dt: torch.from_numpy(a).to(dev, dt)
     adj_info = {"origional": Graph.from_csr(adj["p_origional_rowptr"], adj["p_origional_col"], dev).dense(),
                 "adj": g.dense(), "faces": to(adj["p_faces"], torch.int64)}
-    torch.manual_seed(0)
-    net = ptk_b200.recon.ChartDeformer(adj_info, args, 448).to(dev)
     Bs = 16
     vision = to(meshes["vision_verts"], torch.float32)[None].repeat(Bs, 1, 1)
     touch = torch.rand(Bs, 125, 3, device=dev) * 0.02 + 0.2
-    feats = [torch.rand(Bs, 1824, 448, device=dev), torch.rand(Bs, 1949, 448, device=dev),
-             torch.rand(Bs, 1949, 448, device=dev)]
-    gt = torch.nn.functional.normalize(torch.randn(Bs, 10000, 3, device=dev), dim=-1) * 0.25
-    opt = torch.optim.Adam(net.parameters(), lr=3e-4, fused=True)
-
-    def step():
-        opt.zero_grad(set_to_none=True)
-        verts = net(vision, touch, lambda it, v: feats[it])
-        loss, _ = ptk_b200.recon.recon_loss(verts, adj_info["faces"], gt, number_points=10000)
-        loss.backward()
-        opt.step()
-
-    ms = timeit(step, 5, warm=2)
-    ms_graph = None
-    try:  # the same step replayed from one CUDA graph (launch gaps and Python overhead removed)
-        opt_g = torch.optim.Adam(net.parameters(), lr=3e-4, fused=True, capturable=True)
-
-        def step_g():
-            opt_g.zero_grad(set_to_none=True)
-            verts = net(vision, touch, lambda it, v: feats[it])
-            loss, _ = ptk_b200.recon.recon_loss(verts, adj_info["faces"], gt, number_points=10000)
-            loss.backward()
-            opt_g.step()
-            return loss
-
-        graphed = ptk_b200.recon.GraphedStep(step_g)
-        ms_graph = timeit(graphed, 10, warm=2)
-    except Exception as exc:
-        out["recon_step_graph_error"] = repr(exc)[:300]
-    gemm_flop = 3 * 2 * Bs * (1824 * (448 * 300 + 18 * 300 * 300 + 300 * 3) + 2 * 1949 * (448 * 300 + 18 * 300 * 300 + 300 * 3))
-    out["recon_step"] = {"shape": "v_t_p GCN part: B=16, 3 x (448->300x18->3), N=1824/1949/1949, 3 x 10k-point "
-                                  "Chamfer loss, fwd+bwd+Adam; synthetic vertex features (CNN/MLP encoders out of scope)",
-                         "ms": ms, "steps_per_s": 1e3 / ms, "gemm_tflops": gemm_flop / (ms * 1e-3) / 1e12,
-                         "ms_cuda_graph": ms_graph, "steps_per_s_cuda_graph": (1e3 / ms_graph) if ms_graph else None}
     # --- sampler (B=16, V=1949, F=2464, S=10000)
     faces32 = adj_info["faces"].to(torch.int32)
     verts = torch.cat([vision, touch], 1)
