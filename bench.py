@@ -145,6 +145,68 @@ def cpu_chamfer_leg(seconds_target, steps=None, warmup=0):
                       f"(OpenMP, {threads} threads), {el:.1f} s"}, el, n, bs
 
 
+def cpu_recon_leg(Bc=2):
+    """The reference's reconstruction step restated with its own stack on the host (oracle/torch_ref.py: dense
+    adjacency matmul exactly as GCN_layer.forward does, torch brute-force Chamfer): `Bc` objects, one step,
+    all host threads.  A reported baseline for the GCN-step metric, not a target."""
+    import torch
+    from oracle import torch_ref as tr
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    torch.set_num_threads(ncpu)
+    gold = os.path.join(ROOT, "tests", "golden")
+    adj = dict(np.load(os.path.join(gold, "adjacency.npz")))
+    meshes = dict(np.load(os.path.join(gold, "meshes.npz")))
+
+    def dense(tag):
+        rp, col = adj[tag + "_rowptr"], adj[tag + "_col"]
+        n = len(rp) - 1
+        a = torch.zeros(n, n)
+        deg = np.diff(rp)
+        rows = np.repeat(np.arange(n), deg)
+        a[torch.from_numpy(rows), torch.from_numpy(col.astype(np.int64))] = torch.from_numpy(
+            np.repeat((1.0 / deg).astype(np.float32), deg))
+        return a
+
+    a0, a1 = dense("p_origional"), dense("p_adj")
+    faces = torch.from_numpy(adj["p_faces"].astype(np.int64))
+    gen = torch.Generator().manual_seed(0)
+    sizes = [448] + [300] * 19 + [3]
+
+    def make():
+        ws, bs = [], []
+        for i in range(20):
+            stdv = 0.3 * 6.0 / np.sqrt(sizes[i] + 1)
+            ws.append(((torch.rand(1, sizes[i], sizes[i + 1], generator=gen) * 2 - 1) * stdv).requires_grad_(True))
+            bs.append(((torch.rand(sizes[i + 1], generator=gen) * 2 - 1) * 0.1).requires_grad_(True))
+        return ws, bs
+
+    w1, b1 = make()
+    w2, b2 = make()
+    vision = torch.from_numpy(meshes["vision_verts"])[None].repeat(Bc, 1, 1)
+    touch = torch.rand(Bc, 125, 3, generator=gen) * 0.02 + 0.2
+    feats = [torch.rand(Bc, 1824, 448, generator=gen), torch.rand(Bc, 1949, 448, generator=gen),
+             torch.rand(Bc, 1949, 448, generator=gen)]
+    gt = torch.nn.functional.normalize(torch.randn(Bc, 10000, 3, generator=gen), dim=-1) * 0.25
+    t0 = time.perf_counter()
+    verts = vision + tr.gcn_dense(feats[0], w1, b1, a0, 0.33)
+    verts = torch.cat((verts, touch), 1)
+    for it in (1, 2):
+        upd = tr.gcn_dense(feats[it], w2, b2, a1, 0.33)
+        verts = torch.cat((verts[:, :1824] + upd[:, :1824], verts[:, 1824:]), 1)
+    cd = 0
+    for _ in range(3):
+        pts, _ = tr.batch_sample(verts, faces, torch.rand(Bc, 10000, generator=gen), torch.rand(2, Bc, 10000, generator=gen))
+        cd = cd + tr.chamfer_autograd(pts, gt)
+    (9000.0 * (cd / 3).mean()).backward()
+    el = time.perf_counter() - t0
+    return {"objects_per_s": Bc / el, "steps_per_s_at_16_objects": Bc / el / 16.0, "cores": ncpu, "kind": "port",
+            "sample": f"1 step x {Bc} objects (fwd + 3 x 10k-point Chamfer loss + bwd), oracle/torch_ref.py "
+                      f"(dense adjacency as the reference, torch CPU, {ncpu} threads), {el:.1f} s"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -343,6 +405,11 @@ def run_ours(args):
     cpu = None
     if not args.no_cpu:
         cpu, _, _, _ = cpu_chamfer_leg(10.0)
+        if not args.no_extra and world == 1 and isinstance(extra.get("recon_step"), dict):
+            try:
+                extra["recon_step"]["cpu_baseline"] = cpu_recon_leg()
+            except Exception as exc:
+                extra["recon_step"]["cpu_baseline"] = {"error": repr(exc)[:200]}
 
     line = {
         "metric": "chamfer_pairs_per_s_10k", "value": pairs_per_s, "unit": "pairs/s", "n_gpus": world, "steps": K,
