@@ -128,20 +128,30 @@ sgemm_kernel(const float *__restrict__ A, long long lda, const float *__restrict
 // global loads, register-staged double buffering.  Each output is one k-sequential FMA chain starting
 // from 0 -- the arithmetic of a scalar FP32 loop (see ops.py: why the training forward needs that).
 constexpr int FW_BN = 160, FW_BK = 16, FW_PAD = 4;
+constexpr int FW_MAXW = 16;  // mask words per row the forward can emit (K <= 512)
 
 template <int BM>
 __global__ void __launch_bounds__(BM * 2, BM <= 32 ? 6 : (BM <= 64 ? 3 : 2))
 sgemm_fwd_kernel(const float *__restrict__ A, const float *__restrict__ Bm, float *__restrict__ Cm, int M, int N,
-                 int K, int ld1, int nsplit, float *__restrict__ C2, int ld2, int relu2) {
+                 int K, int ld1, int nsplit, float *__restrict__ C2, int ld2, int relu2,
+                 uint32_t *__restrict__ a_bits) {
     // Output: columns n < nsplit -> Cm[m * ld1 + n]; columns n >= nsplit -> C2[m * ld2 + n], optionally ReLU'd
     // (the fused GCN-layer form: the propagated slice goes to a compact scratch for the aggregation, the
     // pass-through slice straight into the layer output).  Plain GEMM: nsplit = N, ld1 = N.
     constexpr int T = BM * 2;
     __shared__ __align__(16) float As[2][FW_BK][BM + FW_PAD];
     __shared__ __align__(16) float Bs[2][FW_BK][FW_BN];
+    // By-product for the backward: bit (k & 31) of a_bits[m * wpr + (k >> 5)] = A[m, k] > 0 -- the ReLU mask of
+    // this layer's input, which the dgrad epilogue needs (every A element passes through registers here anyway).
+    __shared__ uint32_t sbits[BM][FW_MAXW];
     const int tid = threadIdx.x;
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * FW_BN;
     const int tx = tid % 16, ty = tid / 16;
+    const bool emit = a_bits != nullptr && blockIdx.x == 0;  // one column tile of CTAs is enough
+    if (emit) {
+        for (int e = tid; e < BM * FW_MAXW; e += T) sbits[e / FW_MAXW][e % FW_MAXW] = 0u;
+        __syncthreads();
+    }
 
     float4 ra[2];
     // A: global -> registers (transposed into shared memory later); B: cp.async straight into shared
@@ -169,11 +179,21 @@ sgemm_fwd_kernel(const float *__restrict__ A, const float *__restrict__ Bm, floa
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    int k0_staged = 0;  // k offset of the tile held in ra
     auto r2s = [&](int buf) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const int idx = tid + i * T;
             const int r = idx >> 2, kq = idx & 3;
+            if (emit) {
+                // the 4 lanes kq = 0..3 of a row hold the 16 mask bits of this k-tile: OR them together with two
+                // shuffles and let lane kq == 0 store the half word (no atomics)
+                uint32_t h = ((ra[i].x > 0.f ? 1u : 0u) | (ra[i].y > 0.f ? 2u : 0u) | (ra[i].z > 0.f ? 4u : 0u) |
+                              (ra[i].w > 0.f ? 8u : 0u)) << (kq * 4);
+                h |= __shfl_xor_sync(0xffffffffu, h, 1);
+                h |= __shfl_xor_sync(0xffffffffu, h, 2);
+                if (kq == 0) reinterpret_cast<unsigned short *>(&sbits[r][0])[k0_staged >> 4] = (unsigned short)h;
+            }
             As[buf][kq * 4 + 0][r] = ra[i].x;
             As[buf][kq * 4 + 1][r] = ra[i].y;
             As[buf][kq * 4 + 2][r] = ra[i].z;
@@ -197,7 +217,10 @@ sgemm_fwd_kernel(const float *__restrict__ A, const float *__restrict__ Bm, floa
     int buf = 0;
     for (int k0 = 0; k0 < K; k0 += FW_BK) {
         const bool more = k0 + FW_BK < K;
-        if (more) g2r(k0 + FW_BK, buf ^ 1);
+        if (more) {
+            g2r(k0 + FW_BK, buf ^ 1);
+            k0_staged = k0 + FW_BK;
+        }
 #pragma unroll
         for (int k = 0; k < FW_BK; ++k) {
             const float4 a0 = *reinterpret_cast<const float4 *>(&As[buf][k][ty * 4]);
@@ -220,6 +243,14 @@ sgemm_fwd_kernel(const float *__restrict__ A, const float *__restrict__ Bm, floa
             r2s(buf ^ 1);
             __syncthreads();
             buf ^= 1;
+        }
+    }
+    if (emit) {
+        __syncthreads();
+        const int wpr = (K + 31) >> 5;
+        for (int e = tid; e < BM * wpr; e += T) {
+            const int r = e / wpr, w = e - r * wpr;
+            if (m0 + r < M) a_bits[(size_t)(m0 + r) * wpr + w] = sbits[r][w];
         }
     }
 #pragma unroll
@@ -256,7 +287,8 @@ sgemm_fwd_kernel(const float *__restrict__ A, const float *__restrict__ Bm, floa
 
 template <int BM>
 static void launch_fwd(const float *X, const float *W, float *H, int64_t M, int64_t K, int64_t N, cudaStream_t st,
-                       int ld1 = 0, int nsplit = -1, float *C2 = nullptr, int ld2 = 0, int relu2 = 0) {
+                       int ld1 = 0, int nsplit = -1, float *C2 = nullptr, int ld2 = 0, int relu2 = 0,
+                       uint32_t *a_bits = nullptr) {
     dim3 grid((unsigned)ceil_div(N, FW_BN), (unsigned)ceil_div(M, BM));
     if (nsplit < 0) {
         nsplit = (int)N;
@@ -264,7 +296,8 @@ static void launch_fwd(const float *X, const float *W, float *H, int64_t M, int6
         C2 = H;
         ld2 = (int)N;
     }
-    sgemm_fwd_kernel<BM><<<grid, BM * 2, 0, st>>>(X, W, H, (int)M, (int)N, (int)K, ld1, nsplit, C2, ld2, relu2);
+    sgemm_fwd_kernel<BM><<<grid, BM * 2, 0, st>>>(X, W, H, (int)M, (int)N, (int)K, ld1, nsplit, C2, ld2, relu2,
+                                                  K <= 32 * FW_MAXW ? a_bits : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -338,7 +371,7 @@ __global__ void splitk_reduce_kernel(const float *__restrict__ part, int nsplit,
 bool tf32x3_eligible(const void *A, const void *D, int64_t M, int64_t K, int64_t N);
 size_t tf32x3_workspace_bytes(int64_t M, int64_t K, int64_t N);
 int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act, int64_t M, int64_t K, int64_t N,
-                float *D, void *workspace, size_t workspace_bytes, cudaStream_t st);
+                float *D, void *workspace, size_t workspace_bytes, cudaStream_t st, const uint32_t *act_bits = nullptr);
 
 bool wgrad_tf32x3_eligible(const void *X, const void *gH, int64_t M, int64_t Kin, int64_t Nout);
 size_t wgrad_tf32x3_workspace_bytes(int64_t M, int64_t Kin, int64_t Nout);
@@ -401,7 +434,8 @@ extern "C" int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int
 }
 
 extern "C" int ptk_gcn_linear_fwd_split(const float *X, const float *W, int64_t M, int64_t K, int64_t N,
-                                        int64_t n_split, float *head, float *out, int relu, ptk_stream_t stream) {
+                                        int64_t n_split, float *head, float *out, int relu, uint32_t *x_bits,
+                                        ptk_stream_t stream) {
     int rc = check_gemm(X, W, out, M, K, N);
     if (rc) return rc;
     PTK_REQUIRE(head && n_split > 0 && n_split < N && (n_split % 4) == 0, PTK_ERR_SHAPE,
@@ -410,13 +444,14 @@ extern "C" int ptk_gcn_linear_fwd_split(const float *X, const float *W, int64_t 
                 "gcn_linear_fwd_split: needs K %% 4 == 0, N %% 4 == 0, N >= 64");
     PTK_REQUIRE((((uintptr_t)X | (uintptr_t)W | (uintptr_t)head | (uintptr_t)out) % 16) == 0, PTK_ERR_ALIGN,
                 "gcn_linear_fwd_split: pointers must be 16-byte aligned");
-    launch_fwd<64>(X, W, head, M, K, N, as_stream(stream), (int)n_split, (int)n_split, out, (int)N, relu);
+    PTK_REQUIRE(!x_bits || K <= 32 * FW_MAXW, PTK_ERR_SHAPE, "gcn_linear_fwd_split: x_bits needs K <= %d", 32 * FW_MAXW);
+    launch_fwd<64>(X, W, head, M, K, N, as_stream(stream), (int)n_split, (int)n_split, out, (int)N, relu, x_bits);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }
 
-extern "C" int ptk_gcn_linear_dgrad(const float *gH, const float *W, const float *act, int64_t M,
-                                    int64_t K, int64_t N, float *gX, int algo, void *workspace,
+extern "C" int ptk_gcn_linear_dgrad(const float *gH, const float *W, const float *act, const uint32_t *act_bits,
+                                    int64_t M, int64_t K, int64_t N, float *gX, int algo, void *workspace,
                                     size_t workspace_bytes, ptk_stream_t stream) {
     int rc = check_gemm(gH, W, gX, M, K, N);
     if (rc) return rc;
@@ -424,7 +459,8 @@ extern "C" int ptk_gcn_linear_dgrad(const float *gH, const float *W, const float
     const int g_dgrad_mode = algo;
     // gX (M x K) = gH (M x N) . W^T : reduction over N; W as stored (K x N) is the "N' x K'" operand
     if (g_dgrad_mode != 1 && tf32x3_eligible(gH, gX, M, N, K) && (!act || ((uintptr_t)act % 16) == 0))
-        return gemm_tf32x3(gH, W, /*b_is_kn=*/0, act, M, N, K, gX, workspace, workspace_bytes, as_stream(stream));
+        return gemm_tf32x3(gH, W, /*b_is_kn=*/0, act, M, N, K, gX, workspace, workspace_bytes, as_stream(stream),
+                           act ? act_bits : nullptr);
     PTK_REQUIRE(g_dgrad_mode != 2, PTK_ERR_SHAPE, "gcn_linear_dgrad: shape not eligible for the tensor-core path");
     // gX (M x K) = gH (M x N) . W^T : GEMM with m=M, n=K, k=N; B[k=n_out][n=k_in] = W[k_in*N + n_out]
     dim3 grid((unsigned)ceil_div(K, GL_BN), (unsigned)ceil_div(M, GL_BM));

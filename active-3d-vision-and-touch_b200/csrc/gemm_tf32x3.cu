@@ -621,14 +621,16 @@ size_t tf32x3_workspace_bytes(int64_t M, int64_t K, int64_t N) {
 // D (M x N) = A (M x K) . Bsrc, where Bsrc is either (K x N) row-major [b_is_kn = 1: transposed during the
 // split] or (N x K) row-major [b_is_kn = 0].  act (optional): D masked by act > 0.
 int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act, int64_t M, int64_t K, int64_t N,
-                float *D, void *workspace, size_t workspace_bytes, cudaStream_t st) {
+                float *D, void *workspace, size_t workspace_bytes, cudaStream_t st, const uint32_t *act_bits) {
     PTK_REQUIRE(workspace && workspace_bytes >= tf32x3_workspace_bytes(M, K, N), PTK_ERR_WORKSPACE,
                 "gemm_tf32x3: workspace too small");
     float *b_hi = reinterpret_cast<float *>(((uintptr_t)workspace + 255) & ~(uintptr_t)255);
     float *b_lo = b_hi + (size_t)K * N;
     uint32_t *mask = reinterpret_cast<uint32_t *>(((uintptr_t)(b_lo + (size_t)K * N) + 255) & ~(uintptr_t)255);
     const int wpr = (int)ceil_div(N, 32);
-    if (act) {
+    if (act && act_bits) {
+        mask = const_cast<uint32_t *>(act_bits);  // packed by the forward GEMM that consumed `act` (same layout)
+    } else if (act) {
         relu_bits_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(act, (long long)M, (int)N, wpr, mask);
         PTK_CHECK_LAUNCH();
     }

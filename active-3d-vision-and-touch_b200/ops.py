@@ -239,15 +239,15 @@ def _linear_fwd(X2, W2, out=None, algo_id=GEMM_FFMA):
     return H
 
 
-def _linear_dgrad(gH2, W2, act2, algo_id=None):
+def _linear_dgrad(gH2, W2, act2, algo_id=None, act_bits=None):
     algo_id = algo["dgrad"] if algo_id is None else algo_id
     M, N = gH2.shape
     K = W2.shape[0]
     gX = torch.empty(M, K, dtype=torch.float32, device=gH2.device)
     L = _lib.lib()
     ws = _ws(L.ptk_gcn_linear_workspace_bytes(M, K, N), gH2.device)
-    _lib.check(L.ptk_gcn_linear_dgrad(_p(gH2), _p(W2), _p(act2), M, K, N, _p(gX), algo_id, _p(ws), ws.numel(),
-                                      _stream()),
+    _lib.check(L.ptk_gcn_linear_dgrad(_p(gH2), _p(W2), _p(act2), _p(act_bits), M, K, N, _p(gX), algo_id, _p(ws),
+                                      ws.numel(), _stream()),
                "ptk_gcn_linear_dgrad")
     return gX
 
@@ -294,7 +294,7 @@ def _fused_layer_ok(K, N, Lc, relu):
     return relu and K % 4 == 0 and N % 4 == 0 and N >= 64 and 1 <= Lc and Lp < N and Lp <= 384
 
 
-def _fused_layer_fwd(g: Graph, X2, W2, Lc, bias, B, Nv, head_buf):
+def _fused_layer_fwd(g: Graph, X2, W2, Lc, bias, B, Nv, head_buf, x_bits=None):
     """One GCN_layer.forward (vision/model.py:351-363) in two kernels: the exact FFMA2 GEMM writes the
     propagated slice H[:, :Lp] into the compact `head_buf` and relu(H[:, Lp:]) straight into the layer
     output; the aggregation gathers from the head and fills out[:, :, :Lp]."""
@@ -303,8 +303,8 @@ def _fused_layer_fwd(g: Graph, X2, W2, Lc, bias, B, Nv, head_buf):
     Lp = (Lc + 3) // 4 * 4
     out = torch.empty(B, Nv, N, dtype=torch.float32, device=X2.device)
     L = _lib.lib()
-    _lib.check(L.ptk_gcn_linear_fwd_split(_p(X2), _p(W2), M, K, N, Lp, _p(head_buf), _p(out), 1, _stream()),
-               "ptk_gcn_linear_fwd_split")
+    _lib.check(L.ptk_gcn_linear_fwd_split(_p(X2), _p(W2), M, K, N, Lp, _p(head_buf), _p(out), 1, _p(x_bits),
+                                          _stream()), "ptk_gcn_linear_fwd_split")
     k = g.fwd_k
     _lib.check(L.ptk_gcn_aggregate_ex(_p(k.rowptr), _p(k.col), _p(k.val), _p(k.hubs), k.n_hubs, _p(k.common_col),
                                       _p(k.common_w), k.n_common, _p(k.alpha), _p(k.row_skip), Nv, _p(head_buf), B,
@@ -380,6 +380,7 @@ class _GCNStack(torch.autograd.Function):
         acts = [X]
         train = any(ctx.needs_input_grad)
         fwd_algo = algo["fwd_train"] if train else algo["fwd_infer"]
+        bits = [None] * n
         with torch.cuda.device(X.device):
             Hbuf = {}
             for l in range(n):
@@ -392,7 +393,12 @@ class _GCNStack(torch.autograd.Function):
                     head = Hbuf.get(("head", Lp))
                     if head is None:
                         head = Hbuf[("head", Lp)] = torch.empty(B * Nv, Lp, dtype=torch.float32, device=X.device)
-                    acts.append(_fused_layer_fwd(graph, acts[-1].reshape(B * Nv, K), W2, Ls[l], bias, B, Nv, head))
+                    # the GEMM also packs the ReLU mask of its input (= what layer l's dgrad applies)
+                    xb = None
+                    if train and l > 0 and relus[l - 1] and K <= 512:
+                        xb = torch.empty(B * Nv, (K + 31) // 32, dtype=torch.int32, device=X.device)
+                    bits[l] = xb
+                    acts.append(_fused_layer_fwd(graph, acts[-1].reshape(B * Nv, K), W2, Ls[l], bias, B, Nv, head, xb))
                     continue
                 H = Hbuf.get(N)
                 if H is None:
@@ -400,6 +406,7 @@ class _GCNStack(torch.autograd.Function):
                 _linear_fwd(acts[-1].reshape(B * Nv, K), W2, out=H, algo_id=fwd_algo)
                 acts.append(_aggregate(graph, H.reshape(B, Nv, N), Ls[l], bias, relus[l]))
         ctx.save_for_backward(*acts, *[_f32c(w) for w in Ws])
+        ctx.bits = bits  # plain int32 buffers, no autograd history
         ctx.graph, ctx.Ls, ctx.relus, ctx.n = graph, Ls, relus, n
         ctx.wshapes = [w.shape for w in Ws]
         return acts[-1]
@@ -427,7 +434,7 @@ class _GCNStack(torch.autograd.Function):
                     gWs[l] = _linear_wgrad(acts[l].reshape(M, K), gH).reshape(ctx.wshapes[l])
                 if l > 0 or ctx.needs_input_grad[0]:
                     mask = acts[l].reshape(M, K) if (l > 0 and ctx.relus[l - 1]) else None
-                    g = _linear_dgrad(gH, W2, mask).reshape(B, Nv, K)
+                    g = _linear_dgrad(gH, W2, mask, act_bits=ctx.bits[l] if mask is not None else None).reshape(B, Nv, K)
                 else:
                     g = None
         return (g, None, None, None, *gWs, *gbs)

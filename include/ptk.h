@@ -176,11 +176,15 @@ int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int64_t K, int
  * columns [0, n_split) go to `head` (M, n_split) for ptk_gcn_aggregate_ex, columns [n_split, N) are
  * ReLU'd (relu != 0) and written straight into `out` (M, N): GCN_layer.forward's `cat(adj @ H[:, :L],
  * H[:, L:])` + activation (vision/model.py:355-363) without the round trip of the pass-through slice.
- * n_split = L rounded up to a multiple of 4; needs K % 4 == 0, N % 4 == 0, N >= 64, 16-byte alignment. */
+ * n_split = L rounded up to a multiple of 4; needs K % 4 == 0, N % 4 == 0, N >= 64, 16-byte alignment.
+ * x_bits (optional, M x ceil(K/32) words, K <= 512): by-product for the backward -- bit (k & 31) of word
+ * [m * ceil(K/32) + (k >> 5)] = X[m,k] > 0, the packed ReLU mask ptk_gcn_linear_dgrad takes as act_bits. */
 int ptk_gcn_linear_fwd_split(const float *X, const float *W, int64_t M, int64_t K, int64_t N, int64_t n_split,
-                             float *head, float *out, int relu, ptk_stream_t stream);
-int ptk_gcn_linear_dgrad(const float *gH, const float *W, const float *act, int64_t M, int64_t K,
-                         int64_t N, float *gX, int algo, void *workspace, size_t workspace_bytes,
+                             float *head, float *out, int relu, uint32_t *x_bits, ptk_stream_t stream);
+/* act (optional, M x K): gX is masked by act > 0 (ReLU backward of the layer input).  act_bits (optional): the
+ * same mask already packed by ptk_gcn_linear_fwd_split; without it the tensor-core path packs `act` itself. */
+int ptk_gcn_linear_dgrad(const float *gH, const float *W, const float *act, const uint32_t *act_bits, int64_t M,
+                         int64_t K, int64_t N, float *gX, int algo, void *workspace, size_t workspace_bytes,
                          ptk_stream_t stream);
 size_t ptk_gcn_linear_wgrad_workspace_bytes(int64_t M, int64_t K, int64_t N);
 int ptk_gcn_linear_wgrad(const float *X, const float *gH, int64_t M, int64_t K, int64_t N, float *gW,
