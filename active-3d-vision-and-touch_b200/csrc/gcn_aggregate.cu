@@ -686,8 +686,8 @@ extern "C" int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, c
         int TV = 8, BG = 8;
         const long long slots = 4LL * sm_count() * 4;
         while (BG > 1 && ceil_div(Nv, TV) * ceil_div(B, BG) < slots) BG >>= 1;
-        if (const char *e = getenv("PTK_AGG_TV")) TV = atoi(e) > 0 ? atoi(e) : TV;  // tuning overrides
-        if (const char *e = getenv("PTK_AGG_BG")) BG = atoi(e) > 0 ? atoi(e) : BG;
+        if (PTK_TUNING_ENV("PTK_AGG_TV") > 0) TV = PTK_TUNING_ENV("PTK_AGG_TV");  // tools/agg_bench.py sweeps
+        if (PTK_TUNING_ENV("PTK_AGG_BG") > 0) BG = PTK_TUNING_ENV("PTK_AGG_BG");
         const int n_tiles = (int)ceil_div(Nv, TV);
         const unsigned hub_slots = have_hubs ? (unsigned)(common ? BG : BG * n_hubs) : 0u;  // per batch group
         const unsigned grid = (unsigned)((hub_slots + n_tiles) * ceil_div(B, BG));

@@ -411,7 +411,7 @@ extern "C" int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int
         // fastest at every M that occurs here: 120 us vs 145 us (BM 112/128, spilling at the 128-register cap),
         // 136 us (BM 32) and cuBLAS FP32 127 us at M=31184, K=N=300.
         int best = 64;
-        if (const char *e = getenv("PTK_FWD_BM")) best = atoi(e);  // tuning override
+        if (PTK_TUNING_ENV("PTK_FWD_BM") > 0) best = PTK_TUNING_ENV("PTK_FWD_BM");  // tools/gemm_check.py sweeps
         if (best == 32) launch_fwd<32>(X, W, H, M, K, N, as_stream(stream));
         else if (best == 64) launch_fwd<64>(X, W, H, M, K, N, as_stream(stream));
         else if (best == 128) launch_fwd<128>(X, W, H, M, K, N, as_stream(stream));

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "ptk.h"
 
@@ -33,6 +34,17 @@ void set_error(const char *fmt, ...);
 inline cudaStream_t as_stream(ptk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
+
+// Development override: integer value of environment variable `name`, read once per call site
+// (0 / unset = keep the built-in choice).  Used by the tuning tools only.
+#define PTK_TUNING_ENV(name)                                       \
+    ([]() -> int {                                                 \
+        static const int v = []() {                                \
+            const char *e = getenv(name);                          \
+            return e ? atoi(e) : 0;                                \
+        }();                                                       \
+        return v;                                                  \
+    }())
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
