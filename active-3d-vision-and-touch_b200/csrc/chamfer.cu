@@ -102,6 +102,7 @@ chamfer_finalize_kernel(const unsigned long long *__restrict__ keys_x,
         float *dist = dir == 0 ? dist_x : dist_y;
         int32_t *idx = dir == 0 ? idx_x : idx_y;
         float acc = 0.f;
+#pragma unroll 8
         for (int i = tid; i < P; i += 512) {
             unsigned long long k = keys[(size_t)b * P + i];
             float d = __uint_as_float((unsigned int)(k >> 32));

@@ -93,16 +93,23 @@ chamfer_bounds_kernel(const float *__restrict__ x, const float *__restrict__ y, 
     for (int s = 0; s < 2; ++s) {
         const float *p = s == 0 ? x + (size_t)b * P1 * 3 : y + (size_t)b * P2 * 3;
         const int n = (s == 0 ? P1 : P2) * 3;
-        for (int e = tid; e < n; e += 1024) {
-            const float v = p[e];
-            const int c = e % 3;
-            bad |= !(fabsf(v) <= 3.0e38f);  // NaN or Inf
+        // eight loads in flight per thread: at small batches this single CTA per pair is latency-bound
+        for (int e0 = tid; e0 < n; e0 += 8 * 1024) {
+            float v[8];
 #pragma unroll
-            for (int k = 0; k < 3; ++k)
-                if (k == c) {
-                    lo[k] = fminf(lo[k], v);
-                    hi[k] = fmaxf(hi[k], v);
-                }
+            for (int u = 0; u < 8; ++u) v[u] = e0 + u * 1024 < n ? p[e0 + u * 1024] : p[tid % 3];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int e = e0 + u * 1024 < n ? e0 + u * 1024 : tid % 3;  // the filler repeats a real element
+                const int c = e % 3;
+                bad |= !(fabsf(v[u]) <= 3.0e38f);  // NaN or Inf
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (k == c) {
+                        lo[k] = fminf(lo[k], v[u]);
+                        hi[k] = fmaxf(hi[k], v[u]);
+                    }
+            }
         }
     }
     __syncthreads();
@@ -137,6 +144,7 @@ chamfer_bounds_kernel(const float *__restrict__ x, const float *__restrict__ y, 
     for (int s = 0; s < 2; ++s) {
         const float *p = s == 0 ? x + (size_t)b * P1 * 3 : y + (size_t)b * P2 * 3;
         const int n = s == 0 ? P1 : P2;
+#pragma unroll 4
         for (int i = tid; i < n; i += 1024) {
             const float dx = __fsub_rn(p[i * 3 + 0], cx), dy = __fsub_rn(p[i * 3 + 1], cy), dz = __fsub_rn(p[i * 3 + 2], cz);
             m2 = fmaxf(m2, __fmaf_ru(dz, dz, __fmaf_ru(dy, dy, __fmul_ru(dx, dx))));
