@@ -226,6 +226,7 @@ def face_areas_normals(verts_packed, faces_i64):
 # whose errors enter the result smoothly, may use the 3xTF32 tensor-core kernel.
 GEMM_AUTO, GEMM_FFMA, GEMM_TF32X3 = 0, 1, 2
 algo = {"fwd_train": GEMM_FFMA, "fwd_infer": GEMM_AUTO, "dgrad": GEMM_AUTO, "wgrad": GEMM_AUTO}
+fuse_layers = True  # training forward of 'cut' layers: split-epilogue GEMM + strided aggregate (tests flip this)
 
 
 def _linear_fwd(X2, W2, out=None, algo_id=GEMM_FFMA):
@@ -388,7 +389,8 @@ class _GCNStack(torch.autograd.Function):
                 W2 = _f32c(Ws[l]).reshape(K, -1)
                 N = W2.shape[1]
                 bias = _f32c(bs[l])
-                if fwd_algo == GEMM_FFMA and _fused_layer_ok(K, N, Ls[l], relus[l]) and bias.data_ptr() % 16 == 0:
+                if fuse_layers and fwd_algo == GEMM_FFMA and _fused_layer_ok(K, N, Ls[l], relus[l]) and \
+                        bias.data_ptr() % 16 == 0:
                     Lp = (Ls[l] + 3) // 4 * 4
                     head = Hbuf.get(("head", Lp))
                     if head is None:

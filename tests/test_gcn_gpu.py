@@ -220,3 +220,30 @@ def test_random_graphs_with_and_without_common_hub_sets(oracle):
             wantT = H.astype(np.float64).copy()
             wantT[:, :, :L] = np.einsum("ji,bjc->bic", dense, H[:, :, :L].astype(np.float64))
             assert rel_err(gT.cpu().numpy(), wantT) < TOL, (case, L)
+
+
+@pytest.mark.parametrize("hidden,cin,tag", [(100, 50, "p"), (128, 448, "g"), (300, 448, "p"), (64, 52, "p")])
+def test_fused_layer_forward_is_bit_identical_to_the_unfused_path(golden, hidden, cin, tag):
+    """The fused training forward (split-epilogue GEMM + strided aggregate + packed ReLU mask for dgrad) must give
+    exactly the outputs and gradients of the plain linear -> aggregate sequence, for every width it accepts."""
+    adj = golden("adjacency")
+    info = {"adj": Graph.from_csr(adj[f"{tag}_adj_rowptr"], adj[f"{tag}_adj_col"], "cuda").dense()}
+    args = types.SimpleNamespace(num_GCN_layers=5, hidden_GCN_size=hidden, cut=0.33)
+    torch.manual_seed(hidden)
+    net = ptk_b200.GCN(cin, args).cuda()
+    n = info["adj"].shape[0]
+    x = torch.rand(3, n, cin, device="cuda")
+    gout = torch.rand(3, n, 3, device="cuda")
+    res = {}
+    for fused in (True, False):
+        ptk_b200.ops.fuse_layers = fused
+        try:
+            xi = x.clone().requires_grad_(True)
+            net.zero_grad(set_to_none=True)
+            y = net(xi, info)
+            (y * gout).sum().backward()
+            res[fused] = [y.detach().clone(), xi.grad.clone()] + [p.grad.clone() for p in net.parameters()]
+        finally:
+            ptk_b200.ops.fuse_layers = True
+    for a, b in zip(res[True], res[False]):
+        assert torch.equal(a, b)
