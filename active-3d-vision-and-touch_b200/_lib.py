@@ -35,6 +35,8 @@ SIGNATURES = {
     "ptk_gcn_linear_fwd_split": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, C.c_int, _vp, _vp]),
     "ptk_gcn_bias_grad_workspace_bytes": (_sz, [_i64, _i64]),
     "ptk_gcn_bias_grad": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
+    "ptk_gcn_bias_grad_batched_workspace_bytes": (_sz, [_i64, _i64, _i64]),
+    "ptk_gcn_bias_grad_batched": (C.c_int, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),
     "ptk_relu_mask": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "ptk_gcn_linear_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "ptk_gcn_linear_fwd": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, C.c_int, _vp, _sz, _vp]),

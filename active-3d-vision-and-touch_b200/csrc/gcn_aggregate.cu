@@ -646,6 +646,9 @@ constexpr int BG_PARTS = 1184;  // 8 slabs per SM: short dependent-load chains i
 // fixed-order shared-memory reduction over the row lanes.
 __global__ void __launch_bounds__(256)
 bias_grad_stage1(const float *__restrict__ g, long long M, int C, int L, float *__restrict__ part) {
+    // blockIdx.y = layer of a batched call: g and part advance by one (M x C) matrix / one partial block per layer
+    g += (size_t)blockIdx.y * (size_t)M * C;
+    part += (size_t)blockIdx.y * gridDim.x * L;
     __shared__ float red[8][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const long long per = (M + gridDim.x - 1) / gridDim.x;
@@ -670,6 +673,8 @@ bias_grad_stage1(const float *__restrict__ g, long long M, int C, int L, float *
 // stage 2: one warp per column; lanes stride over the partials, fixed-order butterfly => deterministic
 __global__ void __launch_bounds__(256)
 bias_grad_stage2(const float *__restrict__ part, int nparts, int C, int L, float *__restrict__ gbias) {
+    part += (size_t)blockIdx.y * nparts * L;
+    gbias += (size_t)blockIdx.y * C;
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (c >= C) return;
@@ -792,6 +797,30 @@ extern "C" int ptk_gcn_aggregate(const int32_t *rowptr, const int32_t *col, cons
 extern "C" size_t ptk_gcn_bias_grad_workspace_bytes(int64_t M, int64_t L) {
     const int64_t nparts = M < BG_PARTS ? M : BG_PARTS;
     return sizeof(float) * (size_t)(nparts > 0 ? nparts : 1) * (size_t)(L > 0 ? L : 1);
+}
+
+extern "C" size_t ptk_gcn_bias_grad_batched_workspace_bytes(int64_t n_mats, int64_t M, int64_t L) {
+    return (size_t)(n_mats > 0 ? n_mats : 1) * ptk_gcn_bias_grad_workspace_bytes(M, L);
+}
+
+extern "C" int ptk_gcn_bias_grad_batched(const float *g, int64_t n_mats, int64_t M, int64_t C, int64_t L,
+                                         float *gbias, void *workspace, size_t workspace_bytes,
+                                         ptk_stream_t stream) {
+    PTK_REQUIRE(g && gbias, PTK_ERR_SHAPE, "gcn_bias_grad_batched: null pointer");
+    PTK_REQUIRE(n_mats > 0 && n_mats <= 65535 && M > 0 && C > 0 && L >= 0 && L <= C, PTK_ERR_SHAPE,
+                "gcn_bias_grad_batched: bad sizes");
+    PTK_REQUIRE(workspace && workspace_bytes >= ptk_gcn_bias_grad_batched_workspace_bytes(n_mats, M, L),
+                PTK_ERR_WORKSPACE, "gcn_bias_grad_batched: workspace too small");
+    cudaStream_t st = as_stream(stream);
+    const int nparts = (int)(M < BG_PARTS ? M : BG_PARTS);
+    float *part = reinterpret_cast<float *>(workspace);
+    if (L > 0) {
+        bias_grad_stage1<<<dim3((unsigned)nparts, (unsigned)n_mats), 256, 0, st>>>(g, (long long)M, (int)C, (int)L, part);
+        PTK_CHECK_LAUNCH();
+    }
+    bias_grad_stage2<<<dim3((unsigned)ceil_div(C, 8), (unsigned)n_mats), 256, 0, st>>>(part, nparts, (int)C, (int)L, gbias);
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
 }
 
 extern "C" int ptk_gcn_bias_grad(const float *g, int64_t M, int64_t C, int64_t L, float *gbias,

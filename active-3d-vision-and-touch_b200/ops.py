@@ -226,6 +226,7 @@ def face_areas_normals(verts_packed, faces_i64):
 # whose errors enter the result smoothly, may use the 3xTF32 tensor-core kernel.
 GEMM_AUTO, GEMM_FFMA, GEMM_TF32X3 = 0, 1, 2
 algo = {"fwd_train": GEMM_FFMA, "fwd_infer": GEMM_AUTO, "dgrad": GEMM_AUTO, "wgrad": GEMM_AUTO}
+batch_bias_grad = True  # one slab + two launches for the bias gradients of a GCN pass (tests flip this)
 fuse_layers = True  # training forward of 'cut' layers: split-epilogue GEMM + strided aggregate (tests flip this)
 
 
@@ -240,11 +241,11 @@ def _linear_fwd(X2, W2, out=None, algo_id=GEMM_FFMA):
     return H
 
 
-def _linear_dgrad(gH2, W2, act2, algo_id=None, act_bits=None):
+def _linear_dgrad(gH2, W2, act2, algo_id=None, act_bits=None, out=None):
     algo_id = algo["dgrad"] if algo_id is None else algo_id
     M, N = gH2.shape
     K = W2.shape[0]
-    gX = torch.empty(M, K, dtype=torch.float32, device=gH2.device)
+    gX = out if out is not None else torch.empty(M, K, dtype=torch.float32, device=gH2.device)
     L = _lib.lib()
     ws = _ws(L.ptk_gcn_linear_workspace_bytes(M, K, N), gH2.device)
     _lib.check(L.ptk_gcn_linear_dgrad(_p(gH2), _p(W2), _p(act2), _p(act_bits), M, K, N, _p(gX), algo_id, _p(ws),
@@ -319,6 +320,17 @@ def _bias_grad(g2, Lc):
     gb = torch.empty(Cc, dtype=torch.float32, device=g2.device)
     ws = _ws(L.ptk_gcn_bias_grad_workspace_bytes(M, Lc), g2.device)
     _lib.check(L.ptk_gcn_bias_grad(_p(g2), M, Cc, Lc, _p(gb), _p(ws), ws.numel(), _stream()), "ptk_gcn_bias_grad")
+    return gb
+
+
+def _bias_grad_batched(slab, Lc):
+    """slab (n, M, C) -> (n, C): the bias gradients of n layers in two launches."""
+    n, M, Cc = slab.shape
+    L = _lib.lib()
+    gb = torch.empty(n, Cc, dtype=torch.float32, device=slab.device)
+    ws = _ws(L.ptk_gcn_bias_grad_batched_workspace_bytes(n, M, Lc), slab.device)
+    _lib.check(L.ptk_gcn_bias_grad_batched(_p(slab), n, M, Cc, Lc, _p(gb), _p(ws), ws.numel(), _stream()),
+               "ptk_gcn_bias_grad_batched")
     return gb
 
 
@@ -422,6 +434,21 @@ class _GCNStack(torch.autograd.Function):
         M = B * Nv
         gWs, gbs = [None] * n, [None] * n
         g = _f32c(gout)
+        # Layers whose output gradient has the same shape and propagated width write it into one slab (the dgrad of
+        # the layer above is pointed at its slice), so their bias gradients are two batched launches at the end
+        # instead of two per layer.  Costs one (M x N) matrix per such layer until the pass is over.
+        need_gb = [ctx.needs_input_grad[4 + n + l] for l in range(n)]
+        widths = [Ws[l].reshape(acts[l].shape[2], -1).shape[1] for l in range(n)]
+        group = []
+        if batch_bias_grad and n >= 3:
+            ref = (widths[n - 2], ctx.Ls[n - 2])
+            group = [l for l in range(n - 1) if need_gb[l] and (widths[l], ctx.Ls[l]) == ref]
+        slot = {l: i for i, l in enumerate(group)}
+        slab = None
+        if len(group) >= 2:
+            slab = torch.empty(len(group), M, widths[group[0]], dtype=torch.float32, device=g.device)
+        else:
+            slot = {}
         with torch.cuda.device(g.device):
             if ctx.relus[n - 1]:
                 g = _relu_mask(g, acts[n])
@@ -429,16 +456,22 @@ class _GCNStack(torch.autograd.Function):
                 K = acts[l].shape[2]
                 W2 = Ws[l].reshape(K, -1)
                 N = W2.shape[1]
-                if ctx.needs_input_grad[4 + n + l]:
+                if need_gb[l] and l not in slot:
                     gbs[l] = _bias_grad(g.reshape(M, N), ctx.Ls[l])
                 gH = _aggregate(ctx.graph, g.reshape(B, Nv, N), ctx.Ls[l], None, False, transpose=True).reshape(M, N)
                 if ctx.needs_input_grad[4 + l]:
                     gWs[l] = _linear_wgrad(acts[l].reshape(M, K), gH).reshape(ctx.wshapes[l])
                 if l > 0 or ctx.needs_input_grad[0]:
                     mask = acts[l].reshape(M, K) if (l > 0 and ctx.relus[l - 1]) else None
-                    g = _linear_dgrad(gH, W2, mask, act_bits=ctx.bits[l] if mask is not None else None).reshape(B, Nv, K)
+                    dst = slab[slot[l - 1]] if (l - 1) in slot else None
+                    g = _linear_dgrad(gH, W2, mask, act_bits=ctx.bits[l] if mask is not None else None,
+                                      out=dst).reshape(B, Nv, K)
                 else:
                     g = None
+            if slot:
+                gb_all = _bias_grad_batched(slab, ctx.Ls[group[0]])
+                for l, i in slot.items():
+                    gbs[l] = gb_all[i]
         return (g, None, None, None, *gWs, *gbs)
 
 

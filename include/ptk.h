@@ -148,6 +148,11 @@ int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, const float 
 size_t ptk_gcn_bias_grad_workspace_bytes(int64_t M, int64_t L);
 int ptk_gcn_bias_grad(const float *g, int64_t M, int64_t C, int64_t L, float *gbias, void *workspace,
                       size_t workspace_bytes, ptk_stream_t stream);
+/* The same for n_mats gradient matrices stored back to back (g: n_mats x M x C, gbias: n_mats x C) in two
+ * launches: the layers of one GCN backward pass write their output gradients into one slab. */
+size_t ptk_gcn_bias_grad_batched_workspace_bytes(int64_t n_mats, int64_t M, int64_t L);
+int ptk_gcn_bias_grad_batched(const float *g, int64_t n_mats, int64_t M, int64_t C, int64_t L, float *gbias,
+                              void *workspace, size_t workspace_bytes, ptk_stream_t stream);
 
 /* out[i] = act[i] > 0 ? g[i] : 0 -- ReLU backward where it cannot be fused into a dgrad epilogue. */
 int ptk_relu_mask(const float *g, const float *act, int64_t n, float *out, ptk_stream_t stream);

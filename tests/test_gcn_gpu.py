@@ -237,6 +237,7 @@ def test_fused_layer_forward_is_bit_identical_to_the_unfused_path(golden, hidden
     res = {}
     for fused in (True, False):
         ptk_b200.ops.fuse_layers = fused
+        ptk_b200.ops.batch_bias_grad = fused   # likewise: slab + batched bias gradients vs one pair of launches per layer
         try:
             xi = x.clone().requires_grad_(True)
             net.zero_grad(set_to_none=True)
@@ -245,5 +246,6 @@ def test_fused_layer_forward_is_bit_identical_to_the_unfused_path(golden, hidden
             res[fused] = [y.detach().clone(), xi.grad.clone()] + [p.grad.clone() for p in net.parameters()]
         finally:
             ptk_b200.ops.fuse_layers = True
+            ptk_b200.ops.batch_bias_grad = True
     for a, b in zip(res[True], res[False]):
         assert torch.equal(a, b)
