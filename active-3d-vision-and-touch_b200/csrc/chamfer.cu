@@ -24,12 +24,12 @@
 //   * a second small kernel unpacks the keys and does the fused mean reduction in a fixed order
 //     (deterministic, no float atomics).
 //   * default algorithm (PTK_CHAMFER_FILTER): the scan above is run on the 3-FFMA expansion
-//     |t|^2 - 2 q.t with packed FFMA2 instructions as a FILTER (chamfer_kernel2.cuh); the recorded
-//     target tiles are TMA-staged (cp.async.bulk + mbarrier, double buffered) from padded SoA arrays a
-//     small pre-pass writes (chamfer_prep_kernel); the recorded
-//     chunk is re-evaluated with the defining arithmetic and the few queries whose runner-up chunk is
-//     within the proven error bound are re-scanned exactly (chamfer_nn_exact2_kernel, list mode).
-//     Results are bit-identical to PTK_CHAMFER_EXACT (the 6-op scan, kept selectable for checks).
+//     |t|^2 - 2 q.t with packed FFMA2 instructions as a FILTER (chamfer_kernel2.cuh).  Its target tiles
+//     are TMA-staged (cp.async.bulk + mbarrier, double buffered) from padded SoA arrays a small
+//     pre-pass writes (chamfer_prep_kernel).  The chunk the filter records is re-evaluated with the
+//     defining arithmetic, and the few queries whose runner-up chunk is within the proven error bound
+//     are re-scanned exactly (chamfer_nn_exact2_kernel, list mode).  Results are bit-identical to
+//     PTK_CHAMFER_EXACT (the 6-op scan on packed FP32x2, kept selectable for checks).
 #include "chamfer_kernel2.cuh"
 
 namespace ptk {

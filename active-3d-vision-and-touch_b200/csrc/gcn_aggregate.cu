@@ -7,6 +7,11 @@
 //   out[b,i,c] = act( sum_{e in row i} val[e] * in[b,col[e],c] + bias[c] )   c <  L
 //   out[b,i,c] = act( in[b,i,c] )                                             c >= L
 //
+// Kernels in this file: gcn_aggregate_tile_kernel (the fast path, see the comment above it: row structure
+// staged once per warp and replayed over a batch group, hub rows factored over their common neighbour set),
+// gcn_aggregate_narrow_kernel (<= 8 channels, the 3-channel output layer) and gcn_aggregate_kernel, the
+// generic first version described next, kept for shapes the other two do not take (C % 4 != 0, L = 0):
+//
 // HBM/L2-bound: one warp per output row, 128-bit loads along the channel dimension (rows are
 // C*4 bytes = 1200 B for C=300: 16-byte aligned), the column indices of a row are fetched 32 at a
 // time by the warp and broadcast with shuffles, neighbour loads are issued 4 deep.  Hub rows
