@@ -80,20 +80,24 @@ class KernelCSR:
 class Graph:
     """CSR of A^ (forward gather) and of A^T (backward gather), resident on one device."""
 
-    def __init__(self, rowptr, col, val, n, device):
+    def __init__(self, rowptr, col, val, n, device, sym_val_t=None):
         self.n = int(n)
         self.nnz = int(len(col))
         self.device = torch.device(device)
         rowptr = np.ascontiguousarray(rowptr, np.int32)
         col = np.ascontiguousarray(col, np.int32)
         val = np.ascontiguousarray(val, np.float32)
-        # transpose: (i, j, v) -> row j
-        rows = np.repeat(np.arange(self.n, dtype=np.int32), np.diff(rowptr))
-        order = np.lexsort((rows, col))
-        col_t = rows[order]
-        val_t = val[order]
-        rowptr_t = np.zeros(self.n + 1, np.int32)
-        np.cumsum(np.bincount(col, minlength=self.n), out=rowptr_t[1:])
+        if sym_val_t is not None:
+            # symmetric pattern (device builder): the transpose shares rowptr / col, only the values differ
+            rowptr_t, col_t, val_t = rowptr, col, np.ascontiguousarray(sym_val_t, np.float32)
+        else:
+            # transpose: (i, j, v) -> row j
+            rows = np.repeat(np.arange(self.n, dtype=np.int32), np.diff(rowptr))
+            order = np.lexsort((rows, col))
+            col_t = rows[order]
+            val_t = val[order]
+            rowptr_t = np.zeros(self.n + 1, np.int32)
+            np.cumsum(np.bincount(col, minlength=self.n), out=rowptr_t[1:])
         self.host = dict(rowptr=rowptr, col=col, val=val, rowptr_t=rowptr_t, col_t=col_t, val_t=val_t)
         hubs = np.nonzero(np.diff(rowptr) > HUB_DEG)[0].astype(np.int32)
         hubs_t = np.nonzero(np.diff(rowptr_t) > HUB_DEG)[0].astype(np.int32)
@@ -129,12 +133,62 @@ class Graph:
             val = np.repeat(w.astype(np.float32), deg)
         return Graph(rowptr, col, val, len(rowptr) - 1, device)
 
+    @staticmethod
+    def from_faces(faces, n, positions=None, centres=None):
+        """Row-normalised adjacency straight from faces, built on the device (csrc/adjacency.cu; replaces
+        calc_adj + the fusing loops of adj_fuse_touch + normalize_adj, utils.py:47-148).
+
+        faces (F,3) integer CUDA tensor with ids in [0,n); positions (n_pos,3) f32: vertices with byte-identical
+        positions are linked to each other and to every id in `centres` (both ways)."""
+        from . import _lib
+        if not faces.is_cuda:
+            raise RuntimeError("Graph.from_faces builds on the GPU: faces must be a CUDA tensor (no CPU fallback)")
+        dev = faces.device
+        if faces.dim() != 2 or faces.shape[1] != 3:
+            raise ValueError(f"faces must be (F,3), got {tuple(faces.shape)}")
+        n = int(n)
+        F = int(faces.shape[0])
+        if F and (int(faces.min()) < 0 or int(faces.max()) >= n):
+            raise ValueError(f"face vertex ids must lie in [0, {n})")
+        f32 = faces.to(torch.int32).contiguous()
+        pos = cen = None
+        n_pos = n_cen = 0
+        if positions is not None and positions.shape[0] > 1:
+            if positions.dim() != 2 or positions.shape[1] != 3 or positions.shape[0] > n:
+                raise ValueError(f"positions must be (n_pos <= {n}, 3), got {tuple(positions.shape)}")
+            pos = positions.detach().to(dev, torch.float32).contiguous()
+            n_pos = int(pos.shape[0])
+        if centres is not None and len(centres):
+            cen = torch.as_tensor(centres, dtype=torch.int32).to(dev).contiguous()
+            n_cen = int(cen.numel())
+            if int(cen.min()) < 0 or int(cen.max()) >= n:
+                raise ValueError(f"centre ids must lie in [0, {n})")
+        L = _lib.lib()
+        ws_bytes = L.ptk_adj_workspace_bytes(n)
+        if ws_bytes == 0:
+            raise ValueError(f"graph of {n} vertices is outside the device builder's range")
+        ptr = lambda t: 0 if t is None else t.data_ptr()
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream().cuda_stream
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+            rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+            _lib.check(L.ptk_adj_count(ptr(f32), F, n, ptr(pos), n_pos, ptr(cen), n_cen, ptr(rowptr), ptr(ws), ws_bytes,
+                                       stream), "ptk_adj_count")
+            nnz = int(rowptr[-1])  # the one host read of the build: sizes col / val
+            col = torch.empty(nnz, dtype=torch.int32, device=dev)
+            val = torch.empty(nnz, dtype=torch.float32, device=dev)
+            val_t = torch.empty(nnz, dtype=torch.float32, device=dev)
+            _lib.check(L.ptk_adj_emit(n, ptr(rowptr), ptr(col), ptr(val), ptr(val_t), ptr(ws), ws_bytes, stream),
+                       "ptk_adj_emit")
+        # ~100-250 KB back to the host for the hub factoring (factor_hubs); the dense matrix never exists
+        return Graph(rowptr.cpu().numpy(), col.cpu().numpy(), val.cpu().numpy(), n, dev, sym_val_t=val_t.cpu().numpy())
+
     def dense(self):
-        a = torch.zeros(self.n, self.n)
-        h = self.host
-        rows = np.repeat(np.arange(self.n), np.diff(h["rowptr"]))
-        a[torch.from_numpy(rows), torch.from_numpy(h["col"].astype(np.int64))] = torch.from_numpy(h["val"])
-        return a.to(self.device)
+        """The reference's dense row-normalised (n,n) tensor (only for callers that insist on it)."""
+        a = torch.zeros(self.n, self.n, device=self.device)
+        rows = torch.repeat_interleave(torch.arange(self.n, device=self.device), torch.diff(self.rowptr.long()))
+        a[rows, self.col.long()] = self.val
+        return a
 
 
 _cache = {}

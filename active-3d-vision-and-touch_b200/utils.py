@@ -126,8 +126,40 @@ def adj_fuse_touch(verts, faces, adj, args):
     return adj, faces
 
 
+def _adj_init_device(verts, faces, args):
+    """adj_init for CUDA inputs: both graphs are built on the device straight from the faces
+    (Graph.from_faces -> ptk_adj_count / ptk_adj_emit); the dense tensors the reference's callers index
+    adj_info with are scattered from the CSR and registered, so they are never scanned."""
+    dev = faces.device
+    n0 = int(faces.max()) + 1  # calc_adj: eye(faces.max() + 1)
+    g0 = _graph.Graph.from_faces(faces, n0)
+    adj_info = {}
+    if getattr(args, "use_touch", False):
+        sheet_verts, sheet_faces = load_mesh_touch(_object_path("touch_chart.obj"), device=dev)
+        ns = int(sheet_faces.max()) + 1
+        k = (1 if args.finger else 4) * args.num_grasps
+        n = n0 + k * ns
+        if verts.shape[0] > n:
+            raise IndexError(f"{verts.shape[0]} vertex positions for a fused graph of {n} vertices")
+        # adjacency blocks sit at n0 + i*ns (utils.py:100-106); the face list is offset by the vertex counts (:110-116)
+        adj_faces = torch.cat([faces] + [sheet_faces + (n0 + i * ns) for i in range(k)])
+        out_faces = torch.cat([faces] + [sheet_faces + (verts.shape[0] + i * sheet_verts.shape[0]) for i in range(k)])
+        centres = [4 + i * ns + n0 for i in range(k)]
+        g = _graph.Graph.from_faces(adj_faces, n, positions=verts, centres=centres)
+    else:
+        g, out_faces = g0, faces
+    for key, gr in (("origional", g0), ("adj", g)):
+        adj_info[key] = gr.dense()
+        _graph.register(adj_info[key], gr)
+    adj_info["faces"] = out_faces
+    return adj_info
+
+
 def adj_init(verts, faces, args):
-    """{'origional', 'adj', 'faces'} (utils.py:56-71)."""
+    """{'origional', 'adj', 'faces'} (utils.py:56-71).  CUDA inputs take the device builder; CPU tensors follow
+    the reference's dense construction literally (host-side tests and tools)."""
+    if faces.is_cuda:
+        return _adj_init_device(verts, faces, args)
     adj = calc_adj(faces)
     adj_info = {"origional": normalize_adj(adj.clone())}
     if args.use_touch:

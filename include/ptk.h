@@ -208,6 +208,29 @@ int ptk_vertex_maxpool_bwd(const float *grad_out, const int32_t *arg, int64_t B,
                            float *grad_in, ptk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * GCN adjacency built on the device and emitted as CSR -- no dense (Nv,Nv) matrix, no host loops.
+ * Replaces calc_adj (pterotactyl/utility/utils.py:134-148: identity + the 6 directed edges of every
+ * face), the fusing step of adj_fuse_touch (utils.py:75-130: vertices whose 3-D positions are byte-
+ * identical are linked to each other and, both ways, to every touch-chart centre) and normalize_adj
+ * (utils.py:47-52: every entry of row i is fl32(1/deg_i)).
+ *   faces      (F,3) int32 vertex ids in [0,n) -- for the fused graph: vision faces followed by the
+ *              touch-chart faces already offset into the fused numbering
+ *   positions  (n_pos,3) f32 positions of vertices 0..n_pos-1 compared for byte equality, or NULL / 0
+ *   centres    (n_centres) int32 ids linked to every vertex that has a twin, or NULL / 0
+ * ptk_adj_count fills rowptr (n+1) int32 and keeps the edge bitmap + degrees in `workspace`
+ * (ptk_adj_workspace_bytes(n); n <= 65536, else 0 / PTK_ERR_SHAPE); the caller reads rowptr[n],
+ * allocates col / val / val_t with that many entries and calls ptk_adj_emit with the same workspace.
+ * Column ids ascend within a row.  val[k] = 1/deg[row]; val_t[k] = 1/deg[col[k]] are the values of the
+ * transposed CSR (the pattern is symmetric, so rowptr and col serve both directions); either may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+size_t ptk_adj_workspace_bytes(int64_t n);
+int ptk_adj_count(const int32_t *faces, int64_t F, int64_t n, const float *positions, int64_t n_pos,
+                  const int32_t *centres, int64_t n_centres, int32_t *rowptr, void *workspace,
+                  size_t workspace_bytes, ptk_stream_t stream);
+int ptk_adj_emit(int64_t n, const int32_t *rowptr, int32_t *col, float *val, float *val_t,
+                 const void *workspace, size_t workspace_bytes, ptk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (end-to-end path: H2D + kernels + D2H inside the call).
  * All pointers are HOST pointers (pinned memory makes the copies asynchronous and faster).
  * ---------------------------------------------------------------------------------------------- */
