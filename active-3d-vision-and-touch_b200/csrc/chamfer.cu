@@ -189,8 +189,8 @@ struct NNPlan {
 };
 
 static NNPlan plan_nn(int64_t B, int64_t Pq_max, int64_t Pt_max, int ndir, int minb) {
-    // Aim for >= 4 waves of CTAs (CH_MINB resident per SM) so that the last, partial wave costs little.
-    // Prefer R = 8 queries per thread (fewest shared-memory loads per evaluation) and get the CTA count
+    // With >= 4 waves of CTAs (minb resident per SM) from the query blocks alone, the target range is not split.
+    // Otherwise prefer R = 8 queries per thread (fewest shared-memory loads per evaluation) and get the CTA count
     // from splitting the target range; fall back to fewer queries per thread for tiny clouds.
     const int64_t want = 4LL * sm_count() * minb;
     NNPlan p;
@@ -200,10 +200,18 @@ static NNPlan plan_nn(int64_t B, int64_t Pq_max, int64_t Pt_max, int ndir, int m
     if (ctas(8) * max_split < want) p.R = 4;
     if (p.R == 4 && ctas(4) * max_split < want) p.R = 2;
     const int64_t base = ctas(p.R);
-    int64_t ns = base >= want ? 1 : ceil_div(want, base);
-    if (ns > max_split) ns = max_split;
+    // Splits of the target range: more splits balance the SMs better (the tail of a launch is about one CTA's
+    // duration ~ Pt / ns), fewer splits save the fixed cost per CTA (query loads, first tile latency, key merge:
+    // ~512 targets' worth, fitted on tools/chamfer_split_sweep.py).  Minimising
+    //     (base * ns / slots) * (Pt / ns + 512) + (Pt / ns + 512)      over ns
+    // gives ns = sqrt(Pt * slots / (512 * base)); within ~3 % of the measured optimum for P = 4k..100k, B = 1..64.
+    const double slots = (double)sm_count() * minb;
+    int64_t ns = base >= want ? 1 : (int64_t)(sqrt((double)Pt_max * slots / (512.0 * (double)base)) + 0.5);
+    auto split_len = [&](int64_t n) { return ceil_div(ceil_div(Pt_max, n), (int64_t)CH_CHUNK) * CH_CHUNK; };
+    if (getenv("PTK_CH_NSPLIT")) ns = atoi(getenv("PTK_CH_NSPLIT"));  // tuning tools only (read per call)
     if (ns < 1) ns = 1;
-    const int64_t len = ceil_div(ceil_div(Pt_max, ns), (int64_t)CH_CHUNK) * CH_CHUNK;
+    if (ns > max_split) ns = max_split;
+    const int64_t len = split_len(ns);
     p.n_split = (int)ceil_div(Pt_max, len);
     p.split_len = (int)len;
     return p;
