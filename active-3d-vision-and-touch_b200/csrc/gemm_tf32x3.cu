@@ -4,7 +4,7 @@
 // its dgrad where the layer is a true GEMM (300x300, 448x300; K >= 32).  The parity contract is FP32
 // (1e-5 relative), so a single TF32 pass (10-bit mantissa) is not admissible; this kernel runs the
 // error-compensated 3xTF32 scheme:
-//       a = a_hi + a_lo,  a_hi = tf32_rna(a),  a_lo = tf32_rna(a - a_hi)     (same for b)
+//       a = a_hi + a_lo,  a_hi = tf32_rna(a),  a_lo = a - a_hi (truncated to TF32 by the tensor core)   (same for b)
 //       D = a_hi*b_lo + a_lo*b_hi + a_hi*b_hi        (a_lo*b_lo ~ 2^-22 relative is dropped)
 // CHUNKED ACCUMULATION.  The tensor core adds into its FP32 accumulator with truncation: measured here,
 // one accumulator carried over the whole reduction gives an error that grows LINEARLY with K (2.4e-6 at
@@ -20,7 +20,9 @@
 //
 // One CTA = one 128 x 160 output tile, 512 threads, 3-stage smem ring, 3 TMEM accumulator buffers:
 //   warp 0       TMA producer: raw FP32 A tile (128 x 32) + pre-split B_hi/B_lo tiles (160 x 32) per
-//                k-block, SWIZZLE_128B, mbarrier expect_tx
+//                k-block, SWIZZLE_128B, mbarrier expect_tx.  (Loading B raw and splitting it in the kernel
+//                too -- 36 instead of 56 KB per k-block -- was measured: not faster, the split of B then
+//                sits on the critical path of every k-block.)
 //   warp 1       MMA issuer (one elected lane): 12 x tcgen05.mma.kind::tf32 (M128 N160 K8) per k-block;
 //                tcgen05.commit releases the smem stage and publishes the TMEM buffer
 //   warps 4-7    converter: split the raw A tile in place into a_hi (overwrites raw) and a_lo
@@ -40,6 +42,7 @@ constexpr int TG_BK = 32;         // fp32 elements per k-block = 128 B = one SWI
 constexpr int TG_STAGES = 3;      // smem ring: 3 x 72 KB
 constexpr int TG_NBUF = 3;        // TMEM accumulator buffers: 3 x 160 columns
 constexpr int TG_THREADS = 512;
+constexpr int TG_CONV_WARPS = 4;  // warps 4-7
 constexpr int TG_A_BYTES = TG_BM * TG_BK * 4;   // 16 KB
 constexpr int TG_B_BYTES = TG_BN * TG_BK * 4;   // 20 KB
 constexpr int TG_STAGE_BYTES = 2 * TG_A_BYTES + 2 * TG_B_BYTES;
@@ -83,10 +86,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ uint32_t tf32_rna(float x) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return r;
+// hi = x rounded to TF32 (nearest, ties away -- what cvt.rna.tf32.f32 returns for finite x) in two integer
+// instructions; the PTX cvt expands to ~4 ALU instructions with its NaN/Inf handling and made the converter
+// warps the slowest stage of the pipeline.  A NaN either stays a NaN or becomes -0 here; its lo part
+// (x - hi) is a NaN in both cases, so non-finite inputs still give non-finite outputs.
+__device__ __forceinline__ uint32_t tf32_hi(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+// lo = x - hi exactly (FP32); the tensor core reads its upper 19 bits, i.e. truncates it to TF32: an error of
+// <= 2^-21 |x| with the sign of lo, i.e. random -- same order as the dropped lo*lo term.
+__device__ __forceinline__ void split_tf32(float x, uint32_t &h, uint32_t &l) {
+    h = tf32_hi(x);
+    l = __float_as_uint(x - __uint_as_float(h));
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4 &v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 "version 1"):
@@ -143,7 +160,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
         for (int s = 0; s < TG_STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
-            mbar_init(bar_conv + 8 * s, 4);
+            mbar_init(bar_conv + 8 * s, TG_CONV_WARPS);
             mbar_init(bar_empty + 8 * s, 1);
         }
         for (int b = 0; b < TG_NBUF; ++b) {
@@ -217,7 +234,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
             __syncwarp();
         }
-    } else if (warp >= 4 && warp < 8) {
+    } else if (warp >= 4 && warp < 4 + TG_CONV_WARPS) {
         // ===================== converter warps =====================
         const int ct = threadIdx.x - 128;  // 0..127
         int total_kb = 0;
@@ -225,19 +242,22 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int kb = 0; kb < total_kb; ++kb) {
             const int s = kb % TG_STAGES;
             mbar_wait(bar_full + 8 * s, (kb / TG_STAGES) & 1);
-            float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * TG_STAGE_BYTES);
-            float4 *lo = reinterpret_cast<float4 *>(smem + (size_t)s * TG_STAGE_BYTES + TG_A_BYTES);
+            const uint32_t stage = smem_u32(smem + (size_t)s * TG_STAGE_BYTES);
+            constexpr int CA = TG_A_BYTES / 16;
+            static_assert(CA % (32 * TG_CONV_WARPS) == 0, "converter chunks must divide evenly");
 #pragma unroll
-            for (int i = 0; i < (TG_BM * TG_BK / 4) / 128; ++i) {
+            for (int i = 0; i < CA / (32 * TG_CONV_WARPS); ++i) {
                 if (p.dbg & 1) break;
-                const int c = ct + i * 128;
-                float4 v = hi[c];
+                const uint32_t hi = stage + 16u * (uint32_t)(ct + i * 32 * TG_CONV_WARPS);  // raw -> a_hi in place
+                const uint32_t lo = hi + (uint32_t)TG_A_BYTES;
+                const uint4 v = lds128(hi);
                 uint4 h, l;
-                h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
-                l.x = tf32_rna(v.x - __uint_as_float(h.x)); l.y = tf32_rna(v.y - __uint_as_float(h.y));
-                l.z = tf32_rna(v.z - __uint_as_float(h.z)); l.w = tf32_rna(v.w - __uint_as_float(h.w));
-                reinterpret_cast<uint4 *>(hi)[c] = h;
-                reinterpret_cast<uint4 *>(lo)[c] = l;
+                split_tf32(__uint_as_float(v.x), h.x, l.x);
+                split_tf32(__uint_as_float(v.y), h.y, l.y);
+                split_tf32(__uint_as_float(v.z), h.z, l.z);
+                split_tf32(__uint_as_float(v.w), h.w, l.w);
+                sts128(hi, h);
+                sts128(lo, l);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic writes -> async proxy (UMMA)
             __syncwarp();
@@ -350,9 +370,10 @@ struct WGParams {
 
 __device__ __forceinline__ void split4(const float v0, const float v1, const float v2, const float v3, uint4 &h,
                                        uint4 &l) {
-    h.x = tf32_rna(v0); h.y = tf32_rna(v1); h.z = tf32_rna(v2); h.w = tf32_rna(v3);
-    l.x = tf32_rna(v0 - __uint_as_float(h.x)); l.y = tf32_rna(v1 - __uint_as_float(h.y));
-    l.z = tf32_rna(v2 - __uint_as_float(h.z)); l.w = tf32_rna(v3 - __uint_as_float(h.w));
+    split_tf32(v0, h.x, l.x);
+    split_tf32(v1, h.y, l.y);
+    split_tf32(v2, h.z, l.z);
+    split_tf32(v3, h.w, l.w);
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
@@ -537,9 +558,8 @@ __global__ void split_tf32_kernel(const float *__restrict__ src, int rows, int c
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)rows * cols) return;
     const int r = (int)(i / cols), c = (int)(i % cols);
-    const float v = src[i];
-    const uint32_t h = tf32_rna(v);
-    const uint32_t l = tf32_rna(v - __uint_as_float(h));
+    uint32_t h, l;
+    split_tf32(src[i], h, l);
     const size_t o = transpose ? (size_t)c * rows + r : (size_t)i;
     hi[o] = __uint_as_float(h);
     lo[o] = __uint_as_float(l);
