@@ -129,6 +129,8 @@ struct TGParams {
     const uint32_t *mask; // optional ReLU mask of D, packed: bit (c & 31) of word [row * wpr + (c >> 5)] = act[row, c] > 0
     int wpr;              // mask words per row = ceil(N / 32)
     int dbg;              // development switches (PTK_TG_DEBUG): 1 = skip A split, 2 = skip drain loads, 4 = skip MMAs
+    float *part;          // (gridDim.x, 128 x 160) partial tiles of the CTAs whose range starts inside a tile
+    int *flags;           // (gridDim.x) 1 once part[c] is complete (zeroed by the weight-split kernel before)
 };
 
 template <bool MASK>
@@ -148,11 +150,18 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + TG_BK - 1) / TG_BK;
-    // persistent: CTA c processes tiles c, c + gridDim.x, ...; tile t -> (m-tile t / tiles_n, n-tile t % tiles_n).
-    // All pipeline counters (smem stage, TMEM buffer) run across tiles, so the epilogue stores of one
-    // tile overlap the TMA / MMA work of the next.
+    // persistent, work split by k-blocks ("stream-K"): the (tile, k-block) pairs are numbered tile-major and CTA c
+    // takes the contiguous range [c U / G, (c+1) U / G) of them -- 488 tiles on 148 SMs would otherwise cost 4 tile
+    // times for 3.3 tiles of work per SM.  A range is at least one tile long, so a tile is shared by at most two
+    // CTAs: the CTA whose range STARTS inside the tile accumulates the tile's last k-blocks first, stores the partial
+    // tile to its workspace slot and raises its flag; the CTA whose range ENDS inside the tile (it gets there last)
+    // adds that partial to its own and runs the epilogue.  Fixed summation order => deterministic.
+    // tile t -> (m-tile t / tiles_n, n-tile t % tiles_n).  All pipeline counters (smem stage, TMEM buffer) run
+    // across tiles, so the epilogue stores of one tile overlap the TMA / MMA work of the next.
     const int tiles_n = (p.N + TG_BN - 1) / TG_BN;
     const int num_tiles = ((p.M + TG_BM - 1) / TG_BM) * tiles_n;
+    const long long units = (long long)num_tiles * num_kb;
+    const int u0 = (int)(units * blockIdx.x / gridDim.x), u1 = (int)(units * (blockIdx.x + 1) / gridDim.x);
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -182,9 +191,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // ===================== TMA producer =====================
         if (lane == 0) {
             int it = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int u = u0; u < u1; ++u, ++it) {
+                const int tile = u / num_kb, kb = u - tile * num_kb;
                 const int m0 = (tile / tiles_n) * TG_BM, n_base = (tile % tiles_n) * TG_BN;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                {
                     const int s = it % TG_STAGES;
                     const uint32_t ph = (it / TG_STAGES) & 1;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -199,8 +209,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = make_idesc_tf32(TG_BN);
-        int total_kb = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) total_kb += num_kb;
+        const int total_kb = u1 - u0;
         for (int kb = 0; kb < total_kb; ++kb) {
             const int s = kb % TG_STAGES, b = kb % TG_NBUF;
             mbar_wait(bar_full + 8 * s, (kb / TG_STAGES) & 1);        // B tiles landed
@@ -237,8 +246,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     } else if (warp >= 4 && warp < 4 + TG_CONV_WARPS) {
         // ===================== converter warps =====================
         const int ct = threadIdx.x - 128;  // 0..127
-        int total_kb = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) total_kb += num_kb;
+        const int total_kb = u1 - u0;
         for (int kb = 0; kb < total_kb; ++kb) {
             const int s = kb % TG_STAGES;
             mbar_wait(bar_full + 8 * s, (kb / TG_STAGES) & 1);
@@ -268,7 +276,13 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int half = (warp - 8) >> 2;       // column half: [0,80) or [80,160)
         int it = 0;                             // running chunk index across tiles
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int dt = threadIdx.x - 256;       // 0..255 among the drain threads
+        for (int u = u0; u < u1;) {
+        const int tile = u / num_kb, kb_begin = u - tile * num_kb;
+        const int kb_end = min(num_kb, kb_begin + (u1 - u));
+        const bool tail_part = kb_begin > 0;       // the tile's first k-blocks belong to CTA blockIdx.x - 1
+        const bool head_part = kb_end < num_kb;    // the tile's last k-blocks belong to CTA blockIdx.x + 1
+        u += kb_end - kb_begin;
         const int m0 = (tile / tiles_n) * TG_BM, n_base = (tile % tiles_n) * TG_BN;
         const int row = m0 + q * 32 + lane;
         float acc[80];
@@ -276,7 +290,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int j = 0; j < 80; ++j) acc[j] = 0.f;
         // ReLU mask of this thread's 80 outputs, fetched while the pipeline fills (bit j: act > 0)
         uint32_t mbits[3] = {0u, 0u, 0u};
-        if (MASK && row < p.M) {
+        if (MASK && row < p.M && !tail_part) {
             // 80 mask bits of this thread's outputs from the packed row mask (4 word loads instead of 20 strided
             // 16-byte loads of the activation itself: the epilogue is one thread per row)
             const int nb0 = n_base + half * 80;
@@ -288,7 +302,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
             for (int i = 0; i < 3; ++i) mbits[i] = __funnelshift_r(w[i], w[i + 1], sh);
         }
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
             const int b = it % TG_NBUF;
             mbar_wait(bar_tfull + 8 * b, (it / TG_NBUF) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -309,6 +323,31 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
+        }
+        if (tail_part) {
+            // partial tile -> slot of this CTA as [20 float4 per thread][256 threads] (coalesced), then the flag
+            float4 *slot = reinterpret_cast<float4 *>(p.part) + (size_t)blockIdx.x * (TG_BM * TG_BN / 4);
+#pragma unroll
+            for (int v = 0; v < 20; ++v)
+                __stcg(slot + v * 256 + dt, make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]));
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 drain warps
+            if (dt == 0) {
+                __threadfence();
+                *reinterpret_cast<volatile int *>(p.flags + blockIdx.x) = 1;
+            }
+            continue;
+        }
+        if (head_part) {
+            const volatile int *flag = p.flags + blockIdx.x + 1;
+            while (*flag == 0) __nanosleep(64);
+            __threadfence();
+            const float4 *slot = reinterpret_cast<const float4 *>(p.part) + (size_t)(blockIdx.x + 1) * (TG_BM * TG_BN / 4);
+#pragma unroll
+            for (int v = 0; v < 20; ++v) {
+                const float4 t = __ldcg(slot + v * 256 + dt);
+                acc[4 * v] += t.x; acc[4 * v + 1] += t.y; acc[4 * v + 2] += t.z; acc[4 * v + 3] += t.w;
+            }
         }
         // epilogue: this thread owns row `row`, columns n_base + half*80 + [0, 80)
         const int nb = n_base + half * 80;
@@ -554,8 +593,10 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
 //   transpose = 0: out[r, c] = split(src[r, c])           (rows x cols) -> (rows x cols)
 //   transpose = 1: out[c, r] = split(src[r, c])           (rows x cols) -> (cols x rows)
 __global__ void split_tf32_kernel(const float *__restrict__ src, int rows, int cols, int transpose,
-                                  float *__restrict__ hi, float *__restrict__ lo) {
+                                  float *__restrict__ hi, float *__restrict__ lo, int *__restrict__ flags,
+                                  int n_flags) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_flags) flags[i] = 0;  // the GEMM's partial-tile flags (same stream, launched right after)
     if (i >= (long long)rows * cols) return;
     const int r = (int)(i / cols), c = (int)(i % cols);
     uint32_t h, l;
@@ -633,9 +674,11 @@ bool tf32x3_eligible(const void *A, const void *D, int64_t M, int64_t K, int64_t
 
 // split B (hi, lo) + the packed ReLU mask of D (M rows x ceil(N/32) words; D has max(K, N) columns at most:
 // the same function sizes forward (D = M x N) and dgrad (D = M x K) workspaces)
+static size_t tf32x3_part_bytes() { return (size_t)sm_count() * (TG_BM * TG_BN * 4 + 4) + 512; }
 size_t tf32x3_workspace_bytes(int64_t M, int64_t K, int64_t N) {
     const int64_t cols = K > N ? K : N;
-    return 2 * sizeof(float) * (size_t)K * (size_t)N + 512 + sizeof(uint32_t) * (size_t)M * (size_t)ceil_div(cols, 32);
+    return 2 * sizeof(float) * (size_t)K * (size_t)N + 512 + sizeof(uint32_t) * (size_t)M * (size_t)ceil_div(cols, 32) +
+           tf32x3_part_bytes();
 }
 
 // D (M x N) = A (M x K) . Bsrc, where Bsrc is either (K x N) row-major [b_is_kn = 1: transposed during the
@@ -648,6 +691,12 @@ int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act
     float *b_lo = b_hi + (size_t)K * N;
     uint32_t *mask = reinterpret_cast<uint32_t *>(((uintptr_t)(b_lo + (size_t)K * N) + 255) & ~(uintptr_t)255);
     const int wpr = (int)ceil_div(N, 32);
+    // partial tiles + flags behind the (always reserved) mask area
+    float *part = reinterpret_cast<float *>(
+        ((uintptr_t)(mask + (size_t)M * (size_t)ceil_div(K > N ? K : N, 32)) + 255) & ~(uintptr_t)255);
+    int *flags = reinterpret_cast<int *>(part + (size_t)sm_count() * (TG_BM * TG_BN));
+    const int64_t num_tiles = ceil_div(M, TG_BM) * ceil_div(N, TG_BN);
+    const int n_ctas = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
     if (act && act_bits) {
         mask = const_cast<uint32_t *>(act_bits);  // packed by the forward GEMM that consumed `act` (same layout)
     } else if (act) {
@@ -656,9 +705,9 @@ int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act
     }
     const long long elems = (long long)K * N;
     if (b_is_kn)
-        split_tf32_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, st>>>(Bsrc, (int)K, (int)N, 1, b_hi, b_lo);
+        split_tf32_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, st>>>(Bsrc, (int)K, (int)N, 1, b_hi, b_lo, flags, n_ctas);
     else
-        split_tf32_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, st>>>(Bsrc, (int)N, (int)K, 0, b_hi, b_lo);
+        split_tf32_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, st>>>(Bsrc, (int)N, (int)K, 0, b_hi, b_lo, flags, n_ctas);
     PTK_CHECK_LAUNCH();
 
     CUtensorMap map_a, map_bhi, map_blo;
@@ -674,9 +723,10 @@ int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act
     static int dbg = -1;
     if (dbg < 0) { const char *e = getenv("PTK_TG_DEBUG"); dbg = e ? atoi(e) : 0; }
     p.dbg = dbg;
+    p.part = part;
+    p.flags = flags;
     const size_t smem = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024;
-    const int64_t num_tiles = ceil_div(M, TG_BM) * ceil_div(N, TG_BN);
-    dim3 grid((unsigned)(num_tiles < sm_count() ? num_tiles : sm_count()));
+    dim3 grid((unsigned)n_ctas);
     static bool attr_set = false;
     if (!attr_set) {
         PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
