@@ -113,3 +113,42 @@ def test_cuda_graph_capture_of_forward():
     g.replay()
     torch.cuda.synchronize()
     assert torch.equal(cham, ref) and torch.equal(ix, rix)
+
+
+def test_config2_touch_chart_loss_full_size(oracle, golden):
+    """BASELINE config 2 shape (touch/train.py:226-240): 64 touch charts (25 vertices, 32 faces) moved by random
+    rigid frames, 4000 sampled points vs 4000 ground-truth points, repeat = 3, loss = 9000 * mean.  Loss, per-chart
+    distances and the gradient on the chart vertices against the C oracle chained the same way."""
+    m = golden("meshes")
+    B, S, P = 64, 4000, 4000
+    rng = np.random.default_rng(2)
+    chart = m["touch_verts"].astype(np.float32)                       # (25, 3)
+    faces = m["touch_faces"].astype(np.int64)                         # (32, 3)
+    rot = np.linalg.qr(rng.standard_normal((B, 3, 3)))[0].astype(np.float32)
+    pos = (0.1 * rng.standard_normal((B, 1, 3))).astype(np.float32)
+    verts = (chart[None] @ rot + pos).astype(np.float32)
+    verts += (0.0005 * rng.standard_normal(verts.shape)).astype(np.float32)
+    u0, uv0 = rng.random((B, P), dtype=np.float32), rng.random((2, B, P), dtype=np.float32)
+    gt, _ = oracle.sample_fwd((chart[None] @ rot + pos).astype(np.float32), faces, u0, uv0)
+    gt = (gt + 0.002 * rng.standard_normal(gt.shape)).astype(np.float32)
+    uni = [(rng.random((B, S), dtype=np.float32), rng.random((2, B, S), dtype=np.float32)) for _ in range(3)]
+
+    vt = torch.from_numpy(verts).cuda().requires_grad_(True)
+    cd = ptk_b200.utils.chamfer_distance(vt, torch.from_numpy(faces).cuda(), torch.from_numpy(gt).cuda(), num=S, repeat=3,
+                                         uniforms=[(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()) for a, b in uni])
+    loss = 9000.0 * cd.mean()
+    loss.backward()
+
+    want_cd = np.zeros(B, np.float64)
+    want_g = np.zeros_like(verts, dtype=np.float64)
+    gcham = np.full(B, 9000.0 / (3 * B), np.float32)
+    for u_face, uv in uni:
+        pts, fidx = oracle.sample_fwd(verts, faces, u_face, uv)
+        cham, _, ix, _, iy = oracle.chamfer_fwd(pts, gt)
+        gx, _ = oracle.chamfer_bwd(pts, gt, ix, iy, gcham, want_y=False)
+        want_g += oracle.sample_bwd(gx, fidx, uv, faces, verts.shape[1])
+        want_cd += cham
+    want_cd /= 3
+    assert rel_err(cd.detach().cpu().numpy(), want_cd) < TOL
+    assert abs(float(loss) - 9000.0 * want_cd.mean()) < TOL * abs(9000.0 * want_cd.mean())
+    assert rel_err(vt.grad.cpu().numpy(), want_g) < TOL
