@@ -153,9 +153,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // persistent, work split by k-blocks ("stream-K"): the (tile, k-block) pairs are numbered tile-major and CTA c
     // takes the contiguous range [c U / G, (c+1) U / G) of them -- 488 tiles on 148 SMs would otherwise cost 4 tile
     // times for 3.3 tiles of work per SM.  A range is at least one tile long, so a tile is shared by at most two
-    // CTAs: the CTA whose range STARTS inside the tile accumulates the tile's last k-blocks first, stores the partial
-    // tile to its workspace slot and raises its flag; the CTA whose range ENDS inside the tile (it gets there last)
-    // adds that partial to its own and runs the epilogue.  Fixed summation order => deterministic.
+    // CTAs.  Every CTA walks its range from the END: CTA c therefore starts with the tile it shares with CTA c+1
+    // (the tile's first k-blocks), stores that partial tile to its workspace slot and raises its flag; CTA c+1 gets
+    // to the tile's remaining k-blocks LAST, adds the partial (head + tail: fixed order => deterministic) and runs
+    // the epilogue.  A CTA thus only ever waits for a lower-numbered CTA, which was dispatched before it.
     // tile t -> (m-tile t / tiles_n, n-tile t % tiles_n).  All pipeline counters (smem stage, TMEM buffer) run
     // across tiles, so the epilogue stores of one tile overlap the TMA / MMA work of the next.
     const int tiles_n = (p.N + TG_BN - 1) / TG_BN;
@@ -191,10 +192,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         // ===================== TMA producer =====================
         if (lane == 0) {
             int it = 0;
-            for (int u = u0; u < u1; ++u, ++it) {
-                const int tile = u / num_kb, kb = u - tile * num_kb;
+            for (int hi = u1; hi > u0;) {
+                const int tile = (hi - 1) / num_kb;
+                const int kb_begin = max(u0 - tile * num_kb, 0), kb_end = hi - tile * num_kb;
+                hi = tile * num_kb + kb_begin;
                 const int m0 = (tile / tiles_n) * TG_BM, n_base = (tile % tiles_n) * TG_BN;
-                {
+                for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
                     const int s = it % TG_STAGES;
                     const uint32_t ph = (it / TG_STAGES) & 1;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -277,12 +280,12 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int half = (warp - 8) >> 2;       // column half: [0,80) or [80,160)
         int it = 0;                             // running chunk index across tiles
         const int dt = threadIdx.x - 256;       // 0..255 among the drain threads
-        for (int u = u0; u < u1;) {
-        const int tile = u / num_kb, kb_begin = u - tile * num_kb;
-        const int kb_end = min(num_kb, kb_begin + (u1 - u));
-        const bool tail_part = kb_begin > 0;       // the tile's first k-blocks belong to CTA blockIdx.x - 1
-        const bool head_part = kb_end < num_kb;    // the tile's last k-blocks belong to CTA blockIdx.x + 1
-        u += kb_end - kb_begin;
+        for (int hi = u1; hi > u0;) {
+        const int tile = (hi - 1) / num_kb;
+        const int kb_begin = max(u0 - tile * num_kb, 0), kb_end = hi - tile * num_kb;
+        hi = tile * num_kb + kb_begin;
+        const bool head_part = kb_end < num_kb;    // the tile's last k-blocks belong to CTA blockIdx.x + 1: publish
+        const bool tail_part = kb_begin > 0;       // the tile's first k-blocks came from CTA blockIdx.x - 1: combine
         const int m0 = (tile / tiles_n) * TG_BM, n_base = (tile % tiles_n) * TG_BN;
         const int row = m0 + q * 32 + lane;
         float acc[80];
@@ -290,7 +293,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int j = 0; j < 80; ++j) acc[j] = 0.f;
         // ReLU mask of this thread's 80 outputs, fetched while the pipeline fills (bit j: act > 0)
         uint32_t mbits[3] = {0u, 0u, 0u};
-        if (MASK && row < p.M && !tail_part) {
+        if (MASK && row < p.M && !head_part) {
             // 80 mask bits of this thread's outputs from the packed row mask (4 word loads instead of 20 strided
             // 16-byte loads of the activation itself: the epilogue is one thread per row)
             const int nb0 = n_base + half * 80;
@@ -324,7 +327,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_tempty + 8 * b);
         }
-        if (tail_part) {
+        if (head_part) {
             // partial tile -> slot of this CTA as [20 float4 per thread][256 threads] (coalesced), then the flag
             float4 *slot = reinterpret_cast<float4 *>(p.part) + (size_t)blockIdx.x * (TG_BM * TG_BN / 4);
 #pragma unroll
@@ -338,15 +341,16 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             }
             continue;
         }
-        if (head_part) {
-            const volatile int *flag = p.flags + blockIdx.x + 1;
+        if (tail_part) {
+            const volatile int *flag = p.flags + blockIdx.x - 1;
             while (*flag == 0) __nanosleep(64);
             __threadfence();
-            const float4 *slot = reinterpret_cast<const float4 *>(p.part) + (size_t)(blockIdx.x + 1) * (TG_BM * TG_BN / 4);
+            const float4 *slot = reinterpret_cast<const float4 *>(p.part) + (size_t)(blockIdx.x - 1) * (TG_BM * TG_BN / 4);
 #pragma unroll
             for (int v = 0; v < 20; ++v) {
                 const float4 t = __ldcg(slot + v * 256 + dt);
-                acc[4 * v] += t.x; acc[4 * v + 1] += t.y; acc[4 * v + 2] += t.z; acc[4 * v + 3] += t.w;
+                acc[4 * v] = t.x + acc[4 * v]; acc[4 * v + 1] = t.y + acc[4 * v + 1];
+                acc[4 * v + 2] = t.z + acc[4 * v + 2]; acc[4 * v + 3] = t.w + acc[4 * v + 3];
             }
         }
         // epilogue: this thread owns row `row`, columns n_base + half*80 + [0, 80)
