@@ -738,7 +738,9 @@ extern "C" int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, c
         // TV = 8 (one row per warp) keeps few batch elements in flight at a time: the rows a batch element
         // gathers stay in L2 until all its tiles are done.  BG amortises the staging of the row structure.
         int TV = 8, BG = 8;
-        const long long slots = 4LL * sm_count() * 4;
+        // >= 6 CTAs per SM before BG is cut: at B = 16 (config 3) BG = 4 -> 976 CTAs measured 10 % faster than the
+        // 3904 single-element CTAs a larger target gives (tools/agg_bench.py 16, PTK_AGG_BG sweep)
+        const long long slots = 6LL * sm_count();
         while (BG > 1 && ceil_div(Nv, TV) * ceil_div(B, BG) < slots) BG >>= 1;
         if (PTK_TUNING_ENV("PTK_AGG_TV") > 0) TV = PTK_TUNING_ENV("PTK_AGG_TV");  // tools/agg_bench.py sweeps
         if (PTK_TUNING_ENV("PTK_AGG_BG") > 0) BG = PTK_TUNING_ENV("PTK_AGG_BG");
