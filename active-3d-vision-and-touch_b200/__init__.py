@@ -10,6 +10,7 @@ Layout
     _lib.py                 ctypes binding (fails loudly when the extension is missing)
     ops.py                  torch.autograd bindings (device pointers + current stream)
     utils.py, model.py      the reference's own signatures (utility.utils, GCN_layer, GCN)
+    encoders.py             Positional_Encoder / Mask_Encoder with the fused NeRF embedding
     host.py                 host-buffer (numpy) entry points = the non-torch end-to-end path
     recon.py                the GCN + Chamfer-loss part of one reconstruction step (Deformation's layout)
     policy.py               batched candidate scoring of the greedy touch policies (environment.best_step)
@@ -19,7 +20,8 @@ Layout
 import os
 import sys
 
-from . import _lib, dist, graph, host, model, obj_io, ops, policy, recon, utils  # noqa: F401
+from . import _lib, dist, encoders, graph, host, model, obj_io, ops, policy, recon, utils  # noqa: F401
+from .encoders import Mask_Encoder, Positional_Encoder  # noqa: F401
 from .model import GCN, GCN_layer  # noqa: F401
 from .utils import batch_sample, chamfer_distance  # noqa: F401
 
@@ -39,7 +41,8 @@ def install(ref_utils=None, ref_models=()):
     """Seam S2: patch the reference's modules in place so its unchanged scripts use the fused path.
 
     ref_utils  : the imported `pterotactyl.utility.utils` module (imported here if None)
-    ref_models : modules holding GCN / GCN_layer copies (vision.model, autoencoder.model, DDQN.model)
+    ref_models : modules holding GCN / GCN_layer copies (vision.model, autoencoder.model, DDQN.model);
+                 vision.model's Positional_Encoder is replaced too
     """
     if ref_utils is None:
         install_pytorch3d_shim()
@@ -52,4 +55,6 @@ def install(ref_utils=None, ref_models=()):
             mod.GCN_layer = GCN_layer
         if hasattr(mod, "GCN"):
             mod.GCN = GCN
+        if hasattr(mod, "Positional_Encoder"):
+            mod.Positional_Encoder = Positional_Encoder
     return ref_utils

@@ -48,6 +48,8 @@ SIGNATURES = {
     "ptk_adj_workspace_bytes": (_sz, [_i64]),
     "ptk_adj_count": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _sz, _vp]),
     "ptk_adj_emit": (C.c_int, [_i64, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ptk_nerf_embed_fwd": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "ptk_nerf_embed_bwd": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "ptk_host_ctx_create": (_vp, [C.c_int]),
     "ptk_host_ctx_destroy": (None, [_vp]),
     "ptk_host_chamfer": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -160,6 +160,37 @@ def vertex_max(feats):
     return _VertexMax.apply(feats)
 
 
+# ------------------------------------------------------------------------------------- positional embedding
+class _NerfEmbed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pos):
+        _need_cuda(pos)
+        pos = _f32c(pos)
+        M = pos.shape[0]
+        out = torch.empty(M, 63, dtype=torch.float32, device=pos.device)
+        with torch.cuda.device(pos.device):
+            _lib.check(_lib.lib().ptk_nerf_embed_fwd(_p(pos), M, _p(out), _stream()), "ptk_nerf_embed_fwd")
+        ctx.save_for_backward(pos)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (pos,) = ctx.saved_tensors
+        gpos = torch.empty_like(pos)
+        with torch.cuda.device(pos.device):
+            _lib.check(_lib.lib().ptk_nerf_embed_bwd(_p(pos), _p(_f32c(g)), pos.shape[0], _p(gpos), _stream()),
+                       "ptk_nerf_embed_bwd")
+        return gpos
+
+
+def nerf_embed(points):
+    """(..., 3) positions -> (..., 63): the 60-wide sin/cos NeRF embedding followed by the positions themselves
+    (Positional_Encoder.nerf_embedding + cat, vision/model.py:381-397), one launch, differentiable."""
+    if points.shape[-1] != 3:
+        raise ValueError(f"positions must end in a dimension of 3, got {tuple(points.shape)}")
+    return _NerfEmbed.apply(points.reshape(-1, 3)).reshape(*points.shape[:-1], 63)
+
+
 # ------------------------------------------------------------------------------------- surface sampling
 class _Sample(torch.autograd.Function):
     @staticmethod

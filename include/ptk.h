@@ -231,6 +231,17 @@ int ptk_adj_emit(int64_t n, const int32_t *rowptr, int32_t *col, float *val, flo
                  const void *workspace, size_t workspace_bytes, ptk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * NeRF positional embedding of vertex positions, fused with the concatenation of the raw positions:
+ * positions (M,3) -> out (M,63), row = [sin(s_0 p), cos(s_0 p), ..., sin(s_9 p), cos(s_9 p), p] with
+ * s_0 = fl32(pi), s_i = fl32(pi*2*i).  Replaces Positional_Encoder.nerf_embedding + torch.cat
+ * (pterotactyl/reconstruction/vision/model.py:381-391, 396-397; ~45 launches per call).  bwd overwrites
+ * grad_positions (M,3) from grad_out (M,63).
+ * ---------------------------------------------------------------------------------------------- */
+int ptk_nerf_embed_fwd(const float *positions, int64_t M, float *out, ptk_stream_t stream);
+int ptk_nerf_embed_bwd(const float *positions, const float *grad_out, int64_t M, float *grad_positions,
+                       ptk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (end-to-end path: H2D + kernels + D2H inside the call).
  * All pointers are HOST pointers (pinned memory makes the copies asynchronous and faster).
  * ---------------------------------------------------------------------------------------------- */
