@@ -215,3 +215,14 @@ def gcn_dense(features, weights, biases, adj, cut):
     for i in range(n):
         features = gcn_layer_dense(features, weights[i], biases[i], adj, cut, i < n - 1, i < n - 1)
     return features
+
+
+# ---------------------------------------------------------------- positional embedding (as the reference)
+def nerf_embedding(points):
+    """Positional_Encoder.nerf_embedding followed by the cat with the positions
+    (pterotactyl/reconstruction/vision/model.py:381-391, 396-397): (M,3) -> (M,63)."""
+    parts = []
+    for i in range(10):
+        s = np.pi if i == 0 else np.pi * 2 * i
+        parts += [torch.sin(s * points), torch.cos(s * points)]
+    return torch.cat((torch.cat(parts, dim=-1), points), dim=-1)

@@ -146,3 +146,15 @@ def test_torch_dense_restatement_matches_reference(golden):
     bs = [torch.from_numpy(g[f"{name}_b{i}"]) for i in range(nl)]
     y = tr.gcn_dense(torch.from_numpy(g[name + "_x"]), ws, bs, dense, float(g[name + "_cut"][0]))
     assert rel_err(y.numpy(), g[name + "_y"]) < 1e-6
+
+
+@pytest.mark.parametrize("tag", ["small", "c3"])
+def test_nerf_embedding_restatement_matches_reference(golden, tag):
+    """oracle/torch_ref.nerf_embedding vs the reference's own Positional_Encoder.nerf_embedding output."""
+    from oracle import torch_ref as tr
+    g = golden("encoder")
+    pos = torch.from_numpy(g[f"{tag}_pos"]).reshape(-1, 3)
+    emb = tr.nerf_embedding(pos)
+    assert emb.shape == (pos.shape[0], 63)
+    assert np.array_equal(emb[:, :60].numpy(), g[f"{tag}_embedding"])
+    assert torch.equal(emb[:, 60:], pos)
