@@ -11,6 +11,7 @@ References (relative to /root/reference):
   pterotactyl/utility/utils.py:152-187  batch_sample
   pterotactyl/utility/utils.py:204-217  chamfer_distance
   pterotactyl/reconstruction/vision/model.py:351-363  GCN_layer.forward
+  pterotactyl/reconstruction/vision/model.py:381-397  Positional_Encoder.nerf_embedding (+ cat)
   PyTorch3D v0.5.0 (not vendored): loss/chamfer.py, ops/knn.py, ops/mesh_face_areas_normals.py,
   ops/sample_points_from_meshes.py::_rand_barycentric_coords (SURVEY.md Appendix B).
 """
