@@ -22,7 +22,7 @@ import sys
 
 from . import _lib, dist, encoders, graph, host, model, obj_io, ops, policy, recon, utils  # noqa: F401
 from .encoders import Mask_Encoder, Positional_Encoder  # noqa: F401
-from .model import GCN, GCN_layer  # noqa: F401
+from .model import GCN, Encoder, GCN_layer, Graph_Model  # noqa: F401
 from .utils import batch_sample, chamfer_distance  # noqa: F401
 
 __all__ = ["ops", "utils", "model", "graph", "host", "dist", "GCN", "GCN_layer", "batch_sample",
@@ -57,4 +57,8 @@ def install(ref_utils=None, ref_models=()):
             mod.GCN = GCN
         if hasattr(mod, "Positional_Encoder"):
             mod.Positional_Encoder = Positional_Encoder
+        if hasattr(mod, "Encoder") and hasattr(mod, "AutoEncoder"):  # autoencoder/model.py:45
+            mod.Encoder = model.Encoder
+        if hasattr(mod, "Graph_Model"):  # policies/DDQN/model.py:65
+            mod.Graph_Model = model.Graph_Model
     return ref_utils
