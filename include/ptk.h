@@ -169,7 +169,10 @@ int ptk_relu_mask(const float *g, const float *act, int64_t n, float *out, ptk_s
  *   wgrad : gW (K,N) = X^T . gH  (overwrites gW; the sum over the M rows is split across CTAs and
  *           reduced in a fixed order through the workspace => deterministic)
  * ---------------------------------------------------------------------------------------------- */
-size_t ptk_gcn_linear_workspace_bytes(int64_t M, int64_t K, int64_t N); /* fwd and dgrad */
+/* Workspace of fwd and dgrad: the split weights, the packed ReLU mask and one partial output tile + flag per
+ * persistent CTA (the tensor-core kernel deals its k-blocks out evenly; a tile shared by two CTAs is combined
+ * through that slot in a fixed order).  One workspace must not be shared by calls running concurrently. */
+size_t ptk_gcn_linear_workspace_bytes(int64_t M, int64_t K, int64_t N);
 /* algo: PTK_GEMM_AUTO (tensor cores where eligible), PTK_GEMM_FFMA (exact-FP32 FFMA, k-sequential
  * accumulation like a scalar FP32 loop) or PTK_GEMM_TF32X3 (error if the shape is not eligible). */
 #define PTK_GEMM_AUTO 0
