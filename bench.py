@@ -491,6 +491,13 @@ def recon_step_measurement(torch, ptk_b200, dev, rank, world):
            "grad_allreduce": (f"{len(reducer.buckets)} NCCL buckets overlapped with backward" if world > 1 else "none (1 GPU)")}
     gemm_flop = 3 * 2 * Bs * (1824 * (448 * 300 + 18 * 300 * 300 + 300 * 3) + 2 * 1949 * (448 * 300 + 18 * 300 * 300 + 300 * 3))
     out["gemm_tflops_per_gpu"] = gemm_flop / (ms * 1e-3) / 1e12
+    # north_star's yardstick for the step: algorithmic GEMM flop (964 GFLOP per step at 16 objects) over
+    # the chip's FP32 FMA peak.  The backward GEMMs run on the tensor cores, so this is a throughput fraction, not a
+    # pipe utilisation; aggregation, Chamfer and optimizer time count against it.
+    info = ptk_b200._lib.device_info(dev.index or 0)
+    fp32_peak = 2 * 128 * info["sm_count"] * info["clock_khz"] * 1e3 / 1e12
+    out["fp32_peak_tflops"] = fp32_peak
+    out["fp32_roofline_frac"] = out["gemm_tflops_per_gpu"] / fp32_peak
     if world == 1:
         try:  # the same step replayed from one CUDA graph (launch gaps and Python overhead removed)
             opt_g = torch.optim.Adam(net.parameters(), lr=3e-4, fused=True, capturable=True)
@@ -507,6 +514,7 @@ def recon_step_measurement(torch, ptk_b200, dev, rank, world):
             msg = timeit(graphed, 10, 2)
             out["ms_cuda_graph"] = msg
             out["steps_per_s_cuda_graph"] = 1e3 / msg
+            out["fp32_roofline_frac_cuda_graph"] = gemm_flop / (msg * 1e-3) / 1e12 / fp32_peak
         except Exception as exc:
             out["cuda_graph_error"] = repr(exc)[:300]
     return out
