@@ -654,23 +654,35 @@ bias_grad_stage1(const float *__restrict__ g, long long M, int C, int L, float *
     // blockIdx.y = layer of a batched call: g and part advance by one (M x C) matrix / one partial block per layer
     g += (size_t)blockIdx.y * (size_t)M * C;
     part += (size_t)blockIdx.y * gridDim.x * L;
-    __shared__ float red[8][33];
+    // four 32-column blocks per pass: 4 independent loads per row and thread in flight, one barrier pair per pass
+    constexpr int NB = 4;
+    __shared__ float red[NB][8][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const long long per = (M + gridDim.x - 1) / gridDim.x;
     const long long r0 = (long long)blockIdx.x * per;
     const long long r1 = r0 + per < M ? r0 + per : M;
-    for (int cbase = 0; cbase < L; cbase += 32) {
-        const int c = cbase + cx;
-        float acc = 0.f;
-        if (c < L)
-            for (long long r = r0 + ry; r < r1; r += 8) acc += g[(size_t)r * C + c];
-        red[ry][cx] = acc;
-        __syncthreads();
-        if (ry == 0 && c < L) {
-            float t = red[0][cx];
+    for (int cbase = 0; cbase < L; cbase += 32 * NB) {
+        float acc[NB];
 #pragma unroll
-            for (int y = 1; y < 8; ++y) t += red[y][cx];
-            part[(size_t)blockIdx.x * L + c] = t;
+        for (int j = 0; j < NB; ++j) acc[j] = 0.f;
+#pragma unroll 4
+        for (long long r = r0 + ry; r < r1; r += 8) {
+            const float *row = g + (size_t)r * C + cbase + cx;
+#pragma unroll
+            for (int j = 0; j < NB; ++j)
+                if (cbase + 32 * j + cx < L) acc[j] += row[32 * j];
+        }
+#pragma unroll
+        for (int j = 0; j < NB; ++j) red[j][ry][cx] = acc[j];
+        __syncthreads();
+        if (ry < NB) {  // warp j finishes column block j (fixed order over the row lanes)
+            const int c = cbase + 32 * ry + cx;
+            if (c < L) {
+                float t = red[ry][0][cx];
+#pragma unroll
+                for (int y = 1; y < 8; ++y) t += red[ry][y][cx];
+                part[(size_t)blockIdx.x * L + c] = t;
+            }
         }
         __syncthreads();
     }
