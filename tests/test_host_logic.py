@@ -96,6 +96,35 @@ def test_install_patches_reference_module():
     assert fake.chamfer_distance is ptk_b200.utils.chamfer_distance
     assert fake.batch_sample is ptk_b200.utils.batch_sample
     assert fake_model.GCN is ptk_b200.GCN and fake_model.GCN_layer is ptk_b200.GCN_layer
+    assert not hasattr(fake_model, "Encoder") and not hasattr(fake_model, "Graph_Model")
+    # the autoencoder / DDQN modules: their GCN consumers and the Positional_Encoder copies are replaced too
+    ae = types.SimpleNamespace(GCN_layer=None, Encoder=None, AutoEncoder=None, Positional_Encoder=None)
+    ddqn = types.SimpleNamespace(GCN_layer=None, Graph_Model=None, Positional_Encoder=None, Encoder=None)
+    ptk_b200.install(fake, [ae, ddqn])
+    assert ae.Encoder is ptk_b200.model.Encoder and ae.Positional_Encoder is ptk_b200.Positional_Encoder
+    assert ddqn.Graph_Model is ptk_b200.model.Graph_Model and ddqn.GCN_layer is ptk_b200.GCN_layer
+    assert ddqn.Encoder is None  # an unrelated class called Encoder (no AutoEncoder beside it) is left alone
+
+
+def test_encoder_mirrors_state_dict_layout():
+    """Positional_Encoder / Mask_Encoder / Encoder / Graph_Model keep the reference's parameter names
+    (vision/model.py:367-414, autoencoder/model.py:45-92, DDQN/model.py:65-101)."""
+    pe, me = ptk_b200.Positional_Encoder(48), ptk_b200.Mask_Encoder(48)
+    assert list(pe.state_dict()) == ["model.0.weight", "model.0.bias", "model.2.weight", "model.2.bias",
+                                     "model.4.weight", "model.4.bias"]
+    assert pe.model[0].weight.shape == (12, 63) and pe.model[4].weight.shape == (48, 24)
+    assert list(me.state_dict()) == ["model.0.weight"] and me.model[0].weight.shape == (4, 48)
+    enc = ptk_b200.model.Encoder(50, types.SimpleNamespace(num_GCN_layers=3, hidden_GCN_size=40, cut=0.33,
+                                                           encoding_size=20))
+    keys = list(enc.state_dict())
+    assert keys[:6] == ["layers.0.weight", "layers.0.bias", "layers.1.weight", "layers.1.bias", "layers.2.weight",
+                        "layers.2.bias"]
+    assert keys[6:] == [f"mlp.{i}.0.{w}" for i in range(4) for w in ("weight", "bias")]
+    assert enc.layers[2].do_cut is False and enc.layers[2].propagated() == 40 and enc.layers[0].propagated() == 13
+    gm = ptk_b200.model.Graph_Model(types.SimpleNamespace(layers=2, hidden_dim=100, num_actions=50, cut=0.33),
+                                    {"adj": torch.eye(3)})
+    assert [tuple(l.weight.shape) for l in gm.layers] == [(1, 300, 100), (1, 100, 50)]
+    assert "positional_embedding.model.4.weight" in gm.state_dict() and "mask_embedding.model.0.weight" in gm.state_dict()
 
 
 def test_pytorch3d_shim_imports():
