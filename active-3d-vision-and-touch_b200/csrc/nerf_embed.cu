@@ -59,7 +59,7 @@ nerf_embed_bwd_kernel(const float *__restrict__ pos, const float *__restrict__ g
 using namespace ptk;
 
 extern "C" int ptk_nerf_embed_fwd(const float *positions, int64_t M, float *out, ptk_stream_t stream) {
-    PTK_REQUIRE(M >= 0 && M < (1LL << 40), PTK_ERR_SHAPE, "nerf_embed_fwd: bad M = %lld", (long long)M);
+    PTK_REQUIRE(M >= 0 && M < (1LL << 31), PTK_ERR_SHAPE, "nerf_embed_fwd: bad M = %lld", (long long)M);
     if (M == 0) return PTK_OK;
     PTK_REQUIRE(positions && out, PTK_ERR_SHAPE, "nerf_embed_fwd: null pointer");
     nerf_embed_fwd_kernel<<<(unsigned)ceil_div(M * NE_W, 256), 256, 0, as_stream(stream)>>>(positions, (long long)M, out);
@@ -69,7 +69,7 @@ extern "C" int ptk_nerf_embed_fwd(const float *positions, int64_t M, float *out,
 
 extern "C" int ptk_nerf_embed_bwd(const float *positions, const float *grad_out, int64_t M, float *grad_positions,
                                   ptk_stream_t stream) {
-    PTK_REQUIRE(M >= 0 && M < (1LL << 40), PTK_ERR_SHAPE, "nerf_embed_bwd: bad M = %lld", (long long)M);
+    PTK_REQUIRE(M >= 0 && M < (1LL << 31), PTK_ERR_SHAPE, "nerf_embed_bwd: bad M = %lld", (long long)M);
     if (M == 0) return PTK_OK;
     PTK_REQUIRE(positions && grad_out && grad_positions, PTK_ERR_SHAPE, "nerf_embed_bwd: null pointer");
     nerf_embed_bwd_kernel<<<(unsigned)ceil_div(M * 3, 256), 256, 0, as_stream(stream)>>>(positions, grad_out, (long long)M,
