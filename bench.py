@@ -63,7 +63,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25", "-i",
                  str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -73,6 +73,13 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), line.strip()))
+
+    def wait_ready(self, timeout=5.0):
+        """Block until nvidia-smi has delivered its first row (its start-up can take longer than the whole timed
+        region on a fresh box), so that the timed region is guaranteed to be sampled."""
+        t_end = time.time() + timeout
+        while self.proc is not None and not self.rows and time.time() < t_end and self.proc.poll() is None:
+            time.sleep(0.01)
 
     def stop(self, t0, t1):
         if self.proc is None:
@@ -92,8 +99,10 @@ class ClockSampler:
             for n, v in zip(names, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
-        if not sm:  # timed region shorter than the sampling period: use every sample we have
+        if not sm:  # no row inside the window: fall back to the rows of the warm-up right before it (same load)
             for ts, line in self.rows:
+                if ts < t0 - 1.0:
+                    continue
                 f = [x.strip() for x in line.split(",")]
                 try:
                     sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
@@ -287,14 +296,18 @@ def run_ours(args):
         _lib.check(L.ptk_chamfer_bwd(p(xs[i % NSETS]), p(ys[i % NSETS]), p(idx_x), p(idx_y), p(gcham), B, P, P,
                                      p(gx), p(gy), sp), "ptk_chamfer_bwd")
 
+    sampler = ClockSampler(local) if rank == 0 else None  # started before the warm-up: nvidia-smi needs time to come up
     for i in range(W):
         fwd(i); bwd(i)
     torch.cuda.synchronize()
+    if sampler:
+        sampler.wait_ready()
+        fwd(0); bwd(0)  # untimed: the GPU is under load again when the timed region starts
+        torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
 
-    sampler = ClockSampler(local) if rank == 0 else None
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
     t_wall0 = time.time()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
