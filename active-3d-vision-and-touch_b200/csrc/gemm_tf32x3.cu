@@ -671,6 +671,18 @@ relu_bits_kernel(const float *__restrict__ act, long long M, int N, int wpr, uin
     }
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize has to be set once per DEVICE (a process may drive several):
+// one bit per (kernel family, device ordinal).
+static unsigned long long g_smem_optin[2] = {0ull, 0ull};
+static bool smem_optin_done(int family) {
+    int dev = 0;
+    return cudaGetDevice(&dev) == cudaSuccess && dev < 64 && ((g_smem_optin[family] >> dev) & 1ull);
+}
+static void smem_optin_mark(int family) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev < 64) g_smem_optin[family] |= 1ull << dev;
+}
+
 bool tf32x3_eligible(const void *A, const void *D, int64_t M, int64_t K, int64_t N) {
     // TMA needs 16-byte aligned bases and row pitches; tiny reductions / outputs stay on the SIMT path
     return M >= 1 && K >= 32 && N >= 16 && (K % 4) == 0 && (((uintptr_t)A) % 16) == 0 && (((uintptr_t)D) % 16) == 0;
@@ -731,11 +743,10 @@ int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act
     p.flags = flags;
     const size_t smem = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024;
     dim3 grid((unsigned)n_ctas);
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!smem_optin_done(0)) {  // the attribute is per device
         PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        smem_optin_mark(0);
     }
     if (act)
         gemm_tf32x3_kernel<true><<<grid, TG_THREADS, smem, st>>>(map_a, map_bhi, map_blo, p);
@@ -787,10 +798,9 @@ int wgrad_tf32x3(const float *X, const float *gH, int64_t M, int64_t Kin, int64_
     p.M = (int)M; p.Kin = (int)Kin; p.Nout = (int)Nout; p.kb_per_split = w.kb_per_split; p.num_kb_total = w.num_kb;
     p.part = part;
     const size_t smem = (size_t)WG_NS * TG_STAGE_BYTES + (size_t)WG_NR * WG_RAW_BYTES + 1024;
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!smem_optin_done(1)) {
         PTK_CHECK_CUDA(cudaFuncSetAttribute(wgrad_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
+        smem_optin_mark(1);
     }
     dim3 grid((unsigned)w.tiles_m, (unsigned)w.tiles_n, (unsigned)w.splits);
     wgrad_tf32x3_kernel<<<grid, WG_THREADS, smem, st>>>(map_x, map_g, p);
