@@ -16,17 +16,19 @@ Layout
     policy.py               batched candidate scoring of the greedy touch policies (environment.best_step)
     dist.py                 object/batch sharding + NCCL gradient all-reduce / loss gather
     pytorch3d_shim/         the five pytorch3d.* names the reference imports
+    import_stubs.py         import-only placeholders for matplotlib / trimesh / pyrender / pybullet / submitit
 """
 import os
 import sys
 
-from . import _lib, dist, encoders, graph, host, model, obj_io, ops, policy, recon, utils  # noqa: F401
+from . import _lib, dist, encoders, graph, host, import_stubs, model, obj_io, ops, policy, recon, utils  # noqa: F401
+from .import_stubs import install_import_stubs  # noqa: F401
 from .encoders import Mask_Encoder, Positional_Encoder  # noqa: F401
 from .model import GCN, Encoder, GCN_layer, Graph_Model  # noqa: F401
 from .utils import batch_sample, chamfer_distance  # noqa: F401
 
 __all__ = ["ops", "utils", "model", "graph", "host", "dist", "GCN", "GCN_layer", "batch_sample",
-           "chamfer_distance", "install", "install_pytorch3d_shim"]
+           "chamfer_distance", "install", "install_pytorch3d_shim", "install_import_stubs", "find_reference"]
 
 _SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pytorch3d_shim")
 
@@ -37,28 +39,87 @@ def install_pytorch3d_shim():
         sys.path.insert(0, _SHIM)
 
 
+def find_reference():
+    """Directory that holds an importable `pterotactyl/` (the reference checkout or its install), or None.
+    Order: $PTK_REFERENCE, an already importable `pterotactyl`, <repo>/baseline/_ref (tools/install_reference.py),
+    /root/reference."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cands = [os.environ.get("PTK_REFERENCE"), None, os.path.join(root, "baseline", "_ref"), "/root/reference"]
+    for c in cands:
+        if c is None:
+            try:
+                spec = importlib.util.find_spec("pterotactyl")
+            except (ImportError, ValueError):
+                spec = None
+            if spec is not None and spec.submodule_search_locations:
+                return os.path.dirname(list(spec.submodule_search_locations)[0])
+            continue
+        if os.path.isfile(os.path.join(c, "pterotactyl", "utility", "utils.py")):
+            return c
+    return None
+
+
+def import_reference(*names):
+    """Import unedited reference modules (`"utility.utils"`, `"reconstruction.vision.model"`, ...) with the
+    pytorch3d shim and the import stubs in place; returns them in order.  Raises ImportError when no reference
+    checkout / install can be found (find_reference)."""
+    import importlib
+    install_pytorch3d_shim()
+    install_import_stubs()
+    ref = find_reference()
+    if ref is None:
+        raise ImportError("no pterotactyl checkout found: set PTK_REFERENCE or run tools/install_reference.py")
+    if ref not in sys.path:
+        sys.path.append(ref)
+    mods = [importlib.import_module("pterotactyl." + n) for n in names]
+    return mods[0] if len(mods) == 1 else mods
+
+
+_originals = []  # (module, attribute, value before install()) -- what uninstall() restores
+
+
+def _patch(mod, name, value):
+    _originals.append((mod, name, getattr(mod, name, None)))
+    setattr(mod, name, value)
+
+
 def install(ref_utils=None, ref_models=()):
     """Seam S2: patch the reference's modules in place so its unchanged scripts use the fused path.
 
-    ref_utils  : the imported `pterotactyl.utility.utils` module (imported here if None)
+    ref_utils  : the imported `pterotactyl.utility.utils` module (imported here, through the pytorch3d shim and
+                 the import stubs, if None)
     ref_models : modules holding GCN / GCN_layer copies (vision.model, autoencoder.model, DDQN.model);
-                 vision.model's Positional_Encoder is replaced too
+                 their Positional_Encoder copies are replaced too
+    `uninstall()` puts every replaced attribute back.
     """
     if ref_utils is None:
-        install_pytorch3d_shim()
-        from pterotactyl.utility import utils as ref_utils  # noqa: WPS433
+        ref_utils = import_reference("utility.utils")
     for name in ("chamfer_distance", "batch_sample", "calc_adj", "normalize_adj", "adj_fuse_touch",
                  "adj_init", "load_mesh_touch", "load_mesh_vision"):
-        setattr(ref_utils, name, getattr(utils, name))
+        _patch(ref_utils, name, getattr(utils, name))
     for mod in ref_models:
         if hasattr(mod, "GCN_layer"):
-            mod.GCN_layer = GCN_layer
+            _patch(mod, "GCN_layer", GCN_layer)
         if hasattr(mod, "GCN"):
-            mod.GCN = GCN
+            _patch(mod, "GCN", GCN)
         if hasattr(mod, "Positional_Encoder"):
-            mod.Positional_Encoder = Positional_Encoder
+            _patch(mod, "Positional_Encoder", Positional_Encoder)
         if hasattr(mod, "Encoder") and hasattr(mod, "AutoEncoder"):  # autoencoder/model.py:45
-            mod.Encoder = model.Encoder
+            _patch(mod, "Encoder", model.Encoder)
         if hasattr(mod, "Graph_Model"):  # policies/DDQN/model.py:65
-            mod.Graph_Model = model.Graph_Model
+            _patch(mod, "Graph_Model", model.Graph_Model)
     return ref_utils
+
+
+def uninstall():
+    """Undo every install() since the last uninstall(): the reference's own functions and classes are back."""
+    while _originals:
+        mod, name, value = _originals.pop()
+        if value is None:
+            try:
+                delattr(mod, name)
+            except AttributeError:
+                pass
+        else:
+            setattr(mod, name, value)

@@ -18,6 +18,7 @@ SIGNATURES = {
     "ptk_version": (C.c_int, []),
     "ptk_last_error": (C.c_char_p, []),
     "ptk_device_info": (C.c_int, [C.c_int] + [C.POINTER(C.c_int)] * 6),
+    "ptk_launch_count": (C.c_uint64, []),
     "ptk_chamfer_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "ptk_chamfer_set_algo": (C.c_int, [C.c_int]),
     "ptk_chamfer_get_algo": (C.c_int, []),
@@ -101,6 +102,11 @@ def check(rc, what=""):
     if rc == PTK_ERR_SHAPE:
         raise ValueError(msg)  # PyTorch3D raises ValueError on shape errors
     raise RuntimeError(f"libptk_b200 error {rc}: {msg}")
+
+
+def launch_count():
+    """Kernels launched by libptk_b200.so in this process so far."""
+    return int(lib().ptk_launch_count())
 
 
 def device_info(device=0):

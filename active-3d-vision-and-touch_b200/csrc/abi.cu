@@ -2,6 +2,8 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+
 #include "ptk_common.cuh"
 
 namespace ptk {
@@ -14,6 +16,10 @@ void set_error(const char *fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<unsigned long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 148;
@@ -34,6 +40,8 @@ int sm_count() {
 extern "C" int ptk_version(void) { return PTK_ABI_VERSION; }
 
 extern "C" const char *ptk_last_error(void) { return ptk::g_err; }
+
+extern "C" uint64_t ptk_launch_count(void) { return ptk::g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int ptk_device_info(int device, int *sm_count, int *clock_khz, int *l2_bytes,
                                int *smem_optin, int *cc_major, int *cc_minor) {

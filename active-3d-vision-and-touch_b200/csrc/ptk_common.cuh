@@ -29,7 +29,14 @@ void set_error(const char *fmt, ...);
         }                                    \
     } while (0)
 
-#define PTK_CHECK_LAUNCH() PTK_CHECK_CUDA(cudaGetLastError())
+void count_launch();  // ptk_launch_count(): one tick per kernel launch of this library
+
+// after EVERY <<<>>> of this library, exactly once
+#define PTK_CHECK_LAUNCH()                   \
+    do {                                     \
+        ::ptk::count_launch();               \
+        PTK_CHECK_CUDA(cudaGetLastError());  \
+    } while (0)
 
 inline cudaStream_t as_stream(ptk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

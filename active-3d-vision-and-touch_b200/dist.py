@@ -70,21 +70,31 @@ def gather_objects_vector(local_vec, n_total, group=None):
 class GradReducer:
     """Bucketed gradient all-reduce overlapped with the backward.
 
-    Parameters are packed, in reverse registration order (the order the backward produces them),
-    into flat buckets of ~bucket_mb.  A post-accumulate-grad hook per parameter copies the gradient
-    into its bucket; when a bucket is complete its all-reduce is launched asynchronously.  `finish()`
-    waits, divides by the global object count ratio and scatters the averaged gradients back.
-    With loss = mean over the GLOBAL batch, each rank scales its local-sum loss by 1/B_global and the
-    reduction op is SUM, so the result equals the single-GPU gradient of the concatenated batch.
+    Parameters are packed, in reverse registration order (the order the backward produces them), into flat
+    buckets of ~bucket_mb.  A post-accumulate-grad hook per parameter copies the gradient into its bucket (no copy
+    when `p.grad` already IS the bucket slice, see below); a bucket's all-reduce is launched asynchronously once it
+    AND every earlier bucket is complete, so every rank issues the collectives in the same (bucket) order even if a
+    parameter receives its gradient late -- or not at all -- on some rank.  `finish()` launches whatever is left,
+    waits, and points every `p.grad` at its (reduced) bucket slice: no copy back.  Nothing is divided: the reduction
+    is a SUM, so each rank scales its local-sum loss by 1/B_global and the result equals the single-GPU gradient of
+    the concatenated batch (vision/train.py:144 `loss.mean()`).
+
+    One backward per `finish()`.  A second backward before `finish()` (gradient accumulation, several losses)
+    would overwrite a bucket that may already be in flight: the hook raises instead of reducing garbage.  To
+    accumulate over micro-batches, run the extra backwards inside `no_sync()` and only the last one outside.
+    With `optimizer.zero_grad(set_to_none=False)` the gradients stay views of the buckets and autograd accumulates
+    straight into them.
     """
 
-    def __init__(self, params, bucket_mb=32, group=None):
+    def __init__(self, params, bucket_mb=32, group=None, first_bucket_mb=None):
         self.group = group
         self.params = [p for p in params if p.requires_grad]
         self.enabled = dist.is_initialized() and dist.get_world_size(group) > 1
         self.buckets = []  # (flat tensor, [(param, offset, numel)])
         self._pending = {}
         self._handles = []
+        self._next = 0  # next bucket to launch: collectives are issued strictly in bucket order
+        self._sync = True
         if not self.enabled:
             return
         cap = int(bucket_mb * (1 << 20) / 4)
@@ -114,35 +124,64 @@ class GradReducer:
     def reset(self):
         self._pending = {bi: len(items) for bi, (_, items) in enumerate(self.buckets)}
         self._handles = []
+        self._next = 0
+
+    def no_sync(self):
+        """Context manager: backwards inside it only accumulate into p.grad (no bucket copy, no collective)."""
+        reducer = self
+
+        class _NoSync:
+            def __enter__(self):
+                reducer._sync = False
+
+            def __exit__(self, *exc):
+                reducer._sync = True
+
+        return _NoSync()
+
+    def _launch_ready(self):
+        while self._next < len(self.buckets) and self._pending[self._next] == 0:
+            flat, _ = self.buckets[self._next]
+            self._handles.append((self._next, dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group,
+                                                              async_op=True)))
+            self._next += 1
 
     def _make_hook(self, bi, off, n):
         def hook(p):
+            if not self._sync:
+                return
+            if self._pending[bi] <= 0:
+                raise RuntimeError(
+                    "GradReducer: a parameter received a second gradient before finish() -- its bucket may already "
+                    "be in flight. Call finish() after every backward, or run the extra backwards of a gradient "
+                    "accumulation inside reducer.no_sync().")
             flat, _ = self.buckets[bi]
-            flat[off:off + n].copy_(p.grad.reshape(-1))
+            view = flat[off:off + n]
+            if p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad.reshape(-1))
             self._pending[bi] -= 1
-            if self._pending[bi] == 0:
-                self._handles.append((bi, dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)))
+            self._launch_ready()
         return hook
 
     def finish(self):
-        """Wait for all buckets and write the reduced gradients back into p.grad."""
+        """Launch the buckets that are still waiting (in order), wait for all of them and make every p.grad the
+        reduced slice of its bucket."""
         if not self.enabled:
             return
-        for bi, n in self._pending.items():  # parameters that received no gradient this step
-            if n > 0:
+        for bi in range(self._next, len(self.buckets)):
+            if self._pending[bi] > 0:  # parameters that received no gradient this step (on this rank)
                 flat, items = self.buckets[bi]
                 for p, off, cnt in items:
+                    view = flat[off:off + cnt]
                     if p.grad is None:
-                        flat[off:off + cnt].zero_()
-                    else:
-                        flat[off:off + cnt].copy_(p.grad.reshape(-1))
-                self._handles.append((bi, dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)))
+                        view.zero_()
+                    elif p.grad.data_ptr() != view.data_ptr():
+                        view.copy_(p.grad.reshape(-1))
+                self._pending[bi] = 0
+        self._launch_ready()
         for bi, h in self._handles:
             h.wait()
             flat, items = self.buckets[bi]
             for p, off, cnt in items:
-                if p.grad is None:
-                    p.grad = flat[off:off + cnt].view_as(p).clone()
-                else:
-                    p.grad.copy_(flat[off:off + cnt].view_as(p))
+                p.grad = flat[off:off + cnt].view_as(p)
         self.reset()

@@ -170,12 +170,16 @@ class _NerfEmbed(torch.autograd.Function):
         out = torch.empty(M, 63, dtype=torch.float32, device=pos.device)
         with torch.cuda.device(pos.device):
             _lib.check(_lib.lib().ptk_nerf_embed_fwd(_p(pos), M, _p(out), _stream()), "ptk_nerf_embed_fwd")
-        ctx.save_for_backward(pos)
+        # The reference's Deformation.forward updates `vertices` IN PLACE right after encoding them
+        # (vision/model.py:250,270,283), so the input must not be what the backward reads: the positions are the
+        # last three columns of the output (model.py:396-397), which nobody writes to.
+        ctx.save_for_backward(out)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        (pos,) = ctx.saved_tensors
+        (out,) = ctx.saved_tensors
+        pos = out[:, 60:].contiguous()
         gpos = torch.empty_like(pos)
         with torch.cuda.device(pos.device):
             _lib.check(_lib.lib().ptk_nerf_embed_bwd(_p(pos), _p(_f32c(g)), pos.shape[0], _p(gpos), _stream()),

@@ -9,8 +9,12 @@ scored by ONE sample + Chamfer pass and the masked arg-min runs on the device; n
 per candidate.  The simulator, the touch CNN and the deformation encoders stay the reference's own
 code: this module starts from the candidate meshes they produce.
 
-Multi-GPU: candidates are whole objects, so `score_candidates(..., shard=True)` splits the E*A rows
-over the ranks (ptk_b200.dist) and all-gathers the (E*A,) score vector -- the only collective.
+`best_step_batched` is the whole inner loop of `best_step` in one call: deformation network (no grad) on all
+E * A candidates -> 3 x (surface sampling + Chamfer) -> masked arg-min, in device-sized chunks.
+
+Multi-GPU: candidates are whole objects, so `score_candidates(..., shard=True)` / `best_step_batched(...,
+shard=True)` split the E*A rows over the ranks (ptk_b200.dist) and all-gather the (E*A,) score vector -- the
+only collective.
 """
 import torch
 
@@ -60,3 +64,64 @@ def best_actions(scores, mask=None):
     first = (s == best[:, None]).to(torch.int64).argmax(dim=1)
     arg = torch.where(torch.isinf(best), torch.full_like(first, -1), first)
     return arg, torch.where(torch.isinf(best), torch.full_like(best, 1000.0), best)
+
+
+def best_step_batched(deform, img, charts, gt_points, faces, mask=None, num=10000, loss_coeff=9000.0, repeat=3,
+                      chunk=400, shard=False, generator=None, uniforms=None):
+    """The candidate loop of ActiveTouch.best_step (environment.py:167-180) as one batched pass.
+
+    The reference evaluates, for each of the A actions in turn, `compute_obs` = `self.deform(img, charts)` under
+    no_grad followed by `get_score` = `loss_coeff * utils.chamfer_distance(verts, faces, gt, num)` and `.cpu()`
+    (environment.py:221-257), then keeps per environment the lowest score among unmasked actions.  Here:
+
+    deform     the deformation network, called as the reference calls it: `deform(img, charts) -> (verts, mask)`
+               (the reference's own `Deformation` after ptk_b200.install(), or any callable with that contract)
+    img        (E, 3, H, W) one image per environment (or None for touch-only models); repeated per candidate
+    charts     the dict `prepare_mesh` / `get_inputs` build, with a leading (E, A) candidate grid on the touch
+               entries: 'touch_charts' (E, A, T, 3), 'touch_masks' (E, A, T, 1); 'vision_charts' (E, V0, 3) and
+               'vision_masks' (E, V0, 1) are per environment (optionally (E, A, ...) too)
+    gt_points  (E, P, 3); faces (F, 3) shared; mask (E, A) nonzero = action already taken
+    chunk      candidates per deformation pass (bounds activation memory: 400 x 1949 x 448 floats = 1.4 GB)
+
+    Returns (actions (E,) int64 with -1 where the reference keeps None, best scores (E,), scores (E, A)).
+    With shard=True every rank evaluates its contiguous block of the E*A candidates and the scores are
+    all-gathered, so all ranks return the same decision."""
+    tc = charts["touch_charts"]
+    if tc.dim() != 4:
+        raise ValueError(f"touch_charts must be (E, A, T, 3), got {tuple(tc.shape)}")
+    E, A = tc.shape[:2]
+    if gt_points.shape[0] != E:
+        raise ValueError("gt_points must have one cloud per environment")
+    lo, hi = 0, E * A
+    if shard:
+        rank, world = _dist.rank_world()
+        lo, hi = _dist.shard_bounds(E * A, rank, world)
+
+    def cand(t, idx):
+        """Rows `idx` of a chart tensor: per candidate when it carries the (E, A) grid, else per environment."""
+        if t.dim() == 4 and tuple(t.shape[:2]) == (E, A):
+            return t.reshape(E * A, *t.shape[2:]).index_select(0, idx)
+        return t.index_select(0, idx // A)
+
+    env = lambda t, idx: t.index_select(0, idx // A)  # img, gt_points: one per environment
+
+    out = []
+    with torch.no_grad():
+        for s in range(lo, hi, max(int(chunk), 1)):
+            e = min(s + max(int(chunk), 1), hi)
+            idx = torch.arange(s, e, device=tc.device)
+            sub = {k: cand(v, idx) for k, v in charts.items()}
+            verts = deform(env(img, idx) if img is not None else None, sub)
+            verts = verts[0] if isinstance(verts, (tuple, list)) else verts
+            uni = None
+            if uniforms is not None:
+                uni = [(uf[s:e].contiguous(), uv[:, s:e].contiguous()) for uf, uv in uniforms]
+            cd = utils.chamfer_distance(verts, faces, env(gt_points, idx), num=num, repeat=repeat,
+                                        generator=generator, uniforms=uni)
+            out.append(loss_coeff * cd)
+        scores = torch.cat(out) if out else torch.empty(0, device=tc.device)
+        if shard:
+            scores = _dist.gather_objects_vector(scores, E * A)
+        scores = scores.reshape(E, A)
+        actions, best = best_actions(scores, mask)
+    return actions, best, scores

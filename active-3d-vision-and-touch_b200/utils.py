@@ -10,6 +10,7 @@ arguments, return values and error behaviour, backed by libptk_b200.so.
 reference's train / eval / policy scripts pick the new path up without edits.
 """
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -17,20 +18,39 @@ import torch
 from . import graph as _graph
 from . import obj_io, ops
 
-_faces_cache = {}
+_faces_cache = {}  # id(faces) -> (weakref to that very tensor, its _version, int32 copy, largest vertex id)
 
 
-def _faces_i32(faces):
-    """(F,3) int64 faces of the reference -> cached int32 copy on the same device."""
-    if faces.dtype == torch.int32:
-        return faces.contiguous()
-    key = (faces.data_ptr(), faces._version, tuple(faces.shape), str(faces.device))
+def _faces_i32(faces, n_verts=None):
+    """(F,3) int64 faces of the reference -> int32 copy on the same device, validated.
+
+    The copy and the id range are cached PER LIVE TENSOR OBJECT: a hit requires that the weak reference still
+    points at this very tensor and that its version counter is unchanged, so a new tensor that happens to reuse
+    a freed tensor's address (the caching allocator does that all the time) can never be served a stale copy.
+    Vertex ids are checked against [0, n_verts): torch's own indexing would raise where the kernels would read out
+    of bounds (one host read per new faces tensor, none afterwards)."""
+    key = id(faces)
     hit = _faces_cache.get(key)
-    if hit is None:
+    if hit is None or hit[0]() is not faces or hit[1] != faces._version:
+        if faces.dim() != 2 or faces.shape[1] != 3:
+            raise ValueError(f"faces must be (F,3), got {tuple(faces.shape)}")
+        f32 = faces.contiguous() if faces.dtype == torch.int32 else faces.to(torch.int32).contiguous()
+        lo, hi = (int(faces.min()), int(faces.max())) if faces.numel() else (0, -1)
+        if lo < 0:
+            raise IndexError(f"negative vertex id {lo} in faces")
         if len(_faces_cache) > 64:
-            _faces_cache.clear()
-        hit = _faces_cache[key] = faces.to(torch.int32).contiguous()
-    return hit
+            for k in [k for k, v in _faces_cache.items() if v[0]() is None]:
+                del _faces_cache[k]
+            if len(_faces_cache) > 64:
+                _faces_cache.clear()
+        try:
+            ref = weakref.ref(faces)
+        except TypeError:  # pragma: no cover
+            return f32
+        hit = _faces_cache[key] = (ref, faces._version, f32, hi)
+    if n_verts is not None and hit[3] >= n_verts:
+        raise IndexError(f"faces reference vertex {hit[3]} but the meshes have {n_verts} vertices")
+    return hit[2]
 
 
 def draw_uniforms(bs, num, device, generator=None):
@@ -46,7 +66,7 @@ def batch_sample(verts, faces, num=10000, generator=None, uniforms=None):
     """Sample `num` area-weighted surface points per mesh.  verts (B,V,3), faces (F,3) shared by the
     batch -> (B,num,3).  Gradients flow to verts only (utils.py:152-187)."""
     u_face, uv = uniforms if uniforms is not None else draw_uniforms(verts.shape[0], num, verts.device, generator)
-    pts, _ = ops.sample_points(verts, _faces_i32(faces), u_face, uv)
+    pts, _ = ops.sample_points(verts, _faces_i32(faces, verts.shape[-2]), u_face, uv)
     return pts
 
 

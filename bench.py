@@ -31,9 +31,8 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL prints "NCCL version ..." on stdout at NCCL_DEBUG=VERSION/INFO; stdout must carry exactly one JSON line
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() in ("VERSION", "INFO") and not os.environ.get("PTK_KEEP_NCCL_DEBUG"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# NCCL_DEBUG is left as the launcher set it: whatever NCCL prints goes to stderr (run_ours dup2()s fd 1 onto fd 2
+# while the job runs), stdout carries exactly one JSON line.
 
 P = 10000           # points per cloud
 B_PER_GPU = 256     # cloud pairs per GPU per step
@@ -220,12 +219,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    info, el, n, bs = cpu_chamfer_leg(None, steps=max(args.steps, 1), warmup=min(args.warmup, 1))
+    info, el, n, bs = cpu_chamfer_leg(None, steps=max(args.steps, 1), warmup=max(args.warmup, 0))
     line = {
         "impl": "reference", "metric": "chamfer_pairs_per_s_10k", "value": info["value"], "unit": "pairs/s",
-        "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * el / n,
+        "n_gpus": args.gpus, "steps": n, "warmup": max(args.warmup, 0), "ms_per_step": 1e3 * el / n,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": workload_config(args.gpus, sample_pairs=bs),
+        "config": workload_config(args.gpus),
         "cpu_baseline": info,
         "e2e": {"value": info["value"], "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -235,14 +234,12 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus, sample_pairs=None):
+def workload_config(n_gpus):
     cfg = {"workload": f"Chamfer fwd+bwd, {P}x{P} points, batch {B_PER_GPU} pairs per GPU (BASELINE configs[4] "
                        f"cell P=10k,B=256; north_star target shape)",
            "points": P, "pairs_per_gpu": B_PER_GPU, "global_pairs": B_PER_GPU * n_gpus,
            "parallelism": f"object-sharded x{n_gpus}, no data-path collective",
            "l2_policy": f"rotating {NSETS} input sets ({NSETS * 2 * B_PER_GPU * P * 12 / 1e6:.0f} MB > 126 MB L2)"}
-    if sample_pairs is not None:
-        cfg["cpu_sample_pairs_per_step"] = sample_pairs
     return cfg
 
 
@@ -309,6 +306,7 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K)]
+    launches0 = _lib.launch_count()
     t_wall0 = time.time()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     start.record(stream)
@@ -321,8 +319,12 @@ def run_ours(args):
     stop.record(stream)
     torch.cuda.synchronize()
     t_wall1 = time.time()
+    launches = _lib.launch_count() - launches0  # kernels of libptk_b200.so launched inside the timed region, this rank
     if world > 1:
         dist.barrier()
+        t = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        launches = int(t.item())
     total_ms = start.elapsed_time(stop)
     fwd_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     bwd_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
@@ -356,17 +358,41 @@ def run_ours(args):
         t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    ctx.close()
     e2e = {"value": world * B * ke / e2e_s, "unit": "pairs/s", "h2d_bytes_per_step": 2 * B * P * 12 + B * 4,
            "d2h_bytes_per_step": B * 4, "steps": ke, "ms_per_step": 1e3 * e2e_s / ke,
            "api": "ptk_host_chamfer (C ABI, pinned host buffers; backward on device, loss read back)"}
+    # the same call returning BOTH gradient clouds to the host as well (2 x 31 MB more D2H per step)
+    hgx, hgy = torch.empty(B, P, 3).pin_memory(), torch.empty(B, P, 3).pin_memory()
+    outg = {"cham": hcham.numpy(), "grad_x": hgx.numpy(), "grad_y": hgy.numpy()}
+    for i in range(2):
+        ctx.chamfer(hx[i % 2].numpy(), hy[i % 2].numpy(), grad_cham=hg, out=outg)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(ke):
+        ctx.chamfer(hx[i % 2].numpy(), hy[i % 2].numpy(), grad_cham=hg, out=outg)
+    e2eg_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2eg_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2eg_s = float(t.item())
+    ctx.close()
+    e2e["with_grads"] = {"value": world * B * ke / e2eg_s, "unit": "pairs/s", "ms_per_step": 1e3 * e2eg_s / ke,
+                         "h2d_bytes_per_step": 2 * B * P * 12 + B * 4, "d2h_bytes_per_step": B * 4 + 2 * B * P * 12,
+                         "note": "loss AND both (B,P,3) gradient clouds copied back to pinned host memory"}
 
-    recon = None
-    if not args.no_extra:
+    recon = policy = None
+    if not args.no_extra:  # collective measurements: every rank takes part
         try:
             recon = recon_step_measurement(torch, ptk_b200, dev, rank, world)
         except Exception as exc:  # secondary numbers must never lose the headline
             recon = {"error": repr(exc)[:300]}
+        torch.cuda.empty_cache()
+        try:
+            policy = policy_measurement(torch, ptk_b200, dev, rank, world)
+        except Exception as exc:
+            policy = {"error": repr(exc)[:300]}
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
@@ -379,16 +405,24 @@ def run_ours(args):
     sm_max_mhz = (clocks or {}).get("sm_max_mhz") or info["clock_khz"] / 1e3
     peak_tflops = 2 * 128 * info["sm_count"] * sm_max_mhz * 1e6 / 1e12   # FP32 FMA peak of the chip
     achieved = FLOP_PER_EVAL * evals / (fwd_ms * 1e-3) / 1e12
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "chamfer_scan_traffic.json")))
+        if (tj["pairs"], tj["points"]) == (B, P):
+            traffic, traffic_src = float(tj["dram_bytes_read"]) + float(tj["dram_bytes_write"]), tj["source"]
+    except Exception:
+        pass
     rescued = C.c_int64(0)
     _lib.check(L.ptk_chamfer_rescued(p(ws), B, P, P, C.byref(rescued), sp), "ptk_chamfer_rescued")
     roofline = {
         "kernel": "chamfer_nn_filter_tma_kernel<8,16,128,4,1024> (the event pair also spans chamfer_bounds_kernel, chamfer_prep_kernel, the "
                   "exact rescue pass chamfer_nn_exact2_kernel and chamfer_finalize_kernel, ~2 % together)",
         "bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this exact shape, from the committed
-        # `ncu --set full` capture profiles/r01_ncu_chamfer_filter_v4.txt (143.6 MB + 27.4 MB); the algorithmic
-        # minimum is the two clouds read once (61 MB) + their SoA copies (82 MB) + 41 MB of keys: HBM is idle here
-        "traffic": 170.997e6 if (B, P) == (256, 10000) else None, "traffic_unit": "bytes per launch (ncu)",
+        # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the scan kernel at this exact shape, read from the
+        # committed summary of an `ncu --set full` capture (profiles/chamfer_scan_traffic.json names the capture);
+        # null when that file does not cover this shape.  Algorithmic minimum: two clouds (61 MB) + their SoA copies
+        # (82 MB) + 41 MB of keys: HBM is idle in this kernel.
+        "traffic": traffic, "traffic_unit": "bytes per launch (ncu)", "traffic_source": traffic_src,
         "evals_per_s": evals / (fwd_ms * 1e-3), "ms_per_launch": fwd_ms,
         "rescued_queries_frac": rescued.value / (2.0 * B * P),
         "peak_source": f"derived, MEASURED_PEAKS.json has no FP32 entry: 2 flop x 128 FP32 lanes x {info['sm_count']} SMs x "
@@ -409,6 +443,8 @@ def run_ours(args):
              "device": torch.cuda.get_device_name(dev), "sm_count": info["sm_count"]}
     if recon is not None:
         extra["recon_step"] = recon
+    if policy is not None:
+        extra["policy_scoring"] = policy
     if not args.no_extra:
         try:
             extra.update(extra_measurements(torch, ptk_b200, dev, hbm_peak, hbm_src))
@@ -428,7 +464,7 @@ def run_ours(args):
         "metric": "chamfer_pairs_per_s_10k", "value": pairs_per_s, "unit": "pairs/s", "n_gpus": world, "steps": K,
         "warmup": W, "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "fp32", "data": "synthetic", "config": workload_config(world),
-        "clocks": clocks, "e2e": e2e, "gpu_launches": 7 * K * world,
+        "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
         "roofline": roofline, "cpu_baseline": cpu, "extra": extra,
     }
     sys.stdout.flush()
@@ -439,13 +475,31 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def recon_step_measurement(torch, ptk_b200, dev, rank, world):
-    """BASELINE configs[2]-shaped reconstruction step on EVERY rank (weak scaling, 16 objects per GPU): 3 GCN passes
-    (448 -> 300 x 18 -> 3, N = 1824/1949/1949) + 3 x 10k-point Chamfer loss + backward + Adam; for world > 1 the
-    parameter gradients go through the bucketed NCCL all-reduce that overlaps the backward (ptk_b200.dist).
-    The CNN/MLP vertex-feature encoders are out of scope: vertex features are synthetic."""
-    import types
+def _timeit_ranks(torch, fn, iters, warm, dev, world):
+    """CUDA-event time per call of fn after `warm` untimed calls; barrier first, MAX over ranks."""
     import torch.distributed as dist
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / iters
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def _recon_setup(torch, ptk_b200, dev, rank, Bs, seed=0):
+    """Config-3-shaped model + inputs for `Bs` objects on this rank (synthetic vertex features)."""
+    import types
     from ptk_b200.graph import Graph
     gold = os.path.join(ROOT, "tests", "golden")
     adj = dict(np.load(os.path.join(gold, "adjacency.npz")))
@@ -453,65 +507,69 @@ def recon_step_measurement(torch, ptk_b200, dev, rank, world):
     args = types.SimpleNamespace(use_img=True, use_touch=True, finger=True, num_grasps=5, num_GCN_layers=20,
                                  hidden_GCN_size=300, cut=0.33)
     to = lambda a, dt: torch.from_numpy(a).to(dev, dt)
+    g0 = Graph.from_csr(adj["p_origional_rowptr"], adj["p_origional_col"], dev)
     g = Graph.from_csr(adj["p_adj_rowptr"], adj["p_adj_col"], dev)
-    adj_info = {"origional": Graph.from_csr(adj["p_origional_rowptr"], adj["p_origional_col"], dev).dense(),
-                "adj": g.dense(), "faces": to(adj["p_faces"], torch.int64)}
-    torch.manual_seed(0)                                   # identical initial weights on every rank
+    adj_info = {"origional": g0.dense(), "adj": g.dense(), "faces": to(adj["p_faces"], torch.int64)}
+    ptk_b200.graph.register(adj_info["origional"], g0)   # the dense tensors the reference's callers hold are never
+    ptk_b200.graph.register(adj_info["adj"], g)          # scanned: their CSR is known (as utils.adj_init does)
+    torch.manual_seed(seed)                                   # identical initial weights on every rank
     net = ptk_b200.recon.ChartDeformer(adj_info, args, 448).to(dev)
-    Bs = 16
     gen = torch.Generator(device=dev).manual_seed(100 + rank)   # every rank owns different objects
     vision = to(meshes["vision_verts"], torch.float32)[None].repeat(Bs, 1, 1)
     touch = torch.rand(Bs, 125, 3, device=dev, generator=gen) * 0.02 + 0.2
     feats = [torch.rand(Bs, 1824, 448, device=dev, generator=gen), torch.rand(Bs, 1949, 448, device=dev, generator=gen),
              torch.rand(Bs, 1949, 448, device=dev, generator=gen)]
     gt = torch.nn.functional.normalize(torch.randn(Bs, 10000, 3, device=dev, generator=gen), dim=-1) * 0.25
-    opt = torch.optim.Adam(net.parameters(), lr=3e-4, fused=True)
-    reducer = ptk_b200.dist.GradReducer(net.parameters(), bucket_mb=4)
+    return net, adj_info, vision, touch, feats, gt
 
-    def step():
-        opt.zero_grad(set_to_none=True)
-        reducer.reset()
-        verts = net(vision, touch, lambda it, v: feats[it])
-        loss, _ = ptk_b200.recon.recon_loss(verts, adj_info["faces"], gt, number_points=10000)
-        (loss / world).backward()                          # mean over the global batch; gradients reduced with SUM
-        reducer.finish()
-        opt.step()
-        return loss
 
-    def timeit(fn, iters, warm):
-        for _ in range(warm):
-            fn()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        for _ in range(iters):
-            fn()
-        b.record()
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b) / iters
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+def recon_step_measurement(torch, ptk_b200, dev, rank, world):
+    """BASELINE configs[2]-shaped reconstruction step on EVERY rank: 3 GCN passes (448 -> 300 x 18 -> 3,
+    N = 1824/1949/1949) + 3 x 10k-point Chamfer loss + backward + Adam; for world > 1 the parameter gradients go
+    through the bucketed NCCL all-reduce that overlaps the backward (ptk_b200.dist).  Weak scaling (16 objects per
+    GPU) and, for world > 1, strong scaling at the reference's global batch of 16 (16/world objects per GPU), both
+    timed at the actual world size with the all-reduce inside.  The CNN/MLP vertex-feature encoders are out of
+    scope: vertex features are synthetic."""
+    info = ptk_b200._lib.device_info(dev.index or 0)
+    fp32_peak = 2 * 128 * info["sm_count"] * info["clock_khz"] * 1e3 / 1e12
+    flop_per_object = 3 * 2 * (1824 * (448 * 300 + 18 * 300 * 300 + 300 * 3) + 2 * 1949 * (448 * 300 + 18 * 300 * 300 + 300 * 3))
 
-    ms = timeit(step, 5, 2)
+    def measure(Bs, global_objects):
+        net, adj_info, vision, touch, feats, gt = _recon_setup(torch, ptk_b200, dev, rank, Bs)
+        opt = torch.optim.Adam(net.parameters(), lr=3e-4, fused=True)
+        reducer = ptk_b200.dist.GradReducer(net.parameters(), bucket_mb=4)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            verts = net(vision, touch, lambda it, v: feats[it])
+            _, cd = ptk_b200.recon.recon_loss(verts, adj_info["faces"], gt, number_points=10000)
+            loss = 9000.0 * cd.sum() / global_objects         # mean over the GLOBAL batch; gradients reduced with SUM
+            loss.backward()
+            reducer.finish()
+            opt.step()
+            return loss
+
+        n0 = ptk_b200._lib.launch_count()
+        step()
+        launches = ptk_b200._lib.launch_count() - n0
+        ms = _timeit_ranks(torch, step, 5, 2, dev, world)
+        return ms, launches, len(reducer.buckets), (net, adj_info, vision, touch, feats, gt)
+
+    Bs = 16
+    ms, launches, nb, state = measure(Bs, Bs * world)
     out = {"shape": "v_t_p GCN part: 16 objects per GPU, 3 x (448->300x18->3), N=1824/1949/1949, 3 x 10k-point "
                     "Chamfer loss, fwd+bwd+Adam; synthetic vertex features (CNN/MLP encoders out of scope)",
            "n_gpus": world, "ms": ms, "steps_per_s": 1e3 / ms, "objects_per_s": world * Bs * 1e3 / ms,
-           "grad_allreduce": (f"{len(reducer.buckets)} NCCL buckets overlapped with backward" if world > 1 else "none (1 GPU)")}
-    gemm_flop = 3 * 2 * Bs * (1824 * (448 * 300 + 18 * 300 * 300 + 300 * 3) + 2 * 1949 * (448 * 300 + 18 * 300 * 300 + 300 * 3))
-    out["gemm_tflops_per_gpu"] = gemm_flop / (ms * 1e-3) / 1e12
+           "ptk_launches_per_step": launches,
+           "grad_allreduce": (f"{nb} NCCL buckets overlapped with backward" if world > 1 else "none (1 GPU)")}
+    out["gemm_tflops_per_gpu"] = Bs * flop_per_object / (ms * 1e-3) / 1e12
     # north_star's yardstick for the step: algorithmic GEMM flop (SURVEY 8d: 964 GFLOP per step at 16 objects) over
     # the chip's FP32 FMA peak.  The backward GEMMs run on the tensor cores, so this is a throughput fraction, not a
     # pipe utilisation; aggregation, Chamfer and optimizer time count against it.
-    info = ptk_b200._lib.device_info(dev.index or 0)
-    fp32_peak = 2 * 128 * info["sm_count"] * info["clock_khz"] * 1e3 / 1e12
     out["fp32_peak_tflops"] = fp32_peak
     out["fp32_roofline_frac"] = out["gemm_tflops_per_gpu"] / fp32_peak
     if world == 1:
+        net, adj_info, vision, touch, feats, gt = state
         try:  # the same step replayed from one CUDA graph (launch gaps and Python overhead removed)
             opt_g = torch.optim.Adam(net.parameters(), lr=3e-4, fused=True, capturable=True)
 
@@ -524,13 +582,89 @@ def recon_step_measurement(torch, ptk_b200, dev, rank, world):
                 return loss
 
             graphed = ptk_b200.recon.GraphedStep(step_g)
-            msg = timeit(graphed, 10, 2)
+            msg = _timeit_ranks(torch, graphed, 10, 2, dev, world)
             out["ms_cuda_graph"] = msg
             out["steps_per_s_cuda_graph"] = 1e3 / msg
-            out["fp32_roofline_frac_cuda_graph"] = gemm_flop / (msg * 1e-3) / 1e12 / fp32_peak
+            out["fp32_roofline_frac_cuda_graph"] = Bs * flop_per_object / (msg * 1e-3) / 1e12 / fp32_peak
         except Exception as exc:
             out["cuda_graph_error"] = repr(exc)[:300]
+        try:  # what bit-level ReLU-mask parity costs: the same step with the tensor-core (3xTF32) training forward
+            saved = ptk_b200.ops.algo["fwd_train"]
+            ptk_b200.ops.algo["fwd_train"] = ptk_b200.ops.GEMM_TF32X3
+            opt2 = torch.optim.Adam(net.parameters(), lr=3e-4, fused=True)
+
+            def step_tc():
+                opt2.zero_grad(set_to_none=True)
+                verts = net(vision, touch, lambda it, v: feats[it])
+                loss, _ = ptk_b200.recon.recon_loss(verts, adj_info["faces"], gt, number_points=10000)
+                loss.backward()
+                opt2.step()
+                return loss
+
+            ms_tc = _timeit_ranks(torch, step_tc, 5, 2, dev, world)
+            out["tensor_core_forward"] = {
+                "ms": ms_tc, "steps_per_s": 1e3 / ms_tc, "fp32_roofline_frac": Bs * flop_per_object / (ms_tc * 1e-3) / 1e12 / fp32_peak,
+                "note": "ops.algo['fwd_train'] = GEMM_TF32X3: forward GEMMs on tcgen05 (3xTF32, error vs fp64 below "
+                        "the FP32 kernels') -- not the default because a 1e-6 perturbation flips individual ReLUs and "
+                        "the 1e-5 gradient parity against the reference's fp32 run is then lost (SURVEY H1)"}
+        except Exception as exc:
+            out["tensor_core_forward"] = {"error": repr(exc)[:300]}
+        finally:
+            ptk_b200.ops.algo["fwd_train"] = saved
+    del state
+    torch.cuda.empty_cache()
+    if world > 1 and 16 % world == 0:
+        try:
+            Bl = 16 // world
+            ms_s, launches_s, _, st = measure(Bl, 16)
+            del st
+            out["strong_scaling_global_16"] = {
+                "objects_per_gpu": Bl, "ms": ms_s, "steps_per_s": 1e3 / ms_s, "objects_per_s": 16 * 1e3 / ms_s,
+                "note": "the reference's global batch of 16 split over the ranks, NCCL gradient all-reduce inside the "
+                        "timed step, max over ranks (SURVEY 8e: kernels are latency-bound below ~8 objects per GPU)"}
+        except Exception as exc:
+            out["strong_scaling_global_16"] = {"error": repr(exc)[:300]}
+        torch.cuda.empty_cache()
     return out
+
+
+def policy_measurement(torch, ptk_b200, dev, rank, world):
+    """BASELINE configs[3] as ONE call on every rank: 32 environments x 50 candidate actions -> no-grad deformation GCN
+    (3 passes, tensor-core forward) -> 3 x (10k-point sampling + Chamfer) -> masked arg-min, the 1600 candidates
+    sharded over the ranks, one all-gather of the score vector (ptk_b200.policy.best_step_batched)."""
+    E, A = 32, 50
+    chunk = 200
+    net, adj_info, vision, touch, feats, _ = _recon_setup(torch, ptk_b200, dev, 0, chunk)  # same candidates on every rank
+    net.eval()
+    gen = torch.Generator(device=dev).manual_seed(7)
+    charts = {"vision_charts": vision[:1].repeat(E, 1, 1),
+              "touch_charts": (touch[:1, None].repeat(E, A, 1, 1) + 0.01 * torch.rand(E, A, 1, 3, device=dev, generator=gen))}
+    gtp = torch.nn.functional.normalize(torch.randn(E, 10000, 3, device=dev, generator=gen), dim=-1) * 0.25
+    maskp = (torch.rand(E, A, device=dev, generator=gen) < 0.1).to(torch.int64)
+
+    def deform(img, ch):
+        n = ch["vision_charts"].shape[0]
+        return net(ch["vision_charts"], ch["touch_charts"], lambda it, v: feats[it][:n])
+
+    def call():
+        return ptk_b200.policy.best_step_batched(deform, None, charts, gtp, adj_info["faces"], mask=maskp, num=10000,
+                                                 chunk=chunk, shard=world > 1)
+
+    n0 = ptk_b200._lib.launch_count()
+    call()
+    launches = ptk_b200._lib.launch_count() - n0
+    ms = _timeit_ranks(torch, call, 3, 1, dev, world)
+    # scoring alone (candidate meshes given), sharded the same way: what round 1 reported
+    cand = torch.cat([vision[:1], touch[:1]], 1).repeat(E * A, 1, 1).reshape(E, A, -1, 3)
+    cand = cand * (1.0 + 0.01 * torch.rand(E, A, 1, 1, device=dev, generator=gen))
+    ms_score = _timeit_ranks(torch, lambda: ptk_b200.policy.best_actions(
+        ptk_b200.policy.score_candidates(cand, adj_info["faces"], gtp, num=10000, shard=world > 1), maskp), 3, 1, dev, world)
+    return {"shape": "BASELINE configs[3]: 32 envs x 50 actions = 1600 candidates (V=1949, F=2464): deformation GCN "
+                     "(3 x 20 layers, no grad) + 3 x 10k-point samplings + Chamfer each + masked arg-min, one call",
+            "n_gpus": world, "sharded": world > 1, "ms": ms, "candidates_per_s": E * A / (ms * 1e-3),
+            "ptk_launches_per_call_per_rank": launches,
+            "scoring_only": {"ms": ms_score, "candidates_per_s": E * A / (ms_score * 1e-3),
+                             "note": "sample + Chamfer + arg-min on given candidate meshes (no GCN)"}}
 
 
 def extra_measurements(torch, ptk_b200, dev, hbm_peak, hbm_src):
@@ -584,21 +718,6 @@ def extra_measurements(torch, ptk_b200, dev, hbm_peak, hbm_src):
     ms = timeit(lambda: ptk_b200.ops.sample_points(verts, faces32, uf, uv), 20)
     out["sampler"] = {"shape": "B=16 V=1949 F=2464 S=10000", "ms": ms}
 
-    # --- config 4: greedy-policy scoring, 32 environments x 50 candidate actions in one batched pass
-    E, A = 32, 50
-    cand = torch.cat([vision, touch], 1)[:1].repeat(E * A, 1, 1).reshape(E, A, -1, 3)
-    cand = cand * (1.0 + 0.01 * torch.rand(E, A, 1, 1, device=dev))
-    gtp = torch.nn.functional.normalize(torch.randn(E, 10000, 3, device=dev), dim=-1) * 0.25
-    maskp = (torch.rand(E, A, device=dev) < 0.1).to(torch.int64)
-
-    def policy():
-        sc = ptk_b200.policy.score_candidates(cand, adj_info["faces"], gtp, num=10000)
-        return ptk_b200.policy.best_actions(sc, maskp)
-
-    ms = timeit(policy, 3, warm=1)
-    out["policy_scoring"] = {"shape": "BASELINE configs[3]: 32 envs x 50 actions = 1600 candidate meshes (V=1949, F=2464), "
-                                      "3 x 10k-point samplings + Chamfer each, masked arg-min on the device",
-                             "ms": ms, "candidates_per_s": E * A / (ms * 1e-3)}
     return out
 
 

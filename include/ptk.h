@@ -46,6 +46,10 @@ const char *ptk_last_error(void);
 /* SM count, max SM clock (kHz), L2 bytes, opt-in shared memory per block, compute capability. */
 int ptk_device_info(int device, int *sm_count, int *clock_khz, int *l2_bytes, int *smem_optin,
                     int *cc_major, int *cc_minor);
+/* Number of kernels this library has launched in the calling process so far (all threads, all streams; launches
+ * recorded into a CUDA graph count once, at capture).  No reference counterpart: it lets a harness state how many of
+ * the library's own kernels ran inside a timed region (bench.py `gpu_launches`) instead of assuming it. */
+uint64_t ptk_launch_count(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Chamfer distance / 1-NN between point clouds.

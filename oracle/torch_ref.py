@@ -23,6 +23,8 @@ def ieee_sqrt(t):
     """Correctly rounded fp32 sqrt.  torch's vectorised CPU sqrt is NOT always correctly rounded
     (measured here: 10 of 1088 face areas of test_objects/0.obj differ in the last bit from
     numpy / C sqrtf), whereas CUDA sqrtf -- what the reference executes -- is IEEE sqrt.rn.f32."""
+    if t.is_cuda:
+        return torch.sqrt(t)
     return torch.from_numpy(np.sqrt(t.detach().numpy()))
 
 
@@ -31,8 +33,8 @@ def knn1(p1, p2, chunk=512):
     """knn_points(p1, p2, K=1): squared L2, lowest index on ties.  (B,P1,3),(B,P2,3) ->
     dists (B,P1) f32, idx (B,P1) i64.  Non-FMA arithmetic ((dx^2 + dy^2) + dz^2)."""
     B, P1, _ = p1.shape
-    dists = torch.empty(B, P1, dtype=p1.dtype)
-    idx = torch.empty(B, P1, dtype=torch.int64)
+    dists = torch.empty(B, P1, dtype=p1.dtype, device=p1.device)
+    idx = torch.empty(B, P1, dtype=torch.int64, device=p1.device)
     for b in range(B):
         for s in range(0, P1, chunk):
             a = p1[b, s:s + chunk]
@@ -40,6 +42,8 @@ def knn1(p1, p2, chunk=512):
             sq = diff * diff
             d = (sq[..., 0] + sq[..., 1]) + sq[..., 2]
             m, i = d.min(dim=1)  # torch.min returns the first minimal index on CPU
+            if d.is_cuda:  # ... but any of several equal minima on CUDA: take the first one explicitly
+                i = (d == m[:, None]).to(torch.uint8).argmax(dim=1)
             dists[b, s:s + chunk] = m
             idx[b, s:s + chunk] = i
     return dists, idx
@@ -59,7 +63,7 @@ def chamfer_autograd(x, y):
         _, ix = knn1(x, y)
         _, iy = knn1(y, x)
     B = x.shape[0]
-    ar = torch.arange(B)[:, None]
+    ar = torch.arange(B, device=x.device)[:, None]
     dx = ((x - y[ar, ix]) ** 2).sum(-1)
     dy = ((y - x[ar, iy]) ** 2).sum(-1)
     return dx.sum(1) / x.shape[1] + dy.sum(1) / y.shape[1]
@@ -121,10 +125,10 @@ def batch_sample(verts, faces, u_face, uv):
     """utils.batch_sample (utils.py:152-187) with explicit uniforms; differentiable w.r.t. verts."""
     with torch.no_grad():
         areas = mesh_face_areas(verts, faces)
-        cum = face_cumweights(areas.numpy())
-        fidx = torch.from_numpy(pick_faces(cum, u_face.numpy()))
+        cum = face_cumweights(areas.cpu().numpy())
+        fidx = torch.from_numpy(pick_faces(cum, u_face.cpu().numpy())).to(verts.device)
     B = verts.shape[0]
-    ar = torch.arange(B)[:, None]
+    ar = torch.arange(B, device=verts.device)[:, None]
     tri = faces[fidx]  # (B,S,3)
     A = verts[ar, tri[..., 0]]
     Bv = verts[ar, tri[..., 1]]

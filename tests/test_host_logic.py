@@ -174,3 +174,28 @@ def test_factor_hubs_is_exact_on_the_real_graphs_and_falls_back_otherwise(golden
     col = np.concatenate(rows).astype(np.int32)
     f = factor_hubs(rowptr, col, rng.random(len(col)).astype(np.float32), n)
     assert f["common_col"] is None and len(f["hubs"]) == 2
+
+
+def test_faces_cache_never_serves_a_stale_copy_and_checks_the_id_range():
+    """a faces tensor freed and replaced by another one at the same address must not get the old
+    int32 copy; ids outside [0, V) raise like torch indexing would instead of reading out of bounds."""
+    import gc
+    from ptk_b200.utils import _faces_i32
+    g = torch.Generator().manual_seed(0)
+    for _ in range(40):
+        f = torch.randint(0, 50, (64, 3), generator=g)
+        got = _faces_i32(f, 50)
+        assert got.dtype == torch.int32 and torch.equal(got.long(), f)
+        del f, got
+        gc.collect()
+    f = torch.randint(0, 50, (64, 3), generator=g)
+    a = _faces_i32(f, 50)
+    assert _faces_i32(f, 50) is a  # same live tensor, same version: cached
+    f[0, 0] = 49  # in-place edit bumps the version
+    assert _faces_i32(f, 50)[0, 0] == 49
+    with pytest.raises(IndexError):
+        _faces_i32(f, 49)
+    with pytest.raises(IndexError):
+        _faces_i32(torch.tensor([[0, 1, -1]]), 5)
+    with pytest.raises(ValueError):
+        _faces_i32(torch.zeros(4, 2, dtype=torch.int64), 5)

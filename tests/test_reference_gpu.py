@@ -1,0 +1,174 @@
+"""The reference's OWN modules on the B200 path (north_star: "existing training, eval and policy
+scripts pick up the new path without edits").
+
+An unedited `pterotactyl` (baseline/_ref, written by tools/install_reference.py; or $PTK_REFERENCE) is imported with
+the pytorch3d shim + import stubs and run twice on the same GPU:
+
+  reference arm : its own GCN / GCN_layer / Positional_Encoder / Deformation classes, dense adjacency from its own
+                  adj_init, torch GEMMs; Chamfer loss from oracle/torch_ref.py (PyTorch3D is not installable)
+  B200 arm      : the same scripts after ptk_b200.install() -- nothing else changes
+
+S1  the reference's own `utils.batch_sample` / `utils.chamfer_distance` BODIES over the pytorch3d shim
+S2  the reference's own `Deformation` (BASELINE config 3, `v_t_p`: N=1824 'origional' graph first, touch charts
+    concatenated afterwards) forward + loss + backward, and its `Engine.train` method for three Adam steps
+INTEGRATION.md's snippets are executed verbatim by tests/test_reference_import.py (no GPU needed).
+
+Tolerances: outputs, losses 1e-5 relative (north_star).  Gradients of the 20-layer network: 1e-5 against the fp32
+reference arm OR the SURVEY-H1 criterion (error against an fp64 run of the reference <= 2x the reference's own fp32
+error): a single ReLU flipping in a 20-layer stack moves gradients by more than 1e-5 in either arm.
+"""
+import numpy as np
+import pytest
+import torch
+
+import ptk_b200
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def ref():
+    if ptk_b200.find_reference() is None:
+        pytest.skip("no pterotactyl checkout: run tools/install_reference.py (needs /root/reference) or set PTK_REFERENCE")
+    import ref_harness as H
+    H.strict_fp32()
+    r = H.Reference()
+    yield r
+    ptk_b200.uninstall()
+
+
+# ----------------------------------------------------------------------------------------------- S1
+def _packed_areas(V, F):
+    v0, v1, v2 = V[F[:, 0]], V[F[:, 1]], V[F[:, 2]]
+    a, b = v1 - v0, v2 - v0
+    cx = a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1]
+    cy = a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2]
+    cz = a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
+    return torch.sqrt((cx * cx + cy * cy) + cz * cz) * 0.5, None
+
+
+def test_s1_unedited_utils_bodies_over_the_shim(ref):
+    """utils.py:152-217 run literally (ATen multinomial and all); only the five pytorch3d names are ours."""
+    from oracle import torch_ref as tr
+    from ref_harness import rel_err
+    ptk_b200.uninstall()
+    U = ref.utils
+    assert U.batch_sample.__module__ == "pterotactyl.utility.utils"  # the reference's body, not ours
+    assert U.cuda_cd.__module__.startswith("pytorch3d")
+    verts, faces = U.load_mesh_touch(ref.chart("test_objects/0.obj"))  # shim load_obj, then .cuda() (utils.py:194-200)
+    assert verts.is_cuda and faces.dtype == torch.int64 and verts.shape == (242, 3) and faces.shape == (544, 3)
+    B, num = 3, 5000
+    scale = torch.tensor([1.0, 1.3, 0.7], device="cuda")[:, None, None]
+    v_shim = (verts[None] * scale).clone().requires_grad_(True)
+    v_rest = v_shim.detach().clone().requires_grad_(True)
+    gt = U.batch_sample(verts[None].repeat(B, 1, 1) * 1.05, faces, num=4000).detach()
+
+    torch.manual_seed(7)
+    pts_shim = U.batch_sample(v_shim, faces, num=num)
+    torch.manual_seed(11)
+    cd_shim = U.chamfer_distance(v_shim, faces, gt, num=num)
+    cd_shim.sum().backward()
+
+    saved = U.cuda_cd, U.mesh_face_areas_normals
+    try:  # the same bodies with the PyTorch3D names rebound to the eager-torch restatement
+        U.cuda_cd = lambda x, y, batch_reduction=None: (tr.chamfer_autograd(x, y), None)
+        U.mesh_face_areas_normals = _packed_areas
+        torch.manual_seed(7)
+        pts_rest = U.batch_sample(v_rest, faces, num=num)
+        torch.manual_seed(11)
+        cd_rest = U.chamfer_distance(v_rest, faces, gt, num=num)
+        cd_rest.sum().backward()
+    finally:
+        U.cuda_cd, U.mesh_face_areas_normals = saved
+    assert torch.equal(pts_shim, pts_rest), "areas from ptk_face_areas_normals changed the multinomial draw"
+    assert rel_err(cd_shim, cd_rest) < TOL
+    assert rel_err(v_shim.grad, v_rest.grad) < TOL
+
+
+# ----------------------------------------------------------------------------------------------- S2
+@pytest.fixture(scope="module")
+def c3(ref):
+    """Both arms (+ an fp64 run of the reference arm) of one config-3 step, built once."""
+    import ref_harness as H
+    args = H.c3_args()
+    batch = H.make_batch(args, B=2, seed=0)
+    out = {"args": args, "batch": batch}
+    info, mesh, net = ref.build(args, patched=False)
+    out["state"] = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    out["ref_classes"] = (type(net.mesh_deform_1).__module__, type(net.positional_encoder).__module__)
+    out["ref_adj_shapes"] = (tuple(info["origional"].shape), tuple(info["adj"].shape), tuple(info["faces"].shape))
+    out["ref"] = ref.step(args, net, info, mesh, batch, patched=False)
+    del net
+    info64, mesh64, net64 = ref.build(args, patched=False, state=out["state"], dtype=torch.float64)
+    out["ref64"] = ref.step(args, net64, info64, mesh64, batch, patched=False)
+    del net64
+    info, mesh, net = ref.build(args, patched=True, state=out["state"])
+    out["b200_classes"] = (type(net.mesh_deform_1).__module__, type(net.positional_encoder).__module__)
+    out["b200_adj_shapes"] = (tuple(info["origional"].shape), tuple(info["adj"].shape), tuple(info["faces"].shape))
+    out["b200_graphs"] = (ptk_b200.graph.graph_of(info["origional"]).n, ptk_b200.graph.graph_of(info["adj"]).n)
+    out["b200"] = ref.step(args, net, info, mesh, batch, patched=True)
+    del net
+    ptk_b200.uninstall()
+    torch.cuda.empty_cache()
+    return out
+
+
+def test_s2_install_swaps_the_classes_the_reference_builds(c3):
+    assert c3["ref_classes"] == ("pterotactyl.reconstruction.vision.model",) * 2
+    assert c3["b200_classes"] == ("ptk_b200.model", "ptk_b200.encoders")
+    # v_t_p: first deformation on the 1824-vertex 'origional' graph, then the fused 1949-vertex one; 2464 faces
+    assert c3["ref_adj_shapes"] == ((1824, 1824), (1949, 1949), (2464, 3)) == c3["b200_adj_shapes"]
+    assert c3["b200_graphs"] == (1824, 1949)
+
+
+def test_s2_reference_deformation_v_t_p_forward_and_loss(c3):
+    from ref_harness import rel_err
+    v_ref, l_ref, _ = c3["ref"]
+    v_b, l_b, _ = c3["b200"]
+    assert v_b.shape == v_ref.shape == (2, 1949, 3)
+    assert rel_err(v_b, v_ref) < TOL
+    assert rel_err(l_b, l_ref) < TOL
+    # and both sit on the fp64 run of the reference
+    assert rel_err(v_b, c3["ref64"][0]) < 2 * max(rel_err(v_ref, c3["ref64"][0]), TOL)
+
+
+def test_s2_reference_deformation_v_t_p_gradients(c3):
+    from ref_harness import grad_report
+    g_ref, g_b, g_64 = c3["ref"][2], c3["b200"][2], c3["ref64"][2]
+    assert set(g_ref) == set(g_b) == set(g_64)
+    rows, zero = grad_report(g_b, g_ref, g_64)
+    assert len(rows) > 100
+    for direct, e_b, e_r, k in rows:
+        assert direct < TOL or e_b <= 2 * max(e_r, TOL), (k, direct, e_b, e_r)
+    for n_b, n_r, k in zero:  # structurally zero gradients stay noise in both arms
+        assert n_b < 1e-5 and n_r < 1e-5, (k, n_b, n_r)
+    print("max direct grad error %.2e; max err vs fp64: b200 %.2e, reference-fp32 %.2e" % tuple(
+        max(r[i] for r in rows) for i in range(3)))
+
+
+def test_s2_reference_engine_train_three_adam_steps(ref):
+    """Engine.train (vision/train.py:120-157) itself -- zero_grad, prepare_mesh, Deformation, utils.chamfer_distance,
+    backward, Adam -- over three batches, stock vs installed."""
+    import ref_harness as H
+    args = H.c3_args(num_GCN_layers=6, hidden_GCN_size=120, number_points=2000)
+    batches = [H.make_batch(args, B=2, seed=s) for s in (1, 2, 3)]
+    info, mesh, net = ref.build(args, patched=False)
+    state0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    loss_ref, final_ref = ref.engine_train(args, net, info, mesh, batches, patched=False)
+    del net
+    info, mesh, net = ref.build(args, patched=True, state=state0)
+    loss_b, final_b = ref.engine_train(args, net, info, mesh, batches, patched=True)
+    ptk_b200.uninstall()
+    assert abs(loss_b - loss_ref) / abs(loss_ref) < 1e-4, (loss_b, loss_ref)  # mean of three steps' losses
+    # Adam's first steps move every weight by ~lr regardless of gradient size, so compare the UPDATE directions
+    # where the gradient is not noise: the parameters the steps moved the most
+    moved = 0.0
+    for k, v in final_ref.items():
+        if not v.is_floating_point() or "running" in k or "num_batches" in k:
+            continue
+        d_ref, d_b = (v - state0[k]).double(), (final_b[k] - state0[k]).double()
+        moved = max(moved, float(d_ref.abs().max()))
+        cos = float((d_ref * d_b).sum() / (d_ref.norm() * d_b.norm()).clamp_min(1e-30))
+        assert cos > 0.99, (k, cos)
+    assert moved > 1e-4
