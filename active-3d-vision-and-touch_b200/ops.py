@@ -379,13 +379,12 @@ class _GCNLayer(torch.autograd.Function):
     """One GCN_layer.forward (vision/model.py:351-363): linear + aggregate (+bias, +ReLU)."""
 
     @staticmethod
-    def forward(ctx, X, W, bias, graph, Lc, relu):
+    def forward(ctx, X, W, bias, graph, Lc, relu, train):
         _need_cuda(X, W, bias)
         X, W, bias = _f32c(X), _f32c(W), _f32c(bias)
         B, Nv, K = X.shape
         W2 = W.reshape(K, -1)
         with torch.cuda.device(X.device):
-            train = any(ctx.needs_input_grad[:3])
             H = _linear_fwd(X.reshape(B * Nv, K), W2,
                             algo_id=algo["fwd_train"] if train else algo["fwd_infer"]).reshape(B, Nv, -1)
             out = _aggregate(graph, H, Lc, bias, relu)
@@ -406,11 +405,18 @@ class _GCNLayer(torch.autograd.Function):
             gH = _aggregate(ctx.graph, gout, ctx.Lc, None, False, transpose=True).reshape(B * Nv, N)
             gW = _linear_wgrad(X.reshape(B * Nv, K), gH).reshape(ctx.wshape) if ctx.needs_input_grad[1] else None
             gX = _linear_dgrad(gH, W2, None).reshape(B, Nv, K) if ctx.needs_input_grad[0] else None
-        return gX, gW, gb, None, None, None
+        return gX, gW, gb, None, None, None, None
+
+
+def _will_backprop(*tensors):
+    """True when autograd records this call: grad mode on and something requires grad.  (Inside
+    autograd.Function.forward grad mode is always off and ctx.needs_input_grad ignores torch.no_grad(), so this is
+    decided by the caller and passed in.)"""
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in tensors)
 
 
 def gcn_layer(X, W, bias, adj, Lc, relu):
-    return _GCNLayer.apply(X, W, bias, graph_of(adj), int(Lc), bool(relu))
+    return _GCNLayer.apply(X, W, bias, graph_of(adj), int(Lc), bool(relu), _will_backprop(X, W, bias))
 
 
 class _GCNStack(torch.autograd.Function):
@@ -419,14 +425,13 @@ class _GCNStack(torch.autograd.Function):
     backward of layer l is fused into the dgrad epilogue of layer l+1 and H buffers are reused."""
 
     @staticmethod
-    def forward(ctx, X, graph, Ls, relus, *params):
+    def forward(ctx, X, graph, Ls, relus, train, *params):
         n = len(params) // 2
         Ws, bs = params[:n], params[n:]
         _need_cuda(X, *params)
         X = _f32c(X)
         B, Nv, _ = X.shape
         acts = [X]
-        train = any(ctx.needs_input_grad)
         fwd_algo = algo["fwd_train"] if train else algo["fwd_infer"]
         bits = [None] * n
         with torch.cuda.device(X.device):
@@ -448,12 +453,18 @@ class _GCNStack(torch.autograd.Function):
                         xb = torch.empty(B * Nv, (K + 31) // 32, dtype=torch.int32, device=X.device)
                     bits[l] = xb
                     acts.append(_fused_layer_fwd(graph, acts[-1].reshape(B * Nv, K), W2, Ls[l], bias, B, Nv, head, xb))
+                    if not train:
+                        acts = acts[-1:]
                     continue
                 H = Hbuf.get(N)
                 if H is None:
                     H = Hbuf[N] = torch.empty(B * Nv, N, dtype=torch.float32, device=X.device)
                 _linear_fwd(acts[-1].reshape(B * Nv, K), W2, out=H, algo_id=fwd_algo)
                 acts.append(_aggregate(graph, H.reshape(B, Nv, N), Ls[l], bias, relus[l]))
+                if not train:
+                    acts = acts[-1:]  # inference: nothing is kept for a backward, layer l-1's output is free again
+        if not train:
+            return acts[-1]
         ctx.save_for_backward(*acts, *[_f32c(w) for w in Ws])
         ctx.bits = bits  # plain int32 buffers, no autograd history
         ctx.graph, ctx.Ls, ctx.relus, ctx.n = graph, Ls, relus, n
@@ -472,7 +483,7 @@ class _GCNStack(torch.autograd.Function):
         # Layers whose output gradient has the same shape and propagated width write it into one slab (the dgrad of
         # the layer above is pointed at its slice), so their bias gradients are two batched launches at the end
         # instead of two per layer.  Costs one (M x N) matrix per such layer until the pass is over.
-        need_gb = [ctx.needs_input_grad[4 + n + l] for l in range(n)]
+        need_gb = [ctx.needs_input_grad[5 + n + l] for l in range(n)]
         widths = [Ws[l].reshape(acts[l].shape[2], -1).shape[1] for l in range(n)]
         group = []
         if batch_bias_grad and n >= 3:
@@ -494,7 +505,7 @@ class _GCNStack(torch.autograd.Function):
                 if need_gb[l] and l not in slot:
                     gbs[l] = _bias_grad(g.reshape(M, N), ctx.Ls[l])
                 gH = _aggregate(ctx.graph, g.reshape(B, Nv, N), ctx.Ls[l], None, False, transpose=True).reshape(M, N)
-                if ctx.needs_input_grad[4 + l]:
+                if ctx.needs_input_grad[5 + l]:
                     gWs[l] = _linear_wgrad(acts[l].reshape(M, K), gH).reshape(ctx.wshapes[l])
                 if l > 0 or ctx.needs_input_grad[0]:
                     mask = acts[l].reshape(M, K) if (l > 0 and ctx.relus[l - 1]) else None
@@ -507,9 +518,9 @@ class _GCNStack(torch.autograd.Function):
                 gb_all = _bias_grad_batched(slab, ctx.Ls[group[0]])
                 for l, i in slot.items():
                     gbs[l] = gb_all[i]
-        return (g, None, None, None, *gWs, *gbs)
+        return (g, None, None, None, None, *gWs, *gbs)
 
 
 def gcn_stack(X, adj, weights, biases, Ls, relus):
     return _GCNStack.apply(X, graph_of(adj), tuple(int(v) for v in Ls), tuple(bool(r) for r in relus),
-                           *weights, *biases)
+                           _will_backprop(X, *weights, *biases), *weights, *biases)

@@ -590,7 +590,7 @@ def recon_step_measurement(torch, ptk_b200, dev, rank, world):
             out["cuda_graph_error"] = repr(exc)[:300]
         try:  # what bit-level ReLU-mask parity costs: the same step with the tensor-core (3xTF32) training forward
             saved = ptk_b200.ops.algo["fwd_train"]
-            ptk_b200.ops.algo["fwd_train"] = ptk_b200.ops.GEMM_TF32X3
+            ptk_b200.ops.algo["fwd_train"] = ptk_b200.ops.GEMM_AUTO  # tcgen05 wherever the kernel accepts the shape
             opt2 = torch.optim.Adam(net.parameters(), lr=3e-4, fused=True)
 
             def step_tc():
@@ -604,7 +604,7 @@ def recon_step_measurement(torch, ptk_b200, dev, rank, world):
             ms_tc = _timeit_ranks(torch, step_tc, 5, 2, dev, world)
             out["tensor_core_forward"] = {
                 "ms": ms_tc, "steps_per_s": 1e3 / ms_tc, "fp32_roofline_frac": Bs * flop_per_object / (ms_tc * 1e-3) / 1e12 / fp32_peak,
-                "note": "ops.algo['fwd_train'] = GEMM_TF32X3: forward GEMMs on tcgen05 (3xTF32, error vs fp64 below "
+                "note": "ops.algo['fwd_train'] = GEMM_AUTO: forward GEMMs on tcgen05 (3xTF32, error vs fp64 below "
                         "the FP32 kernels') -- not the default because a 1e-6 perturbation flips individual ReLUs and "
                         "the 1e-5 gradient parity against the reference's fp32 run is then lost (SURVEY H1)"}
         except Exception as exc:

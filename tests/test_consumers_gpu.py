@@ -69,3 +69,21 @@ def test_ddqn_graph_model_vs_reference_module(golden, finger_graph):
     assert torch.equal(gm(obs, next=True), value)
     (value * torch.from_numpy(g_value).cuda()).sum().backward()
     check_params_and_grads(g, "gm", gm)
+
+
+def test_consumers_no_grad_forward_vs_reference_modules(golden, finger_graph):
+    """Evaluation mode of both consumers (DDQN acts under torch.no_grad(), ddqn.py:81-95): the GCN stack then takes the
+    tensor-core inference forward (ops.algo['fwd_infer']); same reference goldens, same 1e-5."""
+    g = golden("consumers")
+    torch.manual_seed(mk.ENC_SEED)
+    enc = ptk_b200.model.Encoder(50, types.SimpleNamespace(**mk.ENC_ARGS)).cuda()
+    feats, _, mesh, action_mask, _ = mk.inputs(1949)
+    with torch.no_grad():
+        latent = enc(torch.from_numpy(feats).cuda(), finger_graph)
+    assert rel_err(latent.cpu().numpy(), g["enc_latent"]) < TOL
+    torch.manual_seed(mk.GM_SEED)
+    gm = ptk_b200.model.Graph_Model(types.SimpleNamespace(**mk.GM_ARGS), finger_graph).cuda()
+    obs = {"mesh": torch.from_numpy(mesh), "mask": torch.from_numpy(action_mask)}
+    with torch.no_grad():
+        value = gm(obs)
+    assert rel_err(value.cpu().numpy(), g["gm_value"]) < TOL

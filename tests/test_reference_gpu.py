@@ -172,3 +172,71 @@ def test_s2_reference_engine_train_three_adam_steps(ref):
         cos = float((d_ref * d_b).sum() / (d_ref.norm() * d_b.norm()).clamp_min(1e-30))
         assert cos > 0.99, (k, cos)
     assert moved > 1e-4
+
+
+# ----------------------------------------------------------------------------------------------- config 4
+def test_best_step_batched_vs_the_references_candidate_loop(ref):
+    """BASELINE config 4 as one call.  Reference arm = the loop of ActiveTouch.best_step (environment.py:167-180)
+    written out: for each action, the STOCK Deformation under no_grad (compute_obs, :221-227), get_score =
+    loss_coeff * chamfer (restated, :252-257), `.cpu()`, then `if s < best_score[e] and mask[e][i] == 0`.
+    B200 arm = ptk_b200.policy.best_step_batched on the reference's Deformation after install() (tensor-core
+    inference forward, fused sampling + Chamfer, arg-min on the device)."""
+    import ref_harness as H
+    args = H.c3_args(use_img=False, num_GCN_layers=8, hidden_GCN_size=200, number_points=2000)
+    E, A, num = 3, 7, args.number_points
+    g = torch.Generator().manual_seed(4)
+    info, mesh, net = ref.build(args, patched=False)
+    state = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    net.eval()
+    batches = [[H.make_batch(args, B=1, seed=100 * e + a) for a in range(A)] for e in range(E)]
+    touch = torch.stack([torch.stack([batches[e][a]["touch_charts"][0] for a in range(A)]) for e in range(E)]).cuda()
+    touch = touch.view(E, A, -1, 4)                                    # (E, A, 125, 4)
+    gt = torch.stack([batches[e][0]["gt_points"][0] for e in range(E)]).cuda()
+    mask = torch.zeros(E, A)
+    mask[0, 2] = 1
+    mask[2, :] = 1                                                      # every action taken: the reference keeps None
+    uniforms = [(torch.rand(E * A, num, generator=g).cuda(), torch.rand(2, E * A, num, generator=g).cuda())
+                for _ in range(3)]
+    vision = mesh[None].repeat(E, 1, 1)
+    vmask = 3 * torch.ones(E, mesh.shape[0], 1, device="cuda")
+
+    # ---- reference loop
+    from oracle import torch_ref as tr
+    best_actions, best_score = [None] * E, [1000] * E
+    ref_scores = torch.zeros(E, A)
+    for i in range(A):
+        with torch.no_grad():
+            charts = {"touch_charts": touch[:, i, :, :3], "touch_masks": touch[:, i, :, 3:],
+                      "vision_charts": vision, "vision_masks": vmask}
+            verts, _ = net(None, charts)
+            cds = []
+            rows = torch.arange(E) * A + i
+            for uf, uv in uniforms:
+                pts, _ = tr.batch_sample(verts, info["faces"], uf[rows], uv[:, rows])
+                cds.append(tr.chamfer_distance(pts, gt)[0])
+            score = (args.loss_coeff * torch.stack(cds).mean(0)).cpu()
+        ref_scores[:, i] = score
+        for e, s in enumerate(score):
+            if s < best_score[e] and mask[e][i] == 0:
+                best_actions[e], best_score[e] = i, s
+    del net
+
+    # ---- one call on the installed path
+    info, mesh, net = ref.build(args, patched=True, state=state)
+    net.eval()
+    charts = {"touch_charts": touch[..., :3].contiguous(), "touch_masks": touch[..., 3:].contiguous(),
+              "vision_charts": vision, "vision_masks": vmask}
+    n0 = ptk_b200._lib.launch_count()
+    actions, best, scores = ptk_b200.policy.best_step_batched(net, None, charts, gt, info["faces"], mask=mask.cuda(),
+                                                              num=num, loss_coeff=args.loss_coeff, chunk=8,
+                                                              uniforms=uniforms)
+    assert ptk_b200._lib.launch_count() - n0 > 100, "the candidate pass must run libptk_b200 kernels"
+    ptk_b200.uninstall()
+    assert H.rel_err(scores, ref_scores) < 2e-5, H.rel_err(scores, ref_scores)
+    want = [-1 if a is None else a for a in best_actions]
+    assert actions.cpu().tolist() == want
+    for e in range(E):
+        if best_actions[e] is not None:
+            assert abs(float(best[e]) - float(best_score[e])) <= 2e-5 * abs(float(best_score[e]))
+        else:
+            assert float(best[e]) == 1000.0
