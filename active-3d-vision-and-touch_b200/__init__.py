@@ -84,17 +84,22 @@ def _patch(mod, name, value):
     setattr(mod, name, value)
 
 
-def install(ref_utils=None, ref_models=()):
+def install(ref_utils=None, ref_models=(), face_draw="multinomial"):
     """Seam S2: patch the reference's modules in place so its unchanged scripts use the fused path.
 
     ref_utils  : the imported `pterotactyl.utility.utils` module (imported here, through the pytorch3d shim and
                  the import stubs, if None)
     ref_models : modules holding GCN / GCN_layer copies (vision.model, autoencoder.model, DDQN.model);
                  their Positional_Encoder copies are replaced too
-    `uninstall()` puts every replaced attribute back.
+    face_draw  : how the patched batch_sample / chamfer_distance draw faces (ptk_b200.utils.face_draw).  The default
+                 "multinomial" keeps the reference's RNG stream (ATen's Tensor.multinomial does the draw, utils.py:170):
+                 with the same seed the scripts sample exactly the points they sampled before.  "uniform" is the fully
+                 fused explicit-uniform draw.
+    `uninstall()` puts every replaced attribute (and the draw mode) back.
     """
     if ref_utils is None:
         ref_utils = import_reference("utility.utils")
+    _patch(utils, "face_draw", face_draw)
     for name in ("chamfer_distance", "batch_sample", "calc_adj", "normalize_adj", "adj_fuse_touch",
                  "adj_init", "load_mesh_touch", "load_mesh_vision"):
         _patch(ref_utils, name, getattr(utils, name))

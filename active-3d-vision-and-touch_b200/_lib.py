@@ -30,6 +30,7 @@ SIGNATURES = {
     "ptk_sample_fwd": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _vp, _sz, _vp]),
     "ptk_sample_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "ptk_face_areas_normals": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp]),
+    "ptk_mesh_face_areas": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
     "ptk_gcn_aggregate": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i64, _i64, _i64, _vp, C.c_int, _vp, _vp]),
     "ptk_gcn_aggregate_ex": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp,
                                        C.c_int, _vp, _i64, _i64, _vp]),

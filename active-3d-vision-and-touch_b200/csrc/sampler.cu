@@ -104,7 +104,8 @@ sample_points_kernel(const float *__restrict__ verts, int V, const int32_t *__re
     const int tid = threadIdx.x;
     const unsigned long long *cb = cum + (size_t)b * F;
     __shared__ unsigned long long s_cum[SP_SMEM_FACES];
-    const bool in_smem = F <= SP_SMEM_FACES;
+    const bool given = u_face == nullptr;  // the caller drew the faces (face_idx is an input): interpolation only
+    const bool in_smem = !given && F <= SP_SMEM_FACES;
     if (in_smem) {
         for (int f = tid; f < F; f += SP_THREADS) s_cum[f] = cb[f];
         __syncthreads();
@@ -113,22 +114,27 @@ sample_points_kernel(const float *__restrict__ verts, int V, const int32_t *__re
     if (s >= S) return;
     const size_t o = (size_t)b * S + s;
 
-    // face pick: r = (floor(u * 2^24) * total) >> 24 ; first f with cum[f] > r
-    const float sc = __fmul_rn(u_face[o], 16777216.0f);
-    unsigned long long t = sc >= 16777215.0f ? 16777215ull : (sc > 0.0f ? (unsigned long long)sc : 0ull);
-    const unsigned long long total = in_smem ? s_cum[F - 1] : cb[F - 1];
-    // (t * total) >> 24  ==  hi64((t << 40) * total)
-    const unsigned long long r = __umul64hi(t << 40, total);
-    int lo = 0, hi = F - 1;
-    while (lo < hi) {
-        int mid = (lo + hi) >> 1;
-        unsigned long long c = in_smem ? s_cum[mid] : cb[mid];
-        if (c > r)
-            hi = mid;
-        else
-            lo = mid + 1;
+    int f;
+    if (given) {
+        f = min(max(face_idx[o], 0), F - 1);  // an out-of-range id never reads outside the face list
+    } else {
+        // face pick: r = (floor(u * 2^24) * total) >> 24 ; first f with cum[f] > r
+        const float sc = __fmul_rn(u_face[o], 16777216.0f);
+        unsigned long long t = sc >= 16777215.0f ? 16777215ull : (sc > 0.0f ? (unsigned long long)sc : 0ull);
+        const unsigned long long total = in_smem ? s_cum[F - 1] : cb[F - 1];
+        // (t * total) >> 24  ==  hi64((t << 40) * total)
+        const unsigned long long r = __umul64hi(t << 40, total);
+        int lo = 0, hi = F - 1;
+        while (lo < hi) {
+            int mid = (lo + hi) >> 1;
+            unsigned long long c = in_smem ? s_cum[mid] : cb[mid];
+            if (c > r)
+                hi = mid;
+            else
+                lo = mid + 1;
+        }
+        f = lo;
     }
-    const int f = lo;
     const float *vb = verts + (size_t)b * V * 3;
     const float *A = vb + (size_t)faces[f * 3 + 0] * 3;
     const float *Bv = vb + (size_t)faces[f * 3 + 1] * 3;
@@ -222,9 +228,32 @@ __global__ void face_areas_normals_kernel(const float *__restrict__ verts, const
     }
 }
 
+// areas (B,F) of a batch of meshes sharing one int32 face list: the quantity utils.batch_sample normalises and hands to
+// Tensor.multinomial (utils.py:163-170).  Same individually rounded arithmetic as above; NaN areas are kept (the
+// reference zeroes them itself, utils.py:165).
+__global__ void mesh_face_areas_kernel(const float *__restrict__ verts, int V, const int32_t *__restrict__ faces,
+                                       int F, float *__restrict__ areas) {
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= F) return;
+    const float *vb = verts + (size_t)blockIdx.y * V * 3;
+    const int i0 = faces[f * 3 + 0], i1 = faces[f * 3 + 1], i2 = faces[f * 3 + 2];
+    areas[(size_t)blockIdx.y * F + f] = face_area_rn(vb + (size_t)i0 * 3, vb + (size_t)i1 * 3, vb + (size_t)i2 * 3);
+}
+
 }  // namespace ptk
 
 using namespace ptk;
+
+extern "C" int ptk_mesh_face_areas(const float *verts, int64_t B, int64_t V, const int32_t *faces, int64_t F,
+                                   float *areas, ptk_stream_t stream) {
+    PTK_REQUIRE(verts && faces && areas, PTK_ERR_SHAPE, "mesh_face_areas: null pointer");
+    PTK_REQUIRE(B > 0 && V > 0 && F > 0 && B <= 65535 && F < (1 << 28) && V < (1 << 28), PTK_ERR_SHAPE,
+                "mesh_face_areas: bad sizes (B=%lld, V=%lld, F=%lld)", (long long)B, (long long)V, (long long)F);
+    mesh_face_areas_kernel<<<dim3((unsigned)ceil_div(F, 256), (unsigned)B), 256, 0, as_stream(stream)>>>(
+        verts, (int)V, faces, (int)F, areas);
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}
 
 extern "C" int ptk_face_areas_normals(const float *verts, int64_t V, const int64_t *faces, int64_t F,
                                       float *areas, float *normals, ptk_stream_t stream) {
@@ -247,19 +276,21 @@ extern "C" int ptk_sample_fwd(const float *verts, int64_t B, int64_t V, const in
                               int64_t F, const float *u_face, const float *uv, int64_t S, float *pts,
                               int32_t *face_idx, void *workspace, size_t workspace_bytes,
                               ptk_stream_t stream) {
-    PTK_REQUIRE(verts && faces && u_face && uv && pts && face_idx, PTK_ERR_SHAPE,
-                "sample_fwd: null pointer");
+    PTK_REQUIRE(verts && faces && uv && pts && face_idx, PTK_ERR_SHAPE, "sample_fwd: null pointer");
     PTK_REQUIRE(B > 0 && V > 0 && F > 0 && S > 0, PTK_ERR_SHAPE,
                 "sample_fwd: empty input (B=%lld, V=%lld, F=%lld, S=%lld)", (long long)B, (long long)V,
                 (long long)F, (long long)S);
     PTK_REQUIRE(B <= 65535 && F < (1 << 28) && V < (1 << 28), PTK_ERR_SHAPE, "sample_fwd: size out of range");
-    PTK_REQUIRE(workspace && workspace_bytes >= ptk_sample_workspace_bytes(B, F), PTK_ERR_WORKSPACE,
-                "sample_fwd: workspace too small");
     cudaStream_t st = as_stream(stream);
-    auto *cum = reinterpret_cast<unsigned long long *>(workspace);
-    auto *areas = reinterpret_cast<float *>(cum + (size_t)B * F);
-    sample_prepare_kernel<<<(unsigned)B, SP_THREADS, 0, st>>>(verts, (int)V, faces, (int)F, cum, areas);
-    PTK_CHECK_LAUNCH();
+    unsigned long long *cum = nullptr;
+    if (u_face) {  // NULL: the caller supplies face_idx (drawn by its own RNG), only the interpolation runs
+        PTK_REQUIRE(workspace && workspace_bytes >= ptk_sample_workspace_bytes(B, F), PTK_ERR_WORKSPACE,
+                    "sample_fwd: workspace too small");
+        cum = reinterpret_cast<unsigned long long *>(workspace);
+        auto *areas = reinterpret_cast<float *>(cum + (size_t)B * F);
+        sample_prepare_kernel<<<(unsigned)B, SP_THREADS, 0, st>>>(verts, (int)V, faces, (int)F, cum, areas);
+        PTK_CHECK_LAUNCH();
+    }
     dim3 grid((unsigned)ceil_div(S, SP_THREADS), (unsigned)B);
     sample_points_kernel<<<grid, SP_THREADS, 0, st>>>(verts, (int)V, faces, (int)F, cum, u_face, uv,
                                                       uv + (size_t)B * S, (int)S, pts, face_idx);

@@ -198,26 +198,36 @@ def nerf_embed(points):
 # ------------------------------------------------------------------------------------- surface sampling
 class _Sample(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, verts, faces_i32, u_face, uv):
-        _need_cuda(verts, faces_i32, u_face, uv)
-        verts, u_face, uv = _f32c(verts), _f32c(u_face), _f32c(uv)
+    def forward(ctx, verts, faces_i32, u_face, uv, given_idx):
+        _need_cuda(verts, faces_i32, u_face, uv, given_idx)
+        verts, uv = _f32c(verts), _f32c(uv)
         if verts.dim() != 3 or verts.shape[2] != 3:
             raise ValueError(f"verts must be (B,V,3), got {tuple(verts.shape)}")
         if faces_i32.dtype != torch.int32 or faces_i32.dim() != 2 or faces_i32.shape[1] != 3:
             raise ValueError("faces must be an (F,3) int32 tensor")
         B, V, _ = verts.shape
         F = faces_i32.shape[0]
-        S = u_face.shape[1]
-        if tuple(u_face.shape) != (B, S) or tuple(uv.shape) != (2, B, S):
-            raise ValueError("u_face must be (B,S) and uv (2,B,S)")
+        S = uv.shape[2] if uv.dim() == 3 else -1
+        if tuple(uv.shape) != (2, B, S):
+            raise ValueError("uv must be (2,B,S)")
         faces_i32 = faces_i32.contiguous()
         L = _lib.lib()
         pts = torch.empty(B, S, 3, dtype=torch.float32, device=verts.device)
-        fidx = torch.empty(B, S, dtype=torch.int32, device=verts.device)
-        ws = _ws(L.ptk_sample_workspace_bytes(B, F), verts.device)
+        if given_idx is None:
+            u_face = _f32c(u_face)
+            if tuple(u_face.shape) != (B, S):
+                raise ValueError("u_face must be (B,S) and uv (2,B,S)")
+            fidx = torch.empty(B, S, dtype=torch.int32, device=verts.device)
+            ws = _ws(L.ptk_sample_workspace_bytes(B, F), verts.device)
+        else:  # faces drawn by the caller: interpolation only
+            if tuple(given_idx.shape) != (B, S):
+                raise ValueError("face_idx must be (B,S)")
+            fidx = given_idx.to(torch.int32).contiguous()
+            u_face, ws = None, None
         with torch.cuda.device(verts.device):
             _lib.check(L.ptk_sample_fwd(_p(verts), B, V, _p(faces_i32), F, _p(u_face), _p(uv), S, _p(pts),
-                                        _p(fidx), _p(ws), ws.numel(), _stream()), "ptk_sample_fwd")
+                                        _p(fidx), _p(ws), ws.numel() if ws is not None else 0, _stream()),
+                       "ptk_sample_fwd")
         ctx.save_for_backward(fidx, uv, faces_i32)
         ctx.dims = (B, V, F, S)
         ctx.mark_non_differentiable(fidx)
@@ -232,12 +242,26 @@ class _Sample(torch.autograd.Function):
         with torch.cuda.device(gpts.device):
             _lib.check(_lib.lib().ptk_sample_bwd(_p(gpts), _p(fidx), _p(uv), _p(faces_i32), B, V, F, S, _p(gv),
                                                  _stream()), "ptk_sample_bwd")
-        return gv, None, None, None
+        return gv, None, None, None, None
 
 
-def sample_points(verts, faces_i32, u_face, uv):
-    """pts (B,S,3), face_idx (B,S) for explicit uniforms; differentiable w.r.t. verts."""
-    return _Sample.apply(verts, faces_i32, u_face, uv)
+def sample_points(verts, faces_i32, u_face, uv, face_idx=None):
+    """pts (B,S,3), face_idx (B,S) for explicit uniforms; differentiable w.r.t. verts.  With `face_idx` given
+    (u_face ignored) the faces are the caller's draw and only the barycentric interpolation runs."""
+    return _Sample.apply(verts, faces_i32, u_face, uv, face_idx)
+
+
+def mesh_face_areas(verts, faces_i32):
+    """(B,V,3), (F,3) int32 -> areas (B,F): utils.py:163-164 for a batch sharing one face list (no grad)."""
+    _need_cuda(verts, faces_i32)
+    verts = _f32c(verts.detach())
+    B, V, _ = verts.shape
+    F = faces_i32.shape[0]
+    out = torch.empty(B, F, dtype=torch.float32, device=verts.device)
+    with torch.cuda.device(verts.device):
+        _lib.check(_lib.lib().ptk_mesh_face_areas(_p(verts), B, V, _p(faces_i32.contiguous()), F, _p(out), _stream()),
+                   "ptk_mesh_face_areas")
+    return out
 
 
 def face_areas_normals(verts_packed, faces_i64):

@@ -54,30 +54,53 @@ def _faces_i32(faces, n_verts=None):
 
 
 def draw_uniforms(bs, num, device, generator=None):
-    """The RNG stream of one batch_sample call, in the reference's consumption order:
-    first the face draw (Tensor.multinomial, utils.py:170), then torch.rand(2, bs, num)
+    """The RNG stream of one batch_sample call in the explicit-uniform contract, in the reference's consumption
+    order: first the face draw (in place of Tensor.multinomial, utils.py:170), then torch.rand(2, bs, num)
     (_rand_barycentric_coords, utils.py:179)."""
     u_face = torch.rand(bs, num, device=device, generator=generator)
     uv = torch.rand(2, bs, num, device=device, generator=generator)
     return u_face, uv
 
 
-def batch_sample(verts, faces, num=10000, generator=None, uniforms=None):
+# How batch_sample draws the face of every sample when no explicit uniforms are passed:
+#   "uniform"      one torch.rand(bs, num) + an order-independent integer prefix sum, fused in ptk_sample_fwd.
+#                  Bit-exact for a given uniform tensor on any device / torch version; NOT the reference's stream.
+#   "multinomial"  the reference's own statements (utils.py:165-170) on areas from ptk_mesh_face_areas: ATen's
+#                  Tensor.multinomial draws the faces, so with the same seed the sampled points are bit-identical to
+#                  the reference's batch_sample.  install() selects this mode: existing scripts keep their RNG stream.
+face_draw = "uniform"
+
+
+def batch_sample(verts, faces, num=10000, generator=None, uniforms=None, face_draw=None):
     """Sample `num` area-weighted surface points per mesh.  verts (B,V,3), faces (F,3) shared by the
     batch -> (B,num,3).  Gradients flow to verts only (utils.py:152-187)."""
+    f32 = _faces_i32(faces, verts.shape[-2])
+    mode = face_draw or globals()["face_draw"]
+    if uniforms is None and mode == "multinomial":
+        with torch.no_grad():
+            Ar = ops.mesh_face_areas(verts, f32)                       # utils.py:163-164
+            Ar[Ar != Ar] = 0                                           # utils.py:165
+            Ar = torch.abs(Ar / Ar.sum(1).unsqueeze(1))                # utils.py:166
+            Ar[Ar != Ar] = 1                                           # utils.py:167
+            fidx = Ar.multinomial(num, replacement=True, generator=generator)   # utils.py:170 -- ATen draws
+        uv = torch.rand(2, verts.shape[0], num, dtype=torch.float32, device=verts.device, generator=generator)  # :179
+        pts, _ = ops.sample_points(verts, f32, None, uv, face_idx=fidx)
+        return pts
+    if mode not in ("uniform", "multinomial"):
+        raise ValueError(f"face_draw must be 'uniform' or 'multinomial', got {mode!r}")
     u_face, uv = uniforms if uniforms is not None else draw_uniforms(verts.shape[0], num, verts.device, generator)
-    pts, _ = ops.sample_points(verts, _faces_i32(faces, verts.shape[-2]), u_face, uv)
+    pts, _ = ops.sample_points(verts, f32, u_face, uv)
     return pts
 
 
-def chamfer_distance(verts, faces, gt_points, num=1000, repeat=3, generator=None, uniforms=None):
+def chamfer_distance(verts, faces, gt_points, num=1000, repeat=3, generator=None, uniforms=None, face_draw=None):
     """Chamfer distance between a predicted mesh and a ground-truth cloud: mean over `repeat`
     independent surface samplings of pytorch3d-style chamfer(pred_points, gt_points,
     batch_reduction=None).  Returns (B,) (utils.py:204-217)."""
     cds = []
     for r in range(max(int(repeat), 1)):
         uni = uniforms[r] if uniforms is not None else None
-        pred_points = batch_sample(verts, faces, num=num, generator=generator, uniforms=uni)
+        pred_points = batch_sample(verts, faces, num=num, generator=generator, uniforms=uni, face_draw=face_draw)
         cd, _, _ = ops.chamfer(pred_points, gt_points)
         cds.append(cd)
     if len(cds) == 1:

@@ -99,6 +99,9 @@ int ptk_chamfer_bwd(const float *x, const float *y, const int32_t *idx_x, const 
  *   uniform [0,1) draws (the RNG stream); pts (B,S,3); face_idx (B,S) int32 (saved for backward).
  * Face choice uses an order-independent integer prefix sum (see oracle/ptk_oracle.c) so the result
  * is bit-exact for a given uniform stream.
+ * u_face may be NULL: face_idx (B,S) is then an INPUT -- the faces were drawn by the caller (the host
+ * layer's face_draw="multinomial" mode lets ATen's own Tensor.multinomial draw them, which reproduces
+ * the reference's RNG stream) -- and only the interpolation runs; workspace is not used.
  * ---------------------------------------------------------------------------------------------- */
 size_t ptk_sample_workspace_bytes(int64_t B, int64_t F);
 int ptk_sample_fwd(const float *verts, int64_t B, int64_t V, const int32_t *faces, int64_t F,
@@ -108,6 +111,11 @@ int ptk_sample_fwd(const float *verts, int64_t B, int64_t V, const int32_t *face
 int ptk_sample_bwd(const float *grad_pts, const int32_t *face_idx, const float *uv,
                    const int32_t *faces, int64_t B, int64_t V, int64_t F, int64_t S,
                    float *grad_verts, ptk_stream_t stream);
+
+/* Face areas of a batch of meshes sharing one face list: verts (B,V,3), faces (F,3) int32 -> areas (B,F); what
+ * utils.batch_sample computes at utils.py:163-164 before normalising (NaN areas are left for the caller's guards). */
+int ptk_mesh_face_areas(const float *verts, int64_t B, int64_t V, const int32_t *faces, int64_t F, float *areas,
+                        ptk_stream_t stream);
 
 /* pytorch3d.ops.mesh_face_areas_normals(verts, faces) drop-in (utils.py:21,164): packed verts (V,3),
  * int64 faces (F,3) -> areas (F), unit normals (F,3) (normals may be NULL). */

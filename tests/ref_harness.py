@@ -3,9 +3,10 @@ located by ptk_b200.find_reference) once as the reference runs them -- dense adj
 GCN / Deformation classes, Chamfer loss from oracle/torch_ref.py -- and once with ptk_b200.install() applied, on
 the same GPU, the same seeds, the same inputs.  Used by tests/test_reference_gpu.py and tools/reference_step.py.
 
-Why the loss of the reference arm is the torch restatement and not `pytorch3d`: PyTorch3D is absent,
-and `Tensor.multinomial`'s stream cannot be reproduced by any other sampler, so both arms draw the
-explicit-uniform stream of ptk_b200.utils.draw_uniforms from the global CUDA generator, in the same order.
+The loss of the reference arm is the reference's OWN `utils.chamfer_distance` body (Tensor.multinomial, torch.rand, its
+gathers) with only the PyTorch3D names rebound to the eager-torch restatement (PyTorch3D is absent).
+install() keeps the reference's RNG stream (face_draw="multinomial"), so both arms draw the same samples from the same
+seed.
 """
 import copy
 import os
@@ -72,17 +73,35 @@ def make_batch(args, B, seed=0, n_gt=None):
     return {"img": img, "touch_charts": touch, "gt_points": gt.contiguous()}
 
 
-def restated_chamfer_distance(verts, faces, gt_points, num=1000, repeat=3):
-    """utils.chamfer_distance (utils.py:204-217) as the reference computes it, in eager torch on the same device:
-    oracle/torch_ref.batch_sample (explicit-uniform face pick) + brute-force nearest neighbours + autograd gathers.
-    Consumes the global generator exactly like ptk_b200.utils.draw_uniforms."""
-    cds = []
-    for _ in range(repeat):
-        u_face = torch.rand(verts.shape[0], num, device=verts.device)
-        uv = torch.rand(2, verts.shape[0], num, device=verts.device)
-        pts, _ = tr.batch_sample(verts, faces, u_face, uv)
-        cds.append(tr.chamfer_autograd(pts, gt_points))
-    return torch.stack(cds).mean(dim=0)
+def packed_areas(V, F):
+    """pytorch3d.ops.mesh_face_areas_normals restated in eager torch (packed verts / faces): (areas, None)."""
+    v0, v1, v2 = V[F[:, 0]], V[F[:, 1]], V[F[:, 2]]
+    a, b = v1 - v0, v2 - v0
+    cx = a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1]
+    cy = a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2]
+    cz = a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
+    return torch.sqrt((cx * cx + cy * cy) + cz * cz) * 0.5, None
+
+
+class restated_pytorch3d:
+    """Context manager: the reference's `utils` module with its PyTorch3D names rebound to the eager-torch
+    restatement (oracle/torch_ref.py) -- i.e. the reference's own `batch_sample` / `chamfer_distance` BODIES
+    (Tensor.multinomial, torch.rand, gathers: utils.py:152-217) over brute-force nearest neighbours.  This is the
+    reference arm's loss; PyTorch3D itself is not installable."""
+
+    def __init__(self, ref_utils):
+        self.U = ref_utils
+
+    def __enter__(self):
+        U = self.U
+        assert U.chamfer_distance.__module__ == "pterotactyl.utility.utils", "uninstall() first"
+        self.saved = (U.cuda_cd, U.mesh_face_areas_normals)
+        U.cuda_cd = lambda x, y, batch_reduction=None: (tr.chamfer_autograd(x, y), None)
+        U.mesh_face_areas_normals = packed_areas
+        return U
+
+    def __exit__(self, *exc):
+        self.U.cuda_cd, self.U.mesh_face_areas_normals = self.saved
 
 
 class Reference:
@@ -137,8 +156,12 @@ class Reference:
             charts = {k: v.to(dt) for k, v in charts.items()}
         verts = net(img, charts)[0]
         torch.manual_seed(seed)
-        cd_fn = self.utils.chamfer_distance if patched else restated_chamfer_distance
-        loss = cd_fn(verts, mesh_info["faces"], gt_points, num=args.number_points)
+        if patched:  # install() put ptk_b200's function there; it draws faces like the reference (multinomial)
+            assert self.utils.chamfer_distance is ptk_b200.utils.chamfer_distance
+            loss = self.utils.chamfer_distance(verts, mesh_info["faces"], gt_points, num=args.number_points)
+        else:        # the reference's own function body
+            with restated_pytorch3d(self.utils) as U:
+                loss = U.chamfer_distance(verts, mesh_info["faces"], gt_points, num=args.number_points)
         loss = args.loss_coeff * loss.mean()
         loss.backward()
         grads = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
@@ -146,20 +169,36 @@ class Reference:
 
     def engine_train(self, args, net, mesh_info, initial_mesh, batches, patched, seed=321):
         """The reference's Engine.train METHOD, unedited (vision/train.py:120-157), on a list of batches.
-        Returns (mean loss it logged, final state dict)."""
+        Returns (per-step losses, mean loss it logged, final state dict).  A float64 `net` gets float64 batches."""
         train_mod = ptk_b200.import_reference("reconstruction.vision.train")
+        dt = next(net.parameters()).dtype
+        if dt != torch.float32:
+            batches = [{k: (v.to(dt) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in b.items()}
+                       for b in batches]
         eng = train_mod.Engine.__new__(train_mod.Engine)  # __init__ makes directories and needs a config dump
         eng.args, eng.encoder, eng.mesh_info, eng.initial_mesh = args, net, mesh_info, initial_mesh
         eng.epoch, eng.best_loss = 0, 10000
         eng.optimizer = torch.optim.Adam(list(net.parameters()), lr=args.lr, weight_decay=0)
-        logged = {}
+        logged, steps = {}, []
         writer = types.SimpleNamespace(add_scalars=lambda tag, vals, epoch: logged.update({tag: dict(vals)}))
-        saved = train_mod.utils.chamfer_distance
-        if not patched:
-            train_mod.utils.chamfer_distance = restated_chamfer_distance
-        try:
-            torch.manual_seed(seed)
-            eng.train(batches, writer)
-        finally:
-            train_mod.utils.chamfer_distance = saved
-        return logged["train_loss"][args.exp_id], copy.deepcopy(net.state_dict())
+        saved = inner = train_mod.utils.chamfer_distance
+        if patched:
+            assert inner is ptk_b200.utils.chamfer_distance, "install() did not reach the trainer's utils module"
+        else:
+            assert inner.__module__ == "pterotactyl.utility.utils"
+
+        def observed(verts, faces, gt_points, num=1000, repeat=3):  # same call, the per-object distances recorded
+            cd = inner(verts, faces, gt_points, num=num, repeat=repeat)
+            steps.append(float(args.loss_coeff * cd.detach().double().mean()))
+            return cd
+
+        import contextlib
+        ctx = contextlib.nullcontext() if patched else restated_pytorch3d(train_mod.utils)
+        with ctx:
+            train_mod.utils.chamfer_distance = observed
+            try:
+                torch.manual_seed(seed)
+                eng.train(batches, writer)
+            finally:
+                train_mod.utils.chamfer_distance = saved
+        return steps, logged["train_loss"][args.exp_id], copy.deepcopy(net.state_dict())

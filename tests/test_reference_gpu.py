@@ -39,18 +39,9 @@ def ref():
 
 
 # ----------------------------------------------------------------------------------------------- S1
-def _packed_areas(V, F):
-    v0, v1, v2 = V[F[:, 0]], V[F[:, 1]], V[F[:, 2]]
-    a, b = v1 - v0, v2 - v0
-    cx = a[:, 1] * b[:, 2] - a[:, 2] * b[:, 1]
-    cy = a[:, 2] * b[:, 0] - a[:, 0] * b[:, 2]
-    cz = a[:, 0] * b[:, 1] - a[:, 1] * b[:, 0]
-    return torch.sqrt((cx * cx + cy * cy) + cz * cz) * 0.5, None
-
-
 def test_s1_unedited_utils_bodies_over_the_shim(ref):
     """utils.py:152-217 run literally (ATen multinomial and all); only the five pytorch3d names are ours."""
-    from oracle import torch_ref as tr
+    import ref_harness as H
     from ref_harness import rel_err
     ptk_b200.uninstall()
     U = ref.utils
@@ -70,20 +61,56 @@ def test_s1_unedited_utils_bodies_over_the_shim(ref):
     cd_shim = U.chamfer_distance(v_shim, faces, gt, num=num)
     cd_shim.sum().backward()
 
-    saved = U.cuda_cd, U.mesh_face_areas_normals
-    try:  # the same bodies with the PyTorch3D names rebound to the eager-torch restatement
-        U.cuda_cd = lambda x, y, batch_reduction=None: (tr.chamfer_autograd(x, y), None)
-        U.mesh_face_areas_normals = _packed_areas
+    with H.restated_pytorch3d(U):  # the same bodies with the PyTorch3D names rebound to the eager-torch restatement
         torch.manual_seed(7)
         pts_rest = U.batch_sample(v_rest, faces, num=num)
         torch.manual_seed(11)
         cd_rest = U.chamfer_distance(v_rest, faces, gt, num=num)
         cd_rest.sum().backward()
-    finally:
-        U.cuda_cd, U.mesh_face_areas_normals = saved
     assert torch.equal(pts_shim, pts_rest), "areas from ptk_face_areas_normals changed the multinomial draw"
     assert rel_err(cd_shim, cd_rest) < TOL
     assert rel_err(v_shim.grad, v_rest.grad) < TOL
+
+
+def test_batch_sample_multinomial_mode_reproduces_the_references_stream(ref):
+    """north_star: "sampled points must be bit-exact given the same RNG stream" -- with the reference's REAL stream.
+    ptk_b200.utils.batch_sample(face_draw="multinomial") (what install() selects) against the reference's own
+    `utils.batch_sample` body (utils.py:152-187: Tensor.multinomial + torch.rand from the global CUDA generator) run
+    from the same seed: identical points, bit for bit; utils.chamfer_distance likewise (three draws in a row)."""
+    import ref_harness as H
+    ptk_b200.uninstall()
+    U = ref.utils
+    args = H.c3_args()
+    info = ptk_b200.utils.load_mesh_vision(args, ref.chart())[0]
+    faces = info["faces"]                                  # the fused 2464-face list of config 3
+    g = torch.Generator().manual_seed(2)
+    B, V = 4, 1949
+    verts = (torch.randn(B, V, 3, generator=g) * 0.2).cuda()
+    verts[1, 1824:1849] = verts[1, 1824]                   # an empty touch chart: 32 zero-area faces (environment.py:308)
+    verts[2] = 0.0                                         # an all-degenerate mesh: the NaN -> 1 uniform fallback
+    gt = torch.randn(B, 3000, 3, generator=g).cuda() * 0.2
+    for seed, num in ((5, 10000), (6, 1000), (7, 30000)):
+        torch.manual_seed(seed)
+        with H.restated_pytorch3d(U):
+            want = U.batch_sample(verts, faces, num=num)
+        state_after = torch.cuda.get_rng_state()
+        torch.manual_seed(seed)
+        got = ptk_b200.utils.batch_sample(verts, faces, num=num, face_draw="multinomial")
+        assert torch.equal(got, want), (seed, num)
+        assert torch.equal(torch.cuda.get_rng_state(), state_after)   # and the generator is left where the reference leaves it
+    v1 = verts.clone().requires_grad_(True)
+    v2 = verts.clone().requires_grad_(True)
+    torch.manual_seed(9)
+    with H.restated_pytorch3d(U):
+        cd_ref = U.chamfer_distance(v1, faces, gt, num=4000)
+    cd_ref.sum().backward()
+    torch.manual_seed(9)
+    cd = ptk_b200.utils.chamfer_distance(v2, faces, gt, num=4000, face_draw="multinomial")
+    cd.sum().backward()
+    assert H.rel_err(cd, cd_ref) < TOL and H.rel_err(v2.grad, v1.grad) < TOL
+    # explicit uniforms override the mode; an unknown mode is refused
+    with pytest.raises(ValueError):
+        ptk_b200.utils.batch_sample(verts, faces, num=10, face_draw="philox")
 
 
 # ----------------------------------------------------------------------------------------------- S2
@@ -149,29 +176,46 @@ def test_s2_reference_deformation_v_t_p_gradients(c3):
 
 def test_s2_reference_engine_train_three_adam_steps(ref):
     """Engine.train (vision/train.py:120-157) itself -- zero_grad, prepare_mesh, Deformation, utils.chamfer_distance,
-    backward, Adam -- over three batches, stock vs installed."""
+    backward, Adam -- over three batches: stock fp32, stock fp64 and installed.
+
+    The first loss (no update yet) must agree to 1e-5.  From the second step on no two fp32 runs agree tightly: Adam's
+    first updates are ~lr * sign(g), so wherever a gradient component is rounding noise the step is a coin flip, and
+    the stock run is not even reproducible against itself (atomics in grid_sample's backward): measured here, the
+    STOCK fp32 run is 0.1-0.6 % away from its own fp64 run at steps 2-3 and moves by as much between two launches.
+    The installed path must stay within 4x the stock run's distance from fp64 or 2 %, whichever is larger, step by step;
+    final weights within 4x the stock run's distance + a tenth of the Adam step budget."""
     import ref_harness as H
     args = H.c3_args(num_GCN_layers=6, hidden_GCN_size=120, number_points=2000)
     batches = [H.make_batch(args, B=2, seed=s) for s in (1, 2, 3)]
     info, mesh, net = ref.build(args, patched=False)
     state0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    loss_ref, final_ref = ref.engine_train(args, net, info, mesh, batches, patched=False)
+    steps_ref, mean_ref, final_ref = ref.engine_train(args, net, info, mesh, batches, patched=False)
     del net
+    info64, mesh64, net64 = ref.build(args, patched=False, state=state0, dtype=torch.float64)
+    steps_64, _, final_64 = ref.engine_train(args, net64, info64, mesh64, batches, patched=False)
+    del net64
     info, mesh, net = ref.build(args, patched=True, state=state0)
-    loss_b, final_b = ref.engine_train(args, net, info, mesh, batches, patched=True)
+    steps_b, mean_b, final_b = ref.engine_train(args, net, info, mesh, batches, patched=True)
     ptk_b200.uninstall()
-    assert abs(loss_b - loss_ref) / abs(loss_ref) < 1e-4, (loss_b, loss_ref)  # mean of three steps' losses
-    # Adam's first steps move every weight by ~lr regardless of gradient size, so compare the UPDATE directions
-    # where the gradient is not noise: the parameters the steps moved the most
-    moved = 0.0
-    for k, v in final_ref.items():
-        if not v.is_floating_point() or "running" in k or "num_batches" in k:
+    assert len(steps_ref) == len(steps_b) == len(steps_64) == 3
+    assert abs(steps_b[0] - steps_ref[0]) < TOL * abs(steps_ref[0]), (steps_b, steps_ref)
+    assert abs(mean_b - sum(steps_b) / 3) < 1e-4 * abs(mean_b)  # what Engine.train logged is what we observed
+    for s_b, s_r, s_64 in zip(steps_b, steps_ref, steps_64):
+        assert abs(s_b - s_64) <= max(4 * abs(s_r - s_64), 2e-2 * abs(s_64)), (steps_b, steps_ref, steps_64)
+    lr_steps = args.lr * 3
+    checked = 0
+    for k, v64 in final_64.items():
+        if not v64.is_floating_point() or "running" in k or "num_batches" in k:
             continue
-        d_ref, d_b = (v - state0[k]).double(), (final_b[k] - state0[k]).double()
-        moved = max(moved, float(d_ref.abs().max()))
-        cos = float((d_ref * d_b).sum() / (d_ref.norm() * d_b.norm()).clamp_min(1e-30))
-        assert cos > 0.99, (k, cos)
-    assert moved > 1e-4
+        d64 = v64 - state0[k].double()
+        if float(d64.abs().max()) < 0.1 * lr_steps:
+            continue  # structurally zero gradient (conv bias before BatchNorm): pure noise in any fp32 run
+        e_b = float((final_b[k].double() - v64).abs().max())
+        e_r = float((final_ref[k].double() - v64).abs().max())
+        assert e_b <= 4 * e_r + 0.1 * lr_steps, (k, e_b, e_r)
+        checked += 1
+    assert checked > 50
+    print("Engine.train losses  b200 %s\n                     ref  %s\n                     fp64 %s" % (steps_b, steps_ref, steps_64))
 
 
 # ----------------------------------------------------------------------------------------------- config 4

@@ -69,19 +69,27 @@ def main():
     batches = [H.make_batch(args2, B=2, seed=s) for s in (1, 2, 3)]
     info, mesh, net = ref.build(args2, patched=False)
     state0 = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    loss_ref, final_ref = ref.engine_train(args2, net, info, mesh, batches, patched=False)
+    steps_ref, _, final_ref = ref.engine_train(args2, net, info, mesh, batches, patched=False)
+    info64, mesh64, net64 = ref.build(args2, patched=False, state=state0, dtype=torch.float64)
+    steps_64, _, final_64 = ref.engine_train(args2, net64, info64, mesh64, batches, patched=False)
     info, mesh, net = ref.build(args2, patched=True, state=state0)
-    loss_b, final_b = ref.engine_train(args2, net, info, mesh, batches, patched=True)
-    print(f"Engine.train mean loss: reference {loss_ref:.6f} b200 {loss_b:.6f} rel {abs(loss_b - loss_ref) / abs(loss_ref):.2e}")
-    cos_min = 1.0
-    for k, v in final_ref.items():
-        if not v.is_floating_point() or "running" in k or "num_batches" in k:
+    steps_b, _, final_b = ref.engine_train(args2, net, info, mesh, batches, patched=True)
+    print("Engine.train losses per step\n  b200", steps_b, "\n  ref ", steps_ref, "\n  fp64", steps_64)
+    worst = []
+    lr_steps = args2.lr * 3
+    for k, v64 in final_64.items():
+        if not v64.is_floating_point() or "running" in k or "num_batches" in k:
             continue
-        d_ref, d_b = (v - state0[k]).double(), (final_b[k] - state0[k]).double()
-        cos = float((d_ref * d_b).sum() / (d_ref.norm() * d_b.norm()).clamp_min(1e-30))
-        if cos < cos_min:
-            cos_min, worst_k = cos, k
-    print(f"Engine.train update cosine, worst parameter: {cos_min:.6f} ({worst_k})")
+        d64 = v64 - state0[k].double()
+        if float(d64.abs().max()) < 0.1 * lr_steps:
+            continue
+        e_b = float((final_b[k].double() - v64).abs().max())
+        e_r = float((final_ref[k].double() - v64).abs().max())
+        worst.append((e_b / max(e_r, 1e-30), e_b, e_r, k))
+    worst.sort(reverse=True)
+    print("final weights: |b200 - fp64| / |ref - fp64|, worst 8 of", len(worst))
+    for w in worst[:8]:
+        print("   %.2f  %.2e %.2e  %s" % w)
 
 
 if __name__ == "__main__":
