@@ -13,6 +13,14 @@ PTK_OK, PTK_ERR_SHAPE, PTK_ERR_ALIGN, PTK_ERR_ARCH, PTK_ERR_CUDA, PTK_ERR_WORKSP
 
 _vp, _i64, _i32, _sz = C.c_void_p, C.c_int64, C.c_int32, C.c_size_t
 
+
+class GcnCsr(C.Structure):
+    """ptk_gcn_csr of include/ptk.h: one direction of the adjacency, plain CSR + kernel form."""
+    _fields_ = [("rowptr", _vp), ("col", _vp), ("val", _vp), ("hubs", _vp), ("n_hubs", _i32),
+                ("k_rowptr", _vp), ("k_col", _vp), ("k_val", _vp), ("k_hubs", _vp), ("k_n_hubs", _i32),
+                ("common_col", _vp), ("common_w", _vp), ("n_common", _i32), ("alpha", _vp), ("row_skip", _vp)]
+
+
 # name -> (restype, argtypes); mirrors include/ptk.h one to one (tests check the two stay in sync)
 SIGNATURES = {
     "ptk_version": (C.c_int, []),
@@ -45,6 +53,12 @@ SIGNATURES = {
     "ptk_gcn_linear_dgrad": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, C.c_int, _vp, _sz, _vp]),
     "ptk_gcn_linear_wgrad_workspace_bytes": (_sz, [_i64, _i64, _i64]),
     "ptk_gcn_linear_wgrad": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, C.c_int, _vp, _sz, _vp]),
+    "ptk_gcn_stack_fwd_workspace_bytes": (_sz, [_i64, _i64, _i32, _vp, _vp]),
+    "ptk_gcn_stack_fwd": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.c_int,
+                                    _vp, _sz, _vp]),
+    "ptk_gcn_stack_bwd_workspace_bytes": (_sz, [_i64, _i64, _i32, _vp, _vp, _vp, C.c_int]),
+    "ptk_gcn_stack_bwd": (C.c_int, [_vp, _i64, _i64, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                    C.c_int, C.c_int, C.c_int, _vp, _sz, _vp]),
     "ptk_vertex_maxpool_fwd": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "ptk_vertex_maxpool_bwd": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _vp, _vp]),
     "ptk_adj_workspace_bytes": (_sz, [_i64]),

@@ -111,6 +111,25 @@ class Graph:
         self.fwd_k = KernelCSR(factor_hubs(rowptr, col, val, self.n), self.device)
         self.bwd_k = KernelCSR(factor_hubs(rowptr_t, col_t, val_t, self.n), self.device)
 
+    def csr_struct(self, transpose=False):
+        """ctypes ptk_gcn_csr (include/ptk.h) of A^ or its transpose, built once; the device arrays it points at are
+        owned by this Graph."""
+        import ctypes as C
+
+        from . import _lib
+        cache = self.__dict__.setdefault("_csr_structs", {})
+        hit = cache.get(bool(transpose))
+        if hit is None:
+            if transpose:
+                rp, col, val, hubs, nh, k = self.rowptr_t, self.col_t, self.val_t, self.hubs_t, self.n_hubs_t, self.bwd_k
+            else:
+                rp, col, val, hubs, nh, k = self.rowptr, self.col, self.val, self.hubs, self.n_hubs, self.fwd_k
+            ptr = lambda t: None if t is None else t.data_ptr()
+            hit = cache[bool(transpose)] = _lib.GcnCsr(
+                ptr(rp), ptr(col), ptr(val), ptr(hubs), nh, ptr(k.rowptr), ptr(k.col), ptr(k.val), ptr(k.hubs), k.n_hubs,
+                ptr(k.common_col), ptr(k.common_w), k.n_common, ptr(k.alpha), ptr(k.row_skip))
+        return hit
+
     @staticmethod
     def from_dense(adj):
         a = adj.detach().to("cpu", torch.float32).numpy()

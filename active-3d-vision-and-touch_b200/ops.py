@@ -443,6 +443,112 @@ def gcn_layer(X, W, bias, adj, Lc, relu):
     return _GCNLayer.apply(X, W, bias, graph_of(adj), int(Lc), bool(relu), _will_backprop(X, W, bias))
 
 
+native_stack = True  # GCN stacks run through ptk_gcn_stack_fwd/bwd (one C-ABI call per pass); tests flip this
+
+
+def _ptr_array(tensors):
+    arr = (C.c_void_p * len(tensors))()
+    for i, t in enumerate(tensors):
+        arr[i] = None if t is None else t.data_ptr()
+    return arr
+
+
+class _GCNStackNative(torch.autograd.Function):
+    """The whole GCN.forward (vision/model.py:316-331) and its backward, one ptk_gcn_stack_fwd / ptk_gcn_stack_bwd call
+    each: the layer loop, buffer reuse, fused layer forward, packed ReLU masks and batched bias gradients of
+    _GCNStack below, walked in native code (csrc/gcn_stack.cu) -- identical kernels and results, no Python frame
+    between two launches."""
+
+    @staticmethod
+    def forward(ctx, X, graph, Ls, relus, train, *params):
+        n = len(params) // 2
+        _need_cuda(X, *params)
+        X = _f32c(X)
+        B, Nv, K0 = X.shape
+        if Nv != graph.n:
+            raise ValueError(f"features have {Nv} vertices but the adjacency has {graph.n}")
+        Ws = [_f32c(w) for w in params[:n]]
+        bs = [_f32c(b) for b in params[n:]]
+        widths = [K0] + [w.shape[-1] for w in Ws]
+        for l, w in enumerate(Ws):
+            if w.numel() != widths[l] * widths[l + 1]:
+                raise ValueError(f"layer {l}: weight {tuple(w.shape)} does not map {widths[l]} -> {widths[l + 1]} channels")
+        M = B * Nv
+        dev = X.device
+        fwd_algo = algo["fwd_train"] if train else algo["fwd_infer"]
+        c_widths = (C.c_int64 * (n + 1))(*widths)
+        c_Ls = (C.c_int32 * n)(*Ls)
+        c_relus = (C.c_uint8 * n)(*[1 if r else 0 for r in relus])
+        L = _lib.lib()
+        if train:
+            acts = [torch.empty(B, Nv, widths[l + 1], dtype=torch.float32, device=dev) for l in range(n)]
+            bits = [None] * n
+            for l in range(1, n):  # the fused forward of layer l packs the ReLU mask of its input for its own dgrad
+                if fuse_layers and fwd_algo == GEMM_FFMA and relus[l - 1] and widths[l] <= 512 and \
+                        _fused_layer_ok(widths[l], widths[l + 1], Ls[l], relus[l]):
+                    bits[l] = torch.empty(M, (widths[l] + 31) // 32, dtype=torch.int32, device=dev)
+        else:  # inference: two alternating buffers, nothing kept
+            wmax = max(widths[1:])
+            pool = [torch.empty(M * wmax, dtype=torch.float32, device=dev) for _ in range(min(2, n - 1))]
+            acts = [pool[l % 2][:M * widths[l + 1]].view(B, Nv, widths[l + 1]) for l in range(n - 1)]
+            acts.append(torch.empty(B, Nv, widths[n], dtype=torch.float32, device=dev))  # the result owns its memory
+            bits = [None] * n
+        ws = _ws(L.ptk_gcn_stack_fwd_workspace_bytes(B, Nv, n, c_widths, c_Ls), dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.ptk_gcn_stack_fwd(C.byref(graph.csr_struct(False)), B, Nv, n, c_widths, c_Ls, c_relus, _p(X),
+                                           _ptr_array(Ws), _ptr_array(bs), _ptr_array(acts), _ptr_array(bits), fwd_algo,
+                                           int(fuse_layers), _p(ws), ws.numel(), _stream()), "ptk_gcn_stack_fwd")
+        out = acts[-1]
+        if not train:
+            return out
+        ctx.save_for_backward(X, *acts, *Ws)
+        ctx.bits = bits
+        ctx.graph, ctx.Ls, ctx.relus, ctx.n, ctx.widths = graph, Ls, relus, n, widths
+        ctx.wshapes = [w.shape for w in params[:n]]
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        n, widths = ctx.n, ctx.widths
+        saved = ctx.saved_tensors
+        X, acts, Ws = saved[0], saved[1:n + 1], saved[n + 1:]
+        B, Nv, _ = X.shape
+        dev = X.device
+        gout = _f32c(gout)
+        need_gX = ctx.needs_input_grad[0]
+        need_gW = [ctx.needs_input_grad[5 + l] for l in range(n)]
+        need_gb = [ctx.needs_input_grad[5 + n + l] for l in range(n)]
+        gX = torch.empty_like(X) if need_gX else None
+        gWs = [torch.empty(widths[l], widths[l + 1], dtype=torch.float32, device=dev) if need_gW[l] else None
+               for l in range(n)]
+        # bias gradients of the layers that share the hidden width: consecutive rows of one matrix (batched launch)
+        gbs = [None] * n
+        group = []
+        if batch_bias_grad and n >= 3:
+            ref = (widths[n - 1], ctx.Ls[n - 2])
+            group = [l for l in range(n - 1) if need_gb[l] and (widths[l + 1], ctx.Ls[l]) == ref]
+        if len(group) >= 2:
+            gb_all = torch.empty(len(group), widths[n - 1], dtype=torch.float32, device=dev)
+            for i, l in enumerate(group):
+                gbs[l] = gb_all[i]
+        for l in range(n):
+            if need_gb[l] and gbs[l] is None:
+                gbs[l] = torch.empty(widths[l + 1], dtype=torch.float32, device=dev)
+        c_widths = (C.c_int64 * (n + 1))(*widths)
+        c_Ls = (C.c_int32 * n)(*ctx.Ls)
+        c_relus = (C.c_uint8 * n)(*[1 if r else 0 for r in ctx.relus])
+        c_need = (C.c_uint8 * n)(*[1 if v else 0 for v in need_gb])
+        L = _lib.lib()
+        ws = _ws(L.ptk_gcn_stack_bwd_workspace_bytes(B, Nv, n, c_widths, c_Ls, c_need, int(batch_bias_grad)), dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.ptk_gcn_stack_bwd(C.byref(ctx.graph.csr_struct(True)), B, Nv, n, c_widths, c_Ls, c_relus, _p(X),
+                                           _ptr_array(Ws), _ptr_array(acts), _ptr_array(ctx.bits), _p(gout), _p(gX),
+                                           _ptr_array(gWs), _ptr_array(gbs), c_need, int(batch_bias_grad), algo["dgrad"],
+                                           algo["wgrad"], _p(ws), ws.numel(), _stream()), "ptk_gcn_stack_bwd")
+        gWs = [g.reshape(ctx.wshapes[l]) if g is not None else None for l, g in enumerate(gWs)]
+        return (gX, None, None, None, None, *gWs, *gbs)
+
+
 class _GCNStack(torch.autograd.Function):
     """The whole GCN.forward (vision/model.py:316-331): n layers, ReLU on all but the last, the first
     n-1 layers 'cut' (only the first L channels are propagated).  One autograd node so that the ReLU
@@ -546,5 +652,6 @@ class _GCNStack(torch.autograd.Function):
 
 
 def gcn_stack(X, adj, weights, biases, Ls, relus):
-    return _GCNStack.apply(X, graph_of(adj), tuple(int(v) for v in Ls), tuple(bool(r) for r in relus),
-                           _will_backprop(X, *weights, *biases), *weights, *biases)
+    fn = _GCNStackNative if native_stack else _GCNStack
+    return fn.apply(X, graph_of(adj), tuple(int(v) for v in Ls), tuple(bool(r) for r in relus),
+                    _will_backprop(X, *weights, *biases), *weights, *biases)

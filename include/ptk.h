@@ -211,6 +211,49 @@ int ptk_gcn_linear_wgrad(const float *X, const float *gH, int64_t M, int64_t K, 
                          int algo, void *workspace, size_t workspace_bytes, ptk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * A whole GCN.forward / its backward in ONE call (pterotactyl/reconstruction/vision/model.py:316-331; the copies in
+ * autoencoder/model.py:85-92 and policies/DDQN/model.py:122-127).  Walks the layers in native code with exactly the
+ * kernels, order and results of the per-layer entry points above -- what changes is that no host-language frame sits
+ * between two launches (the per-layer kernels are 5-135 us at the training batch).
+ *
+ * ptk_gcn_csr: one direction of the adjacency (A^ for the forward, its transpose for the backward) in both forms the
+ * aggregation takes: the plain CSR + hub list (ptk_gcn_aggregate) and the kernel form with the hub rows' common
+ * neighbour set split off (ptk_gcn_aggregate_ex; n_common == 0: absent, k_* may then equal the plain arrays).
+ *
+ * Layer l maps width[l] -> width[l+1] channels, propagates its first Ls[l] output channels through the adjacency and
+ * applies ReLU iff relus[l].  W[l] (width[l] x width[l+1]) row-major, bias[l] (width[l+1]); acts[l] (B,Nv,width[l+1])
+ * receives the output of layer l (in inference the caller may alternate two buffers).  x_bits (array of n_layers
+ * pointers, entries or the array itself may be NULL): x_bits[l] (B*Nv x ceil(width[l]/32) words) receives the packed
+ * ReLU mask of layer l's INPUT as a by-product of the fused forward, for this layer's dgrad.  algo: PTK_GEMM_* of the
+ * forward GEMMs; fuse != 0 enables the split-epilogue GEMM + strided aggregate for 'cut' ReLU layers (FFMA only).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct ptk_gcn_csr {
+    const int32_t *rowptr, *col; const float *val; const int32_t *hubs; int32_t n_hubs;
+    const int32_t *k_rowptr, *k_col; const float *k_val; const int32_t *k_hubs; int32_t k_n_hubs;
+    const int32_t *common_col; const float *common_w; int32_t n_common; const float *alpha; const uint8_t *row_skip;
+} ptk_gcn_csr;
+
+size_t ptk_gcn_stack_fwd_workspace_bytes(int64_t B, int64_t Nv, int32_t n_layers, const int64_t *widths,
+                                         const int32_t *Ls);
+int ptk_gcn_stack_fwd(const ptk_gcn_csr *graph, int64_t B, int64_t Nv, int32_t n_layers, const int64_t *widths,
+                      const int32_t *Ls, const uint8_t *relus, const float *X, const float *const *W,
+                      const float *const *bias, float *const *acts, uint32_t *const *x_bits, int algo, int fuse,
+                      void *workspace, size_t workspace_bytes, ptk_stream_t stream);
+/* Backward of the same stack.  graph_t: the TRANSPOSED adjacency.  X, W, acts, x_bits as in the forward; gout
+ * (B,Nv,width[n]) the gradient of the last output.  Outputs: gX (B,Nv,width[0]) or NULL; gW[l] (width[l] x width[l+1])
+ * or NULL per layer; gb[l] (width[l+1]) where need_gb[l] != 0.  batch_bias != 0: the layers that share the hidden
+ * width keep their output gradients in one slab and their bias gradients are two launches in total -- this needs
+ * their gb[] pointers to be consecutive rows of one (count x width) matrix, otherwise it falls back to per-layer
+ * bias gradients.  algo_dgrad / algo_wgrad: PTK_GEMM_*. */
+size_t ptk_gcn_stack_bwd_workspace_bytes(int64_t B, int64_t Nv, int32_t n_layers, const int64_t *widths,
+                                         const int32_t *Ls, const uint8_t *need_gb, int batch_bias);
+int ptk_gcn_stack_bwd(const ptk_gcn_csr *graph_t, int64_t B, int64_t Nv, int32_t n_layers, const int64_t *widths,
+                      const int32_t *Ls, const uint8_t *relus, const float *X, const float *const *W,
+                      const float *const *acts, const uint32_t *const *x_bits, const float *gout, float *gX,
+                      float *const *gW, float *const *gb, const uint8_t *need_gb, int batch_bias, int algo_dgrad,
+                      int algo_wgrad, void *workspace, size_t workspace_bytes, ptk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Max over the vertices: (B,Nv,C) -> out (B,C) and arg (B,C) int32 (may be NULL), lowest vertex id on
  * ties, NaN propagates.  Replaces `features.max(dim=1)[0]` after the GCN encoder of the autoencoder
  * (pterotactyl/reconstruction/autoencoder/model.py:91) and `torch.max(x, dim=1)[0]` of the DDQN

@@ -384,3 +384,40 @@ def test_tensor_core_training_forward_flips_relus_which_is_why_it_is_not_the_def
     assert rep["gw19"][0] < 1e-2 and rep["gw0"][0] < 1e-2
     if e_ours <= 2.0 * max(e_ref, 1e-6):
         pytest.skip("no ReLU flipped on this build: the tensor-core forward met H1 on the gradients as well")
+
+
+@pytest.mark.parametrize("hidden,cin,layers,tag", [(300, 448, 20, "p"), (100, 50, 5, "g"), (64, 52, 3, "p"), (40, 16, 1, "p")])
+def test_native_stack_runner_is_bit_identical_to_the_per_layer_calls(golden, hidden, cin, layers, tag):
+    """ptk_gcn_stack_fwd / ptk_gcn_stack_bwd (one C-ABI call per pass, csrc/gcn_stack.cu) against the same layer loop
+    driven from Python through the per-layer entry points: outputs, input gradient and every parameter gradient equal
+    bit for bit, in training and in inference (tensor-core forward), with and without the fused layer forward."""
+    adj = golden("adjacency")
+    info = {"adj": Graph.from_csr(adj[f"{tag}_adj_rowptr"], adj[f"{tag}_adj_col"], "cuda").dense()}
+    args = types.SimpleNamespace(num_GCN_layers=layers, hidden_GCN_size=hidden, cut=0.33)
+    torch.manual_seed(hidden + layers)
+    net = ptk_b200.GCN(cin, args).cuda()
+    n = info["adj"].shape[0]
+    x = torch.rand(2, n, cin, device="cuda")
+    gout = torch.rand(2, n, 3, device="cuda")
+    res = {}
+    try:
+        for native in (True, False):
+            for fused in (True, False):
+                ptk_b200.ops.native_stack, ptk_b200.ops.fuse_layers = native, fused
+                xi = x.clone().requires_grad_(True)
+                net.zero_grad(set_to_none=True)
+                n0 = ptk_b200._lib.launch_count()
+                y = net(xi, info)
+                (y * gout).sum().backward()
+                launches = ptk_b200._lib.launch_count() - n0
+                with torch.no_grad():
+                    yi = net(x, info)
+                res[(native, fused)] = ([y.detach().clone(), xi.grad.clone(), yi.clone()] +
+                                        [p.grad.clone() for p in net.parameters()], launches)
+    finally:
+        ptk_b200.ops.native_stack, ptk_b200.ops.fuse_layers = True, True
+    for fused in (True, False):
+        (a, la), (b, lb) = res[(True, fused)], res[(False, fused)]
+        assert la == lb, "the native runner must launch exactly the kernels the Python loop launches"
+        for u, v in zip(a, b):
+            assert torch.equal(u, v)
