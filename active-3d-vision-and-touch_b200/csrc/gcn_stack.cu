@@ -7,9 +7,47 @@
 // entry points (tests/test_gcn_gpu.py checks bit equality), no Python between launches.
 #include "ptk_common.cuh"
 
+namespace ptk {
+// tensor-core GEMMs (gemm_tf32x3.cu)
+bool tf32x3_eligible(const void *A, const void *D, int64_t M, int64_t K, int64_t N);
+int gemm_tf32x3_presplit(const float *A, const float *b_hi, const float *b_lo, const float *act, const uint32_t *act_bits,
+                         int64_t M, int64_t K, int64_t N, float *D, uint32_t *mask_ws, float *part, int *flags,
+                         cudaStream_t st);
+size_t tf32x3_part_floats();
+int tf32x3_max_ctas();
+int tf32x3_presplit_batched(int n, const float *const *src, const int *rows, const int *cols, int transpose,
+                            float *const *hi, float *const *lo, int *flags, int n_flags, cudaStream_t st);
+bool wgrad_tf32x3_eligible(const void *X, const void *gH, int64_t M, int64_t Kin, int64_t Nout);
+size_t wgrad_tf32x3_workspace_bytes(int64_t M, int64_t Kin, int64_t Nout);
+int wgrad_tf32x3(const float *X, const float *gH, int64_t M, int64_t Kin, int64_t Nout, void *workspace,
+                 size_t workspace_bytes, float **part_out, int *n_splits, cudaStream_t st);
+
+// second stage of the split-M weight gradients of a whole pass in one launch: out[l][e] = sum_s part[l][s, e] in
+// ascending s -- the summation order of splitk_reduce_kernel (gcn_linear.cu), so the results are bit-identical
+constexpr int RB_MAX = 32;
+struct ReduceBatch {
+    const float *part[RB_MAX];
+    float *out[RB_MAX];
+    int ns[RB_MAX];
+    long long elems[RB_MAX];
+};
+__global__ void splitk_reduce_batched_kernel(const __grid_constant__ ReduceBatch b) {
+    const int l = blockIdx.y;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long elems = b.elems[l];
+    if (e >= elems) return;
+    const float *p = b.part[l];
+    float acc = 0.f;
+    for (int s = 0; s < b.ns[l]; ++s) acc += p[(size_t)s * elems + e];
+    b.out[l][e] = acc;
+}
+}  // namespace ptk
+
 using namespace ptk;
 
 namespace {
+
+constexpr int MAX_LAYERS = 4096;
 
 inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
 
@@ -34,10 +72,18 @@ inline bool fused_layer_ok(int64_t K, int64_t N, int64_t Lc, int relu) {
 }
 
 struct FwdPlan {
-    size_t head_off, h_off, lin_off, total;
+    size_t head_off, h_off, lin_off, split_off, flags_off, part_off, total;
+    size_t lin_bytes;
 };
 
-FwdPlan plan_fwd(int64_t M, int32_t n, const int64_t *widths, const int32_t *Ls) {
+// bytes of the pre-split (hi, lo) weights of every layer, laid out back to back
+size_t split_bytes(int32_t n, const int64_t *widths) {
+    size_t b = 0;
+    for (int l = 0; l < n; ++l) b += align_up(2 * sizeof(float) * (size_t)widths[l] * (size_t)widths[l + 1]);
+    return b;
+}
+
+FwdPlan plan_fwd(int64_t M, int32_t n, const int64_t *widths, const int32_t *Ls, int algo) {
     int64_t max_lp = 4, max_n = 1;
     size_t lin = 0;
     for (int l = 0; l < n; ++l) {
@@ -51,12 +97,17 @@ FwdPlan plan_fwd(int64_t M, int32_t n, const int64_t *widths, const int32_t *Ls)
     p.head_off = 0;
     p.h_off = align_up(sizeof(float) * (size_t)M * (size_t)max_lp);
     p.lin_off = p.h_off + align_up(sizeof(float) * (size_t)M * (size_t)max_n);
-    p.total = p.lin_off + align_up(lin) + 256;
+    p.lin_bytes = align_up(lin);
+    p.split_off = p.lin_off + p.lin_bytes;
+    const bool tc = algo != PTK_GEMM_FFMA;  // tensor-core layers take their weights pre-split, in one launch
+    p.flags_off = p.split_off + (tc ? split_bytes(n, widths) : 0);
+    p.part_off = p.flags_off + (tc ? align_up(sizeof(int) * (size_t)n * (size_t)tf32x3_max_ctas()) : 0);
+    p.total = p.part_off + (tc ? align_up(sizeof(float) * tf32x3_part_floats()) : 0) + 256;
     return p;
 }
 
 struct BwdPlan {
-    size_t gh_off, tmp_off, lin_off, bg_off, slab_off, total;
+    size_t gh_off, tmp_off, lin_off, bg_off, slab_off, split_off, flags_off, part_off, mask_off, wg_off, total;
     size_t lin_bytes, bg_bytes;
     int group_n;          // layers whose output gradients live in the slab (0: none)
     int64_t group_w;      // their width
@@ -103,7 +154,17 @@ BwdPlan plan_bwd(int64_t M, int32_t n, const int64_t *widths, const int32_t *Ls,
     p.lin_off = p.tmp_off + align_up(sizeof(float) * (size_t)M * (size_t)max_w);
     p.bg_off = p.lin_off + p.lin_bytes;
     p.slab_off = p.bg_off + p.bg_bytes;
-    p.total = p.slab_off + align_up(sizeof(float) * (size_t)p.group_n * (size_t)M * (size_t)p.group_w) + 256;
+    // tensor-core dgrad: every layer's weights pre-split in one launch, own partial-tile flags per layer, one
+    // partial-tile buffer, one mask area; tensor-core wgrad: every layer keeps its split-M partial sums until the
+    // single batched reduction at the end of the pass
+    p.split_off = p.slab_off + align_up(sizeof(float) * (size_t)p.group_n * (size_t)M * (size_t)p.group_w);
+    p.flags_off = p.split_off + split_bytes(n, widths);
+    p.part_off = p.flags_off + align_up(sizeof(int) * (size_t)n * (size_t)tf32x3_max_ctas());
+    p.mask_off = p.part_off + align_up(sizeof(float) * tf32x3_part_floats());
+    p.wg_off = p.mask_off + align_up(sizeof(uint32_t) * (size_t)M * (size_t)((max_w + 31) / 32));
+    size_t wg = 0;
+    for (int l = 0; l < n; ++l) wg += align_up(wgrad_tf32x3_workspace_bytes(M, widths[l], widths[l + 1]));
+    p.total = p.wg_off + wg + 256;
     return p;
 }
 
@@ -116,7 +177,7 @@ inline bool in_group(const BwdPlan &p, int l, int n, const int64_t *widths, cons
 extern "C" size_t ptk_gcn_stack_fwd_workspace_bytes(int64_t B, int64_t Nv, int32_t n_layers, const int64_t *widths,
                                                     const int32_t *Ls) {
     if (B <= 0 || Nv <= 0 || n_layers <= 0 || !widths || !Ls) return 0;
-    return plan_fwd(B * Nv, n_layers, widths, Ls).total;
+    return plan_fwd(B * Nv, n_layers, widths, Ls, PTK_GEMM_AUTO).total;  // the larger of the two layouts
 }
 
 extern "C" int ptk_gcn_stack_fwd(const ptk_gcn_csr *graph, int64_t B, int64_t Nv, int32_t n_layers,
@@ -125,16 +186,49 @@ extern "C" int ptk_gcn_stack_fwd(const ptk_gcn_csr *graph, int64_t B, int64_t Nv
                                  uint32_t *const *x_bits, int algo, int fuse, void *workspace, size_t workspace_bytes,
                                  ptk_stream_t stream) {
     PTK_REQUIRE(graph && widths && Ls && relus && X && W && bias && acts, PTK_ERR_SHAPE, "gcn_stack_fwd: null pointer");
-    PTK_REQUIRE(B > 0 && Nv > 0 && n_layers > 0 && n_layers <= 4096, PTK_ERR_SHAPE, "gcn_stack_fwd: bad sizes");
+    PTK_REQUIRE(B > 0 && Nv > 0 && n_layers > 0 && n_layers <= MAX_LAYERS, PTK_ERR_SHAPE, "gcn_stack_fwd: bad sizes");
     const int64_t M = B * Nv;
-    const FwdPlan p = plan_fwd(M, n_layers, widths, Ls);
+    PTK_REQUIRE(algo >= 0 && algo <= 2, PTK_ERR_SHAPE, "gcn_stack_fwd: algo must be 0, 1 or 2");
+    const FwdPlan p = plan_fwd(M, n_layers, widths, Ls, algo);
     PTK_REQUIRE(workspace && workspace_bytes >= p.total, PTK_ERR_WORKSPACE, "gcn_stack_fwd: workspace too small");
     PTK_REQUIRE(aligned16(workspace), PTK_ERR_ALIGN, "gcn_stack_fwd: workspace must be 16-byte aligned");
     char *ws = reinterpret_cast<char *>(workspace);
     float *head = reinterpret_cast<float *>(ws + p.head_off);
     float *Hbuf = reinterpret_cast<float *>(ws + p.h_off);
     void *lin = ws + p.lin_off;
-    const size_t lin_bytes = p.total - p.lin_off;
+    const size_t lin_bytes = p.lin_bytes;
+    cudaStream_t st = as_stream(stream);
+    // tensor-core layers: all weight splits of the pass in one launch (instead of one per layer)
+    static thread_local float *b_hi[MAX_LAYERS], *b_lo[MAX_LAYERS];
+    static thread_local bool tc[MAX_LAYERS];
+    int *flags = reinterpret_cast<int *>(ws + p.flags_off);
+    float *part = reinterpret_cast<float *>(ws + p.part_off);
+    if (algo != PTK_GEMM_FFMA) {
+        static thread_local const float *src[MAX_LAYERS];
+        static thread_local float *hi[MAX_LAYERS], *lo[MAX_LAYERS];
+        static thread_local int rows[MAX_LAYERS], cols[MAX_LAYERS];
+        int cnt = 0;
+        size_t off = p.split_off;
+        for (int l = 0; l < n_layers; ++l) {
+            const int64_t K = widths[l], N = widths[l + 1];
+            b_hi[l] = reinterpret_cast<float *>(ws + off);
+            b_lo[l] = b_hi[l] + (size_t)K * N;
+            off += align_up(2 * sizeof(float) * (size_t)K * (size_t)N);
+            // layer inputs and Hbuf are 16-byte aligned whenever X and acts are (checked per layer below)
+            tc[l] = W[l] && tf32x3_eligible(l == 0 ? (const void *)X : (const void *)acts[l - 1], Hbuf, M, K, N);
+            if (tc[l]) {
+                src[cnt] = W[l]; hi[cnt] = b_hi[l]; lo[cnt] = b_lo[l]; rows[cnt] = (int)K; cols[cnt] = (int)N;
+                ++cnt;
+            }
+        }
+        if (cnt > 0) {
+            int rc = tf32x3_presplit_batched(cnt, src, rows, cols, /*transpose=*/1, hi, lo, flags,
+                                             n_layers * tf32x3_max_ctas(), st);
+            if (rc) return rc;
+        }
+    } else {
+        for (int l = 0; l < n_layers; ++l) tc[l] = false;
+    }
     const float *in = X;
     for (int l = 0; l < n_layers; ++l) {
         const int64_t K = widths[l], N = widths[l + 1];
@@ -154,7 +248,12 @@ extern "C" int ptk_gcn_stack_fwd(const ptk_gcn_csr *graph, int64_t B, int64_t Nv
             rc = aggregate(graph, Nv, head, B, Lp, Lc, bias[l], 1, acts[l], Lp, N, stream);
             if (rc) return rc;
         } else {
-            rc = ptk_gcn_linear_fwd(in, W[l], M, K, N, Hbuf, algo, lin, lin_bytes, stream);
+            if (tc[l])
+                rc = gemm_tf32x3_presplit(in, b_hi[l], b_lo[l], nullptr, nullptr, M, K, N, Hbuf, nullptr, part,
+                                          flags + (size_t)l * tf32x3_max_ctas(), st);
+            else
+                rc = ptk_gcn_linear_fwd(in, W[l], M, K, N, Hbuf, algo == PTK_GEMM_TF32X3 ? algo : PTK_GEMM_FFMA, lin,
+                                        lin_bytes, stream);
             if (rc) return rc;
             rc = aggregate(graph, Nv, Hbuf, B, N, Lc, bias[l], relus[l], acts[l], 0, 0, stream);
             if (rc) return rc;
@@ -178,20 +277,70 @@ extern "C" int ptk_gcn_stack_bwd(const ptk_gcn_csr *graph_t, int64_t B, int64_t 
                                  void *workspace, size_t workspace_bytes, ptk_stream_t stream) {
     PTK_REQUIRE(graph_t && widths && Ls && relus && X && W && acts && gout && gW && gb && need_gb, PTK_ERR_SHAPE,
                 "gcn_stack_bwd: null pointer");
-    PTK_REQUIRE(B > 0 && Nv > 0 && n_layers > 0 && n_layers <= 4096, PTK_ERR_SHAPE, "gcn_stack_bwd: bad sizes");
+    PTK_REQUIRE(B > 0 && Nv > 0 && n_layers > 0 && n_layers <= MAX_LAYERS, PTK_ERR_SHAPE, "gcn_stack_bwd: bad sizes");
     const int n = n_layers;
     const int64_t M = B * Nv;
     BwdPlan p = plan_bwd(M, n, widths, Ls, need_gb, batch_bias);
     PTK_REQUIRE(workspace && workspace_bytes >= p.total, PTK_ERR_WORKSPACE, "gcn_stack_bwd: workspace too small");
     PTK_REQUIRE(aligned16(workspace), PTK_ERR_ALIGN, "gcn_stack_bwd: workspace must be 16-byte aligned");
+    PTK_REQUIRE(algo_dgrad >= 0 && algo_dgrad <= 2 && algo_wgrad >= 0 && algo_wgrad <= 2, PTK_ERR_SHAPE,
+                "gcn_stack_bwd: algo must be 0, 1 or 2");
     char *ws = reinterpret_cast<char *>(workspace);
     float *gH = reinterpret_cast<float *>(ws + p.gh_off);
     float *tmp = reinterpret_cast<float *>(ws + p.tmp_off);
     void *lin = ws + p.lin_off;
     void *bg = ws + p.bg_off;
     float *slab = reinterpret_cast<float *>(ws + p.slab_off);
+    cudaStream_t st = as_stream(stream);
+    int *flags = reinterpret_cast<int *>(ws + p.flags_off);
+    float *part = reinterpret_cast<float *>(ws + p.part_off);
+    uint32_t *mask_ws = reinterpret_cast<uint32_t *>(ws + p.mask_off);
+    // tensor-core dgrad: gX = gH . W^T reduces over the layer's OUTPUT width; W (K_in x N_out) row-major is the K-major
+    // operand as stored.  All splits of the pass in one launch.
+    static thread_local float *b_hi[MAX_LAYERS], *b_lo[MAX_LAYERS];
+    static thread_local bool tc_d[MAX_LAYERS];
+    {
+        static thread_local const float *src[MAX_LAYERS];
+        static thread_local float *hi[MAX_LAYERS], *lo[MAX_LAYERS];
+        static thread_local int rows[MAX_LAYERS], cols[MAX_LAYERS];
+        int cnt = 0;
+        size_t off = p.split_off;
+        for (int l = 0; l < n; ++l) {
+            const int64_t K = widths[l], N = widths[l + 1];
+            b_hi[l] = reinterpret_cast<float *>(ws + off);
+            b_lo[l] = b_hi[l] + (size_t)K * N;
+            off += align_up(2 * sizeof(float) * (size_t)K * (size_t)N);
+            const bool wanted = l > 0 || gX;
+            const void *act_in = l == 0 ? (const void *)X : (const void *)acts[l - 1];
+            tc_d[l] = wanted && algo_dgrad != PTK_GEMM_FFMA && W[l] && tf32x3_eligible(gH, l == 0 ? (void *)gX : (void *)tmp, M, N, K) &&
+                      aligned16(act_in);
+            if (tc_d[l]) {
+                src[cnt] = W[l]; hi[cnt] = b_hi[l]; lo[cnt] = b_lo[l]; rows[cnt] = (int)K; cols[cnt] = (int)N;
+                ++cnt;
+            }
+        }
+        if (cnt > 0) {
+            int rc0 = tf32x3_presplit_batched(cnt, src, rows, cols, /*transpose=*/0, hi, lo, flags, n * tf32x3_max_ctas(), st);
+            if (rc0) return rc0;
+        }
+    }
+    ReduceBatch rb;
+    int rb_n = 0;
+    auto flush_reduce = [&]() -> int {
+        if (rb_n == 0) return PTK_OK;
+        long long mx = 0;
+        for (int i = 0; i < rb_n; ++i)
+            if (rb.elems[i] > mx) mx = rb.elems[i];
+        for (int i = rb_n; i < RB_MAX; ++i) { rb.part[i] = rb.part[0]; rb.out[i] = rb.out[0]; rb.ns[i] = 0; rb.elems[i] = 0; }
+        splitk_reduce_batched_kernel<<<dim3((unsigned)ceil_div(mx, 256), (unsigned)rb_n), 256, 0, st>>>(rb);
+        PTK_CHECK_LAUNCH();
+        rb_n = 0;
+        return PTK_OK;
+    };
+    size_t wg_off = p.wg_off;
     // the batched bias gradients are written as one (group_n, width) matrix: the group's gb pointers must be that
-    int first = -1, slot_of[4096];
+    int first = -1;
+    static thread_local int slot_of[MAX_LAYERS];
     if (p.group_n > 0) {
         int s = 0;
         for (int l = 0; l < n - 1; ++l) {
@@ -224,20 +373,43 @@ extern "C" int ptk_gcn_stack_bwd(const ptk_gcn_csr *graph_t, int64_t B, int64_t 
         }
         rc = aggregate(graph_t, Nv, g, B, N, Ls[l], nullptr, 0, gH, 0, 0, stream);
         if (rc) return rc;
+        const size_t wg_bytes = align_up(wgrad_tf32x3_workspace_bytes(M, K, N));
         if (gW[l]) {
-            rc = ptk_gcn_linear_wgrad(act_in, gH, M, K, N, gW[l], algo_wgrad, lin, p.lin_bytes, stream);
-            if (rc) return rc;
+            if (algo_wgrad != PTK_GEMM_FFMA && wgrad_tf32x3_eligible(act_in, gH, M, K, N)) {
+                // split-M partial sums stay in this layer's own region; one batched reduction ends the pass
+                float *wpart = nullptr;
+                int ns = 0;
+                rc = wgrad_tf32x3(act_in, gH, M, K, N, ws + wg_off, wg_bytes, &wpart, &ns, st);
+                if (rc) return rc;
+                rb.part[rb_n] = wpart; rb.out[rb_n] = gW[l]; rb.ns[rb_n] = ns; rb.elems[rb_n] = (long long)K * N;
+                if (++rb_n == RB_MAX) {
+                    rc = flush_reduce();
+                    if (rc) return rc;
+                }
+            } else {
+                rc = ptk_gcn_linear_wgrad(act_in, gH, M, K, N, gW[l], algo_wgrad == PTK_GEMM_TF32X3 ? algo_wgrad : PTK_GEMM_FFMA,
+                                          lin, p.lin_bytes, stream);
+                if (rc) return rc;
+            }
         }
+        wg_off += wg_bytes;
         if (l > 0 || gX) {
             const bool masked = l > 0 && relus[l - 1];
             float *dst = l == 0 ? gX : (slot(l - 1) >= 0 ? slab + (size_t)slot(l - 1) * M * p.group_w : tmp);
-            rc = ptk_gcn_linear_dgrad(gH, W[l], masked ? act_in : nullptr,
-                                      (masked && x_bits) ? x_bits[l] : nullptr, M, K, N, dst, algo_dgrad, lin,
-                                      p.lin_bytes, stream);
+            const uint32_t *bits = (masked && x_bits) ? x_bits[l] : nullptr;
+            if (tc_d[l] && aligned16(dst))
+                rc = gemm_tf32x3_presplit(gH, b_hi[l], b_lo[l], masked ? act_in : nullptr, bits, M, /*reduce over*/ N,
+                                          /*outputs*/ K, dst, mask_ws, part, flags + (size_t)l * tf32x3_max_ctas(), st);
+            else
+                rc = ptk_gcn_linear_dgrad(gH, W[l], masked ? act_in : nullptr, bits, M, K, N, dst,
+                                          algo_dgrad == PTK_GEMM_TF32X3 ? algo_dgrad : PTK_GEMM_FFMA, lin, p.lin_bytes,
+                                          stream);
             if (rc) return rc;
             g = dst;
         }
     }
+    rc = flush_reduce();
+    if (rc) return rc;
     if (p.group_n > 0) {
         rc = ptk_gcn_bias_grad_batched(slab, p.group_n, M, p.group_w, p.group_L, gb[first], bg, p.bg_bytes, stream);
         if (rc) return rc;

@@ -123,6 +123,8 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(TG_BM >> 4) << 24);
 }
 
+constexpr int TG_SPLIT_BATCH = 32;  // layers per batched weight-split launch
+
 struct TGParams {
     int M, N, K;          // D is M x N, reduction K
     float *D;
@@ -610,6 +612,31 @@ __global__ void split_tf32_kernel(const float *__restrict__ src, int rows, int c
     lo[o] = __uint_as_float(l);
 }
 
+// The weight splits of a whole GCN pass in one launch (csrc/gcn_stack.cu): blockIdx.y = layer.  Also zeroes the
+// partial-tile flags of every layer's GEMM (layer l owns flags[l * flags_per_layer ...]).
+struct SplitBatch {
+    const float *src[TG_SPLIT_BATCH];
+    float *hi[TG_SPLIT_BATCH];
+    float *lo[TG_SPLIT_BATCH];
+    int rows[TG_SPLIT_BATCH], cols[TG_SPLIT_BATCH];
+    int transpose;
+    int *flags;
+    int n_flags;
+};
+__global__ void split_tf32_batched_kernel(const __grid_constant__ SplitBatch b) {
+    const int layer = blockIdx.y;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (layer == 0 && i < b.n_flags) b.flags[i] = 0;
+    const int rows = b.rows[layer], cols = b.cols[layer];
+    if (i >= (long long)rows * cols) return;
+    const int r = (int)(i / cols), c = (int)(i % cols);
+    uint32_t h, l;
+    split_tf32(b.src[layer][i], h, l);
+    const size_t o = b.transpose ? (size_t)c * rows + r : (size_t)i;
+    b.hi[layer][o] = __uint_as_float(h);
+    b.lo[layer][o] = __uint_as_float(l);
+}
+
 // ------------------------------------------------------------------------------------------- host
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -697,6 +724,38 @@ size_t tf32x3_workspace_bytes(int64_t M, int64_t K, int64_t N) {
            tf32x3_part_bytes();
 }
 
+static int tg_launch(const float *A, const float *b_hi, const float *b_lo, const uint32_t *mask, int64_t M, int64_t K,
+                     int64_t N, float *D, float *part, int *flags, int n_ctas, cudaStream_t st) {
+    CUtensorMap map_a, map_bhi, map_blo;
+    int rc = make_map(&map_a, A, M, K, TG_BM);
+    if (rc) return rc;
+    rc = make_map(&map_bhi, b_hi, N, K, TG_BN);  // (N x K) K-major; rows beyond N are zero-filled
+    if (rc) return rc;
+    rc = make_map(&map_blo, b_lo, N, K, TG_BN);
+    if (rc) return rc;
+
+    TGParams p;
+    p.M = (int)M; p.N = (int)N; p.K = (int)K; p.D = D; p.mask = mask; p.wpr = (int)ceil_div(N, 32);
+    static int dbg = -1;
+    if (dbg < 0) { const char *e = getenv("PTK_TG_DEBUG"); dbg = e ? atoi(e) : 0; }
+    p.dbg = dbg;
+    p.part = part;
+    p.flags = flags;
+    const size_t smem = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024;
+    dim3 grid((unsigned)n_ctas);
+    if (!smem_optin_done(0)) {  // the attribute is per device
+        PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_optin_mark(0);
+    }
+    if (mask)
+        gemm_tf32x3_kernel<true><<<grid, TG_THREADS, smem, st>>>(map_a, map_bhi, map_blo, p);
+    else
+        gemm_tf32x3_kernel<false><<<grid, TG_THREADS, smem, st>>>(map_a, map_bhi, map_blo, p);
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}
+
 // D (M x N) = A (M x K) . Bsrc, where Bsrc is either (K x N) row-major [b_is_kn = 1: transposed during the
 // split] or (N x K) row-major [b_is_kn = 0].  act (optional): D masked by act > 0.
 int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act, int64_t M, int64_t K, int64_t N,
@@ -726,33 +785,52 @@ int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act
         split_tf32_kernel<<<(unsigned)ceil_div(elems, 256), 256, 0, st>>>(Bsrc, (int)N, (int)K, 0, b_hi, b_lo, flags, n_ctas);
     PTK_CHECK_LAUNCH();
 
-    CUtensorMap map_a, map_bhi, map_blo;
-    int rc = make_map(&map_a, A, M, K, TG_BM);
-    if (rc) return rc;
-    rc = make_map(&map_bhi, b_hi, N, K, TG_BN);  // (N x K) K-major; rows beyond N are zero-filled
-    if (rc) return rc;
-    rc = make_map(&map_blo, b_lo, N, K, TG_BN);
-    if (rc) return rc;
+    return tg_launch(A, b_hi, b_lo, act ? mask : nullptr, M, K, N, D, part, flags, n_ctas, st);
+}
 
-    TGParams p;
-    p.M = (int)M; p.N = (int)N; p.K = (int)K; p.D = D; p.mask = act ? mask : nullptr; p.wpr = wpr;
-    static int dbg = -1;
-    if (dbg < 0) { const char *e = getenv("PTK_TG_DEBUG"); dbg = e ? atoi(e) : 0; }
-    p.dbg = dbg;
-    p.part = part;
-    p.flags = flags;
-    const size_t smem = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024;
-    dim3 grid((unsigned)n_ctas);
-    if (!smem_optin_done(0)) {  // the attribute is per device
-        PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_optin_mark(0);
+// One GEMM whose B operand was split before (tf32x3_presplit_batched); mask_ws (M x ceil(N/32) words) is only used
+// when `act` comes without its packed mask.  flags: this GEMM's own n_ctas ints, zeroed by the batched split.
+int gemm_tf32x3_presplit(const float *A, const float *b_hi, const float *b_lo, const float *act, const uint32_t *act_bits,
+                         int64_t M, int64_t K, int64_t N, float *D, uint32_t *mask_ws, float *part, int *flags,
+                         cudaStream_t st) {
+    const int64_t num_tiles = ceil_div(M, TG_BM) * ceil_div(N, TG_BN);
+    const int n_ctas = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
+    const uint32_t *mask = nullptr;
+    if (act && act_bits) {
+        mask = act_bits;
+    } else if (act) {
+        PTK_REQUIRE(mask_ws, PTK_ERR_WORKSPACE, "gemm_tf32x3_presplit: no mask workspace");
+        relu_bits_kernel<<<(unsigned)ceil_div(M, 8), 256, 0, st>>>(act, (long long)M, (int)N, (int)ceil_div(N, 32), mask_ws);
+        PTK_CHECK_LAUNCH();
+        mask = mask_ws;
     }
-    if (act)
-        gemm_tf32x3_kernel<true><<<grid, TG_THREADS, smem, st>>>(map_a, map_bhi, map_blo, p);
-    else
-        gemm_tf32x3_kernel<false><<<grid, TG_THREADS, smem, st>>>(map_a, map_bhi, map_blo, p);
-    PTK_CHECK_LAUNCH();
+    return tg_launch(A, b_hi, b_lo, mask, M, K, N, D, part, flags, n_ctas, st);
+}
+
+size_t tf32x3_part_floats() { return (size_t)sm_count() * (TG_BM * TG_BN); }
+int tf32x3_max_ctas() { return sm_count(); }
+
+// Split n weight matrices (src[i]: rows[i] x cols[i] row-major) into hi / lo in one launch per 32 layers and zero
+// `n_flags` partial-tile flags.  transpose: write (cols x rows) -- the forward's (K x N) weights as K-major B.
+int tf32x3_presplit_batched(int n, const float *const *src, const int *rows, const int *cols, int transpose,
+                            float *const *hi, float *const *lo, int *flags, int n_flags, cudaStream_t st) {
+    for (int base = 0; base < n; base += TG_SPLIT_BATCH) {
+        SplitBatch b;
+        const int cnt = n - base < TG_SPLIT_BATCH ? n - base : TG_SPLIT_BATCH;
+        long long max_elems = base == 0 ? n_flags : 0;
+        for (int i = 0; i < TG_SPLIT_BATCH; ++i) {
+            const int j = i < cnt ? base + i : base;
+            b.src[i] = src[j]; b.hi[i] = hi[j]; b.lo[i] = lo[j]; b.rows[i] = rows[j]; b.cols[i] = cols[j];
+            const long long e = (long long)rows[j] * cols[j];
+            if (e > max_elems) max_elems = e;
+        }
+        b.transpose = transpose;
+        b.flags = flags;
+        b.n_flags = base == 0 ? n_flags : 0;
+        if (max_elems <= 0) continue;
+        split_tf32_batched_kernel<<<dim3((unsigned)ceil_div(max_elems, 256), (unsigned)cnt), 256, 0, st>>>(b);
+        PTK_CHECK_LAUNCH();
+    }
     return PTK_OK;
 }
 

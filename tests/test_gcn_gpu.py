@@ -418,6 +418,7 @@ def test_native_stack_runner_is_bit_identical_to_the_per_layer_calls(golden, hid
         ptk_b200.ops.native_stack, ptk_b200.ops.fuse_layers = True, True
     for fused in (True, False):
         (a, la), (b, lb) = res[(True, fused)], res[(False, fused)]
-        assert la == lb, "the native runner must launch exactly the kernels the Python loop launches"
+        # same kernels, minus the per-layer weight splits and split-M reductions it batches into one launch per pass
+        assert la <= lb and la >= lb - 3 * layers, (la, lb)
         for u, v in zip(a, b):
             assert torch.equal(u, v)

@@ -45,3 +45,22 @@ s = sum(v[1] for v in tot.values())
 print(f"GPU busy per step: {s/3/1e3:.2f} ms")
 for k, (c, t) in sorted(tot.items(), key=lambda kv: -kv[1][1])[:22]:
     print(f"{t/3/1e3:8.3f} ms {c//3:5d}x {t/c:8.1f} us  {k}")
+
+# ---- idle gaps between consecutive kernels of the last profiled step (where the eager step loses time to the host)
+kern = sorted(((e.time_range.start, e.time_range.end, e.name[:48]) for e in prof.events()
+               if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda t: t[0])
+n3 = len(kern) // 3
+kern = kern[2 * n3:]
+gaps = []
+for (s0, e0, n0), (s1, e1, n1) in zip(kern[:-1], kern[1:]):
+    if s1 > e0:
+        gaps.append((s1 - e0, n0, n1))
+tot_gap = sum(g[0] for g in gaps)
+print(f"idle between kernels in one step: {tot_gap/1e3:.2f} ms over {len(gaps)} gaps "
+      f"(step span {(kern[-1][1]-kern[0][0])/1e3:.2f} ms, {len(kern)} kernels)")
+hist = collections.Counter()
+for g, a_, b_ in gaps:
+    hist[(a_, b_)] += g
+for (a_, b_), g in hist.most_common(14):
+    cnt = sum(1 for x in gaps if (x[1], x[2]) == (a_, b_))
+    print(f"  {g/1e3:7.3f} ms {cnt:4d}x  {a_}  ->  {b_}")
