@@ -23,6 +23,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--use_fast_math=false",
          "-I", INC, "-I", CSRC]
 FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]  # never fast-math: parity is bit-level
+FLAGS += os.environ.get("PTK_EXTRA_NVCC_FLAGS", "").split()  # development experiments only
 
 
 def sources():

@@ -21,6 +21,14 @@ static std::atomic<unsigned long long> g_launches{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+bool pdl_enabled() {
+    static const bool on = []() {
+        const char *e = getenv("PTK_NO_PDL");
+        return !(e && atoi(e) != 0);
+    }();
+    return on;
+}
+
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 148;
     int dev = 0;

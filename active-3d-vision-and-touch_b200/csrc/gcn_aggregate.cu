@@ -387,6 +387,8 @@ gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__r
     __shared__ __align__(16) uint32_t s_off[AG_WARPS][AT_STRIP];
     __shared__ __align__(16) float s_w[AG_WARPS][AT_STRIP];
     __shared__ __align__(16) float s_part[AG_WARPS][NG * 32 * 4];
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int ngroups = C >> 2;
     const int gath = (L + 3) >> 2;
@@ -651,6 +653,8 @@ constexpr int BG_PARTS = 1184;  // 8 slabs per SM: short dependent-load chains i
 // fixed-order shared-memory reduction over the row lanes.
 __global__ void __launch_bounds__(256)
 bias_grad_stage1(const float *__restrict__ g, long long M, int C, int L, float *__restrict__ part) {
+    pdl_launch_dependents();
+    pdl_wait();
     // blockIdx.y = layer of a batched call: g and part advance by one (M x C) matrix / one partial block per layer
     g += (size_t)blockIdx.y * (size_t)M * C;
     part += (size_t)blockIdx.y * gridDim.x * L;
@@ -690,6 +694,8 @@ bias_grad_stage1(const float *__restrict__ g, long long M, int C, int L, float *
 // stage 2: one warp per column; lanes stride over the partials, fixed-order butterfly => deterministic
 __global__ void __launch_bounds__(256)
 bias_grad_stage2(const float *__restrict__ part, int nparts, int C, int L, float *__restrict__ gbias) {
+    pdl_launch_dependents();
+    pdl_wait();
     part += (size_t)blockIdx.y * nparts * L;
     gbias += (size_t)blockIdx.y * C;
     const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -769,9 +775,8 @@ extern "C" int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, c
         hb.common_col = common_col; hb.common_w = common_w; hb.n_common = common ? n_common : 0;
         hb.alpha = hub_alpha; hb.row_skip = common ? row_skip : nullptr;
 #define PTK_TILE(NGv)                                                                                        \
-    gcn_aggregate_tile_kernel<NGv><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hb, hub_slots, (int)Nv, in, \
-                                                                (int)B, (int)C, (int)L, bias, relu, out, TV, BG, n_tiles, hubs_first, \
-                                                                (int)ldi, (int)ldo, warp_is_batch)
+    launch_pdl(gcn_aggregate_tile_kernel<NGv>, dim3(grid), dim3(AG_THREADS), 0, st, rowptr, col, val, hb, hub_slots, (int)Nv, in, \
+               (int)B, (int)C, (int)L, bias, relu, out, TV, BG, n_tiles, hubs_first, (int)ldi, (int)ldo, warp_is_batch)
         if (gath <= 32) PTK_TILE(1);
         else if (gath <= 64) PTK_TILE(2);
         else PTK_TILE(3);
@@ -834,10 +839,10 @@ extern "C" int ptk_gcn_bias_grad_batched(const float *g, int64_t n_mats, int64_t
     const int nparts = (int)(M < BG_PARTS ? M : BG_PARTS);
     float *part = reinterpret_cast<float *>(workspace);
     if (L > 0) {
-        bias_grad_stage1<<<dim3((unsigned)nparts, (unsigned)n_mats), 256, 0, st>>>(g, (long long)M, (int)C, (int)L, part);
+        launch_pdl(bias_grad_stage1, dim3((unsigned)nparts, (unsigned)n_mats), dim3(256), 0, st, g, (long long)M, (int)C, (int)L, part);
         PTK_CHECK_LAUNCH();
     }
-    bias_grad_stage2<<<dim3((unsigned)ceil_div(C, 8), (unsigned)n_mats), 256, 0, st>>>(part, nparts, (int)C, (int)L, gbias);
+    launch_pdl(bias_grad_stage2, dim3((unsigned)ceil_div(C, 8), (unsigned)n_mats), dim3(256), 0, st, part, nparts, (int)C, (int)L, gbias);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }
@@ -852,10 +857,10 @@ extern "C" int ptk_gcn_bias_grad(const float *g, int64_t M, int64_t C, int64_t L
     const int nparts = (int)(M < BG_PARTS ? M : BG_PARTS);
     float *part = reinterpret_cast<float *>(workspace);
     if (L > 0) {
-        bias_grad_stage1<<<nparts, 256, 0, st>>>(g, (long long)M, (int)C, (int)L, part);
+        launch_pdl(bias_grad_stage1, dim3((unsigned)nparts), dim3(256), 0, st, g, (long long)M, (int)C, (int)L, part);
         PTK_CHECK_LAUNCH();
     }
-    bias_grad_stage2<<<(unsigned)ceil_div(C, 8), 256, 0, st>>>(part, nparts, (int)C, (int)L, gbias);
+    launch_pdl(bias_grad_stage2, dim3((unsigned)ceil_div(C, 8)), dim3(256), 0, st, part, nparts, (int)C, (int)L, gbias);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }

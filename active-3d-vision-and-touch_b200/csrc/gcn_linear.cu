@@ -139,6 +139,8 @@ sgemm_fwd_kernel(const float *__restrict__ A, const float *__restrict__ Bm, floa
     // (the fused GCN-layer form: the propagated slice goes to a compact scratch for the aggregation, the
     // pass-through slice straight into the layer output).  Plain GEMM: nsplit = N, ld1 = N.
     constexpr int T = BM * 2;
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ __align__(16) float As[2][FW_BK][BM + FW_PAD];
     __shared__ __align__(16) float Bs[2][FW_BK][FW_BN];
     // By-product for the backward: bit (k & 31) of a_bits[m * wpr + (k >> 5)] = A[m, k] > 0 -- the ReLU mask of
@@ -296,8 +298,8 @@ static void launch_fwd(const float *X, const float *W, float *H, int64_t M, int6
         C2 = H;
         ld2 = (int)N;
     }
-    sgemm_fwd_kernel<BM><<<grid, BM * 2, 0, st>>>(X, W, H, (int)M, (int)N, (int)K, ld1, nsplit, C2, ld2, relu2,
-                                                  K <= 32 * FW_MAXW ? a_bits : nullptr);
+    launch_pdl(sgemm_fwd_kernel<BM>, grid, dim3(BM * 2), 0, st, X, W, H, (int)M, (int)N, (int)K, ld1, nsplit, C2, ld2,
+               relu2, K <= 32 * FW_MAXW ? a_bits : nullptr);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -32,6 +32,8 @@ struct ReduceBatch {
     long long elems[RB_MAX];
 };
 __global__ void splitk_reduce_batched_kernel(const __grid_constant__ ReduceBatch b) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int l = blockIdx.y;
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long elems = b.elems[l];
@@ -332,7 +334,7 @@ extern "C" int ptk_gcn_stack_bwd(const ptk_gcn_csr *graph_t, int64_t B, int64_t 
         for (int i = 0; i < rb_n; ++i)
             if (rb.elems[i] > mx) mx = rb.elems[i];
         for (int i = rb_n; i < RB_MAX; ++i) { rb.part[i] = rb.part[0]; rb.out[i] = rb.out[0]; rb.ns[i] = 0; rb.elems[i] = 0; }
-        splitk_reduce_batched_kernel<<<dim3((unsigned)ceil_div(mx, 256), (unsigned)rb_n), 256, 0, st>>>(rb);
+        launch_pdl(splitk_reduce_batched_kernel, dim3((unsigned)ceil_div(mx, 256), (unsigned)rb_n), dim3(256), 0, st, rb);
         PTK_CHECK_LAUNCH();
         rb_n = 0;
         return PTK_OK;

@@ -152,6 +152,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (p.K + TG_BK - 1) / TG_BK;
+    pdl_launch_dependents();  // the successor may start its own prologue while this grid runs (ptk_common.cuh)
     // persistent, work split by k-blocks ("stream-K"): the (tile, k-block) pairs are numbered tile-major and CTA c
     // takes the contiguous range [c U / G, (c+1) U / G) of them -- 488 tiles on 148 SMs would otherwise cost 4 tile
     // times for 3.3 tiles of work per SM.  A range is at least one tile long, so a tile is shared by at most two
@@ -189,6 +190,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
+    pdl_wait();  // barriers + TMEM are set up; from here on global memory of the predecessors is read
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -459,6 +461,8 @@ wgrad_tf32x3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
+    pdl_launch_dependents();
+    pdl_wait();  // set-up done; the predecessors' global memory is read from here on
 
     if (warp == 0) {
         if (lane == 0) {
@@ -624,6 +628,8 @@ struct SplitBatch {
     int n_flags;
 };
 __global__ void split_tf32_batched_kernel(const __grid_constant__ SplitBatch b) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int layer = blockIdx.y;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (layer == 0 && i < b.n_flags) b.flags[i] = 0;
@@ -749,9 +755,9 @@ static int tg_launch(const float *A, const float *b_hi, const float *b_lo, const
         smem_optin_mark(0);
     }
     if (mask)
-        gemm_tf32x3_kernel<true><<<grid, TG_THREADS, smem, st>>>(map_a, map_bhi, map_blo, p);
+        launch_pdl(gemm_tf32x3_kernel<true>, grid, dim3(TG_THREADS), smem, st, map_a, map_bhi, map_blo, p);
     else
-        gemm_tf32x3_kernel<false><<<grid, TG_THREADS, smem, st>>>(map_a, map_bhi, map_blo, p);
+        launch_pdl(gemm_tf32x3_kernel<false>, grid, dim3(TG_THREADS), smem, st, map_a, map_bhi, map_blo, p);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }
@@ -828,7 +834,7 @@ int tf32x3_presplit_batched(int n, const float *const *src, const int *rows, con
         b.flags = flags;
         b.n_flags = base == 0 ? n_flags : 0;
         if (max_elems <= 0) continue;
-        split_tf32_batched_kernel<<<dim3((unsigned)ceil_div(max_elems, 256), (unsigned)cnt), 256, 0, st>>>(b);
+        launch_pdl(split_tf32_batched_kernel, dim3((unsigned)ceil_div(max_elems, 256), (unsigned)cnt), dim3(256), 0, st, b);
         PTK_CHECK_LAUNCH();
     }
     return PTK_OK;
@@ -881,7 +887,7 @@ int wgrad_tf32x3(const float *X, const float *gH, int64_t M, int64_t Kin, int64_
         smem_optin_mark(1);
     }
     dim3 grid((unsigned)w.tiles_m, (unsigned)w.tiles_n, (unsigned)w.splits);
-    wgrad_tf32x3_kernel<<<grid, WG_THREADS, smem, st>>>(map_x, map_g, p);
+    launch_pdl(wgrad_tf32x3_kernel, grid, dim3(WG_THREADS), smem, st, map_x, map_g, p);
     PTK_CHECK_LAUNCH();
     *part_out = part;
     *n_splits = w.splits;

@@ -40,6 +40,44 @@ void count_launch();  // ptk_launch_count(): one tick per kernel launch of this 
 
 inline cudaStream_t as_stream(ptk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// ---- programmatic dependent launch (PDL).  The kernels of one GCN pass are 5-135 us each and follow one another
+// on a single stream; a plain launch starts a kernel ~2 us after its predecessor drained (measured: 1.0 ms of idle
+// gaps over the ~550 kernels of a reconstruction step).  Launched through launch_pdl(), a kernel may become resident
+// before its predecessor has drained; it must call pdl_wait() before touching global memory (that blocks until the
+// whole predecessor grid has completed and flushed).  Every kernel launched this way waits, so ordering stays
+// transitive along the stream.
+// PTK_NO_PDL=1 launches the same kernels without the attribute (A/B measurements).
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Early trigger: measured HARMFUL here (reconstruction step 20.10 ms with it, 18.97 ms without, 19.62 ms without PDL):
+// successor CTAs that become resident during the tail of a multi-wave kernel take SM slots and skew the successor's
+// own CTA placement.  Without it the successor is still launched early (its launch latency overlaps the predecessor)
+// and released when the predecessor completes.  -DPTK_PDL_EARLY_TRIGGER re-enables it for experiments.
+__device__ __forceinline__ void pdl_launch_dependents() {
+#ifdef PTK_PDL_EARLY_TRIGGER
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+}
+#endif
+
 int sm_count();  // cached cudaDevAttrMultiProcessorCount of the current device
 
 // Development override: integer value of environment variable `name`, read once per call site
