@@ -91,6 +91,7 @@ chamfer_finalize_kernel(const unsigned long long *__restrict__ keys_x,
                         float *__restrict__ dist_x, int32_t *__restrict__ idx_x,
                         float *__restrict__ dist_y, int32_t *__restrict__ idx_y,
                         float *__restrict__ cham) {
+    pdl_wait();  // launched with programmatic stream serialization (ptk_common.cuh)
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     __shared__ float red[16];
@@ -130,6 +131,7 @@ __global__ void chamfer_bwd_direct_kernel(const float *__restrict__ x, const flo
                                           const int32_t *__restrict__ idx_y,
                                           const float *__restrict__ grad_cham, int P1, int P2,
                                           float *__restrict__ grad_x, float *__restrict__ grad_y) {
+    pdl_wait();  // launched with programmatic stream serialization (ptk_common.cuh)
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const float g = grad_cham[b];
@@ -159,6 +161,7 @@ __global__ void chamfer_bwd_scatter_kernel(const float *__restrict__ x, const fl
                                            const int32_t *__restrict__ idx_y,
                                            const float *__restrict__ grad_cham, int P1, int P2,
                                            float *__restrict__ grad_x, float *__restrict__ grad_y) {
+    pdl_wait();  // launched with programmatic stream serialization (ptk_common.cuh)
     const int b = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const float g = grad_cham[b];
@@ -238,16 +241,16 @@ static int launch_nn(const float *x, const float *y, int64_t B, int64_t P1, int6
                 "chamfer: batch %lld too large for one launch (max 32767 clouds)", (long long)B);
     const int iP1 = (int)P1, iP2 = (int)P2;
     if (filter) {
-        chamfer_bounds_kernel<<<(unsigned)B, 1024, 0, st>>>(x, y, iP1, iP2, w.aux, w.count);
+        launch_pdl(chamfer_bounds_kernel, dim3((unsigned)B), dim3(1024), 0, st, x, y, iP1, iP2, w.aux, w.count);
         PTK_CHECK_LAUNCH();
         const int Pp = soa_padded(iP1 > iP2 ? iP1 : iP2);
-        chamfer_prep_kernel<<<dim3((unsigned)ceil_div(Pp, 256), (unsigned)(2 * B)), 256, 0, st>>>(x, y, iP1, iP2, w.aux,
-                                                                                                 w.soa_x, w.soa_y);
+        launch_pdl(chamfer_prep_kernel, dim3((unsigned)ceil_div(Pp, 256), (unsigned)(2 * B)), dim3(256), 0, st, x, y, iP1, iP2,
+                   w.aux, w.soa_x, w.soa_y);
         PTK_CHECK_LAUNCH();
 #define PTK_FILTER(RR)                                                                                          \
-    chamfer_nn_filter_tma_kernel<RR, CH_CHUNK, CH_THREADS, CH_MINB_F, CH_TT_F><<<grid, CH_THREADS, 0, st>>>(     \
-        x, y, iP1, iP2, p.split_len, p.n_split, w.aux, w.soa_x, w.soa_y, w.keys_x, w.keys_y, dir_only, w.rescue_x, \
-        w.rescue_y, w.count, w.flag_x, w.flag_y)
+    launch_pdl(chamfer_nn_filter_tma_kernel<RR, CH_CHUNK, CH_THREADS, CH_MINB_F, CH_TT_F>, grid, dim3(CH_THREADS), 0, st, \
+               x, y, iP1, iP2, p.split_len, p.n_split, w.aux, w.soa_x, w.soa_y, w.keys_x, w.keys_y, dir_only, w.rescue_x, \
+               w.rescue_y, w.count, w.flag_x, w.flag_y)
         switch (p.R) {
             case 8: PTK_FILTER(8); break;
             case 4: PTK_FILTER(4); break;
@@ -257,14 +260,14 @@ static int launch_nn(const float *x, const float *y, int64_t B, int64_t P1, int6
         PTK_CHECK_LAUNCH();
         // rescue pass over the queued (ambiguous) queries; CTAs beyond the list length exit at once
         dim3 rgrid((unsigned)ceil_div(Pq, (int64_t)CH_THREADS * 8), (unsigned)p.n_split, (unsigned)(B * ndir));
-        chamfer_nn_exact2_kernel<8, CH_CHUNK, CH_THREADS, CH_MINB><<<rgrid, CH_THREADS, 0, st>>>(
-            x, y, iP1, iP2, p.split_len, p.n_split, w.keys_x, w.keys_y, dir_only, w.rescue_x, w.rescue_y, w.count);
+        launch_pdl(chamfer_nn_exact2_kernel<8, CH_CHUNK, CH_THREADS, CH_MINB>, rgrid, dim3(CH_THREADS), 0, st, x, y, iP1, iP2,
+                   p.split_len, p.n_split, w.keys_x, w.keys_y, dir_only, w.rescue_x, w.rescue_y, w.count);
         PTK_CHECK_LAUNCH();
         return PTK_OK;
     }
 #define PTK_EXACT(RR)                                                                            \
-    chamfer_nn_exact2_kernel<RR, CH_CHUNK, CH_THREADS, CH_MINB><<<grid, CH_THREADS, 0, st>>>(     \
-        x, y, iP1, iP2, p.split_len, p.n_split, w.keys_x, w.keys_y, dir_only, nullptr, nullptr, nullptr)
+    launch_pdl(chamfer_nn_exact2_kernel<RR, CH_CHUNK, CH_THREADS, CH_MINB>, grid, dim3(CH_THREADS), 0, st, x, y, iP1, iP2, \
+               p.split_len, p.n_split, w.keys_x, w.keys_y, dir_only, nullptr, nullptr, nullptr)
     switch (p.R) {
         case 8: PTK_EXACT(8); break;
         case 4: PTK_EXACT(4); break;
@@ -333,8 +336,8 @@ extern "C" int ptk_knn1_fwd(const float *p1, const float *p2, int64_t B, int64_t
     const ChamferWs w = carve(workspace, B, P1, P2);
     rc = launch_nn(p1, p2, B, P1, P2, w, 0, st);
     if (rc) return rc;
-    chamfer_finalize_kernel<<<(unsigned)B, 512, 0, st>>>(w.keys_x, nullptr, (int)P1, (int)P2, dist, idx,
-                                                         nullptr, nullptr, nullptr);
+    launch_pdl(chamfer_finalize_kernel, dim3((unsigned)B), dim3(512), 0, st, w.keys_x, nullptr, (int)P1, (int)P2, dist, idx,
+               nullptr, nullptr, nullptr);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }
@@ -355,8 +358,8 @@ extern "C" int ptk_chamfer_fwd(const float *x, const float *y, int64_t B, int64_
     const ChamferWs w = carve(workspace, B, P1, P2);
     rc = launch_nn(x, y, B, P1, P2, w, -1, st);
     if (rc) return rc;
-    chamfer_finalize_kernel<<<(unsigned)B, 512, 0, st>>>(w.keys_x, w.keys_y, (int)P1, (int)P2, dist_x,
-                                                         idx_x, dist_y, idx_y, cham);
+    launch_pdl(chamfer_finalize_kernel, dim3((unsigned)B), dim3(512), 0, st, w.keys_x, w.keys_y, (int)P1, (int)P2, dist_x,
+               idx_x, dist_y, idx_y, cham);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }
@@ -372,11 +375,11 @@ extern "C" int ptk_chamfer_bwd(const float *x, const float *y, const int32_t *id
     const int64_t Pm = P1 > P2 ? P1 : P2;
     dim3 grid((unsigned)ceil_div(Pm, 256), (unsigned)B);
     PTK_REQUIRE(B <= 65535, PTK_ERR_SHAPE, "chamfer_bwd: batch too large");
-    chamfer_bwd_direct_kernel<<<grid, 256, 0, st>>>(x, y, idx_x, idx_y, grad_cham, (int)P1, (int)P2,
-                                                    grad_x, grad_y);
+    launch_pdl(chamfer_bwd_direct_kernel, grid, dim3(256), 0, st, x, y, idx_x, idx_y, grad_cham, (int)P1, (int)P2, grad_x,
+               grad_y);
     PTK_CHECK_LAUNCH();
-    chamfer_bwd_scatter_kernel<<<grid, 256, 0, st>>>(x, y, idx_x, idx_y, grad_cham, (int)P1, (int)P2,
-                                                     grad_x, grad_y);
+    launch_pdl(chamfer_bwd_scatter_kernel, grid, dim3(256), 0, st, x, y, idx_x, idx_y, grad_cham, (int)P1, (int)P2, grad_x,
+               grad_y);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }

@@ -78,6 +78,7 @@ constexpr float FILTER_THR_BD = 1.9073486e-6f;  // 32 u = 2^-19
 __global__ void __launch_bounds__(1024)
 chamfer_bounds_kernel(const float *__restrict__ x, const float *__restrict__ y, int P1, int P2,
                       PairAux *__restrict__ aux, unsigned int *__restrict__ rescue_count) {
+    pdl_wait();  // launched with programmatic stream serialization (ptk_common.cuh)
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const float PINF = __int_as_float(0x7f800000), NINF = __int_as_float(0xff800000);
@@ -346,6 +347,7 @@ __host__ __device__ inline int soa_padded(int P) { return (P + SOA_PAD - 1) / SO
 __global__ void __launch_bounds__(256)
 chamfer_prep_kernel(const float *__restrict__ x, const float *__restrict__ y, int P1, int P2,
                     const PairAux *__restrict__ aux, float *__restrict__ soa_x, float *__restrict__ soa_y) {
+    pdl_wait();  // launched with programmatic stream serialization (ptk_common.cuh)
     const int b = blockIdx.y >> 1, cloud = blockIdx.y & 1;
     const int P = cloud == 0 ? P1 : P2;
     const int Pp = soa_padded(P);
@@ -389,6 +391,7 @@ chamfer_nn_filter_tma_kernel(const float *__restrict__ x, const float *__restric
                              int *__restrict__ rescue_x, int *__restrict__ rescue_y,
                              unsigned int *__restrict__ rescue_count, unsigned int *__restrict__ rescue_flag_x,
                              unsigned int *__restrict__ rescue_flag_y) {
+    pdl_wait();  // launched with programmatic stream serialization (ptk_common.cuh)
     static_assert((CHUNK == 16 || CHUNK == 32 || CHUNK == 64) && TT % CHUNK == 0 && SOA_PAD % CHUNK == 0, "tile must hold whole chunks");
     const int z = blockIdx.z;
     const int b = dir_only >= 0 ? z : (z >> 1);
@@ -656,6 +659,7 @@ chamfer_nn_exact2_kernel(const float *__restrict__ x, const float *__restrict__ 
                          int split_len, int n_split, u64 *__restrict__ keys_x,
                          u64 *__restrict__ keys_y, int dir_only, const int *__restrict__ rescue_x,
                          const int *__restrict__ rescue_y, const unsigned int *__restrict__ rescue_count) {
+    pdl_wait();  // launched with programmatic stream serialization (ptk_common.cuh)
     const int z = blockIdx.z;
     const int b = dir_only >= 0 ? z : (z >> 1);
     const int dir = dir_only >= 0 ? dir_only : (z & 1);

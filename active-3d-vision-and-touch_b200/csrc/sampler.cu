@@ -41,6 +41,7 @@ __device__ __forceinline__ unsigned long long face_weight(float a, float amax) {
 __global__ void __launch_bounds__(SP_THREADS)
 sample_prepare_kernel(const float *__restrict__ verts, int V, const int32_t *__restrict__ faces, int F,
                       unsigned long long *__restrict__ cum, float *__restrict__ areas) {
+    pdl_wait();  // launched with programmatic stream serialization (ptk_common.cuh)
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const float *vb = verts + (size_t)b * V * 3;
@@ -100,6 +101,7 @@ sample_points_kernel(const float *__restrict__ verts, int V, const int32_t *__re
                      const unsigned long long *__restrict__ cum, const float *__restrict__ u_face,
                      const float *__restrict__ uu, const float *__restrict__ vv, int S,
                      float *__restrict__ pts, int32_t *__restrict__ face_idx) {
+    pdl_wait();  // launched with programmatic stream serialization (ptk_common.cuh)
     const int b = blockIdx.y;
     const int tid = threadIdx.x;
     const unsigned long long *cb = cum + (size_t)b * F;
@@ -164,6 +166,7 @@ sample_bwd_kernel(const float *__restrict__ grad_pts, const int32_t *__restrict_
                   const float *__restrict__ uu, const float *__restrict__ vv,
                   const int32_t *__restrict__ faces, int V, int S, int samples_per_cta,
                   float *__restrict__ grad_verts) {
+    pdl_wait();  // launched with programmatic stream serialization (ptk_common.cuh)
     const int b = blockIdx.y;
     const int tid = threadIdx.x;
     __shared__ float s_acc[SB_SMEM_VERTS * 3];
@@ -288,12 +291,12 @@ extern "C" int ptk_sample_fwd(const float *verts, int64_t B, int64_t V, const in
                     "sample_fwd: workspace too small");
         cum = reinterpret_cast<unsigned long long *>(workspace);
         auto *areas = reinterpret_cast<float *>(cum + (size_t)B * F);
-        sample_prepare_kernel<<<(unsigned)B, SP_THREADS, 0, st>>>(verts, (int)V, faces, (int)F, cum, areas);
+        launch_pdl(sample_prepare_kernel, dim3((unsigned)B), dim3(SP_THREADS), 0, st, verts, (int)V, faces, (int)F, cum, areas);
         PTK_CHECK_LAUNCH();
     }
     dim3 grid((unsigned)ceil_div(S, SP_THREADS), (unsigned)B);
-    sample_points_kernel<<<grid, SP_THREADS, 0, st>>>(verts, (int)V, faces, (int)F, cum, u_face, uv,
-                                                      uv + (size_t)B * S, (int)S, pts, face_idx);
+    launch_pdl(sample_points_kernel, grid, dim3(SP_THREADS), 0, st, verts, (int)V, faces, (int)F, cum, u_face, uv,
+               uv + (size_t)B * S, (int)S, pts, face_idx);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }
@@ -307,8 +310,8 @@ extern "C" int ptk_sample_bwd(const float *grad_pts, const int32_t *face_idx, co
     PTK_CHECK_CUDA(cudaMemsetAsync(grad_verts, 0, sizeof(float) * (size_t)B * V * 3, st));
     const int per_cta = 2048;
     dim3 grid((unsigned)ceil_div(S, per_cta), (unsigned)B);
-    sample_bwd_kernel<<<grid, SP_THREADS, 0, st>>>(grad_pts, face_idx, uv, uv + (size_t)B * S, faces,
-                                                   (int)V, (int)S, per_cta, grad_verts);
+    launch_pdl(sample_bwd_kernel, grid, dim3(SP_THREADS), 0, st, grad_pts, face_idx, uv, uv + (size_t)B * S, faces, (int)V,
+               (int)S, per_cta, grad_verts);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }
