@@ -9,6 +9,7 @@
 // TF32/BF16 tensor-core math; this file is the exact-FP32 FFMA implementation: 128x128x16 CTA
 // tiles, 8x8 register micro-tiles (2x2 blocks of 4x4 so that shared-memory reads are 128-bit and
 // conflict-free), register-staged global prefetch of the next k-tile.
+#include <cuda.h>
 #include <stdlib.h>
 
 #include "ptk_common.cuh"
@@ -303,6 +304,229 @@ static void launch_fwd(const float *X, const float *W, float *H, int64_t M, int6
 }
 
 // ------------------------------------------------------------------------------------------------
+// TMA-staged form of the exact forward (same arithmetic, same tile, same epilogue).  What limited the kernel above
+// was not the FFMA2 stream but everything around it: per 16-wide k-tile every thread ran ~150 integer instructions
+// of address / predicate arithmetic for its 2 LDG + 5 cp.async, 8 transposing STS and a CTA barrier -- ALU pipe
+// 21 %, FMA pipe 75 % (profiles/r01_ncu_sgemm_fwd_bm64.txt); ALU instructions do not dual-issue with the FMA pipe
+// on sm_100a.  Here one thread issues two cp.async.bulk.tensor copies per k-tile (A box 16 k x 64 rows, W box
+// 160 columns x 16 k; out-of-range rows / columns / k are zero-filled by the TMA unit) into a 4-stage ring guarded by
+// full / empty mbarriers; the 4 warps never meet at a CTA barrier.  A stays row-major in shared memory ([row][16 k]):
+// a thread reads one float4 of 4 consecutive k per row (8 LDS.128 per 4 k-steps -- the count the transposed layout
+// needed) and all 16 threads of a row group read the same address (broadcast).
+constexpr int FT_BM = 64, FT_STAGES = 4, FT_THREADS = 128;
+constexpr int FT_A_BYTES = FT_BM * FW_BK * 4;   // 4 KB   [64 rows][16 k]
+constexpr int FT_B_BYTES = FW_BK * FW_BN * 4;   // 10 KB  [16 k][160 columns]
+constexpr int FT_STAGE_BYTES = FT_A_BYTES + FT_B_BYTES;
+
+__device__ __forceinline__ uint32_t ft_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void ft_mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+
+// shared-space loads by 32-bit address: through C++ pointers derived from the aligned dynamic base the compiler
+// loses the address space and emits generic LD.E (measured: +10 us per launch)
+__device__ __forceinline__ ulonglong2 ft_lds128(uint32_t a) {
+    ulonglong2 v;
+    asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ unsigned long long ft_lds64(uint32_t a) {
+    unsigned long long v;
+    asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float2 ft_lds_f2(uint32_t a) {
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float4 ft_lds_f4(uint32_t a) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+    return v;
+}
+
+__global__ void __launch_bounds__(FT_THREADS, 3)
+sgemm_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                     float *__restrict__ Cm, int M, int N, int K, int ld1, int nsplit, float *__restrict__ C2, int ld2,
+                     int relu2, uint32_t *__restrict__ a_bits) {
+    extern __shared__ __align__(128) uint8_t ft_smem_raw[];
+    const uint32_t smem = (ft_smem_u32(ft_smem_raw) + 127u) & ~127u;  // shared-space address of stage 0
+    __shared__ __align__(8) uint64_t bars[2 * FT_STAGES];
+    __shared__ uint32_t sbits[FT_BM][FW_MAXW];
+    const uint32_t bar_full = ft_smem_u32(&bars[0]), bar_empty = ft_smem_u32(&bars[FT_STAGES]);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int m0 = blockIdx.y * FT_BM, n0 = blockIdx.x * FW_BN;
+    const int tx = tid % 16, ty = tid / 16;
+    const bool emit = a_bits != nullptr && blockIdx.x == 0;  // one column tile of CTAs is enough
+    const int num_kt = (K + FW_BK - 1) / FW_BK;
+    pdl_launch_dependents();
+    if (tid == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        for (int s = 0; s < FT_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * s), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_empty + 8 * s), "r"(FT_THREADS / 32));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (emit)
+        for (int e = tid; e < FT_BM * FW_MAXW; e += FT_THREADS) sbits[e / FW_MAXW][e % FW_MAXW] = 0u;
+    __syncthreads();
+    pdl_wait();  // A is the predecessor's output
+
+    auto issue = [&](int kt) {  // thread 0 only
+        const int s = kt % FT_STAGES;
+        const uint32_t dst = smem + (uint32_t)(s * FT_STAGE_BYTES), bar = bar_full + 8 * s;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(FT_STAGE_BYTES) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(dst), "l"(&map_a), "r"(bar), "r"(kt * FW_BK), "r"(m0) : "memory");
+        asm volatile(
+            "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+            ::"r"(dst + FT_A_BYTES), "l"(&map_w), "r"(bar), "r"(n0), "r"(kt * FW_BK) : "memory");
+    };
+    if (tid == 0)
+        for (int kt = 0; kt < FT_STAGES && kt < num_kt; ++kt) issue(kt);
+
+    unsigned long long acc[8][5];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 5; ++j) acc[i][j] = 0ull;
+
+    for (int kt = 0; kt < num_kt; ++kt) {
+        const int s = kt % FT_STAGES;
+        // refill the slot tile kt-2 lived in (one tile of slack: this thread rarely waits for the other warps)
+        if (tid == 0 && kt >= 2 && kt - 2 + FT_STAGES < num_kt) {
+            ft_mbar_wait(bar_empty + 8 * ((kt - 2) % FT_STAGES), ((kt - 2) / FT_STAGES) & 1);
+            issue(kt - 2 + FT_STAGES);
+        }
+        ft_mbar_wait(bar_full + 8 * s, (kt / FT_STAGES) & 1);
+        const uint32_t As = smem + (uint32_t)(s * FT_STAGE_BYTES);   // [64 rows][16 k] fp32
+        const uint32_t Bs = As + FT_A_BYTES;                          // [16 k][160 columns] fp32
+        if (emit) {
+            // ReLU mask bits of this k-tile of A (see sgemm_fwd_kernel): thread = (row, 8-k half)
+            const int r = tid >> 1, h8 = tid & 1;
+            const float4 v0 = ft_lds_f4(As + 4u * (uint32_t)(r * FW_BK + h8 * 8));
+            const float4 v1 = ft_lds_f4(As + 4u * (uint32_t)(r * FW_BK + h8 * 8 + 4));
+            uint32_t h = ((v0.x > 0.f ? 1u : 0u) | (v0.y > 0.f ? 2u : 0u) | (v0.z > 0.f ? 4u : 0u) | (v0.w > 0.f ? 8u : 0u) |
+                          (v1.x > 0.f ? 16u : 0u) | (v1.y > 0.f ? 32u : 0u) | (v1.z > 0.f ? 64u : 0u) |
+                          (v1.w > 0.f ? 128u : 0u)) << (h8 * 8);
+            h |= __shfl_xor_sync(0xffffffffu, h, 1);
+            if (h8 == 0) reinterpret_cast<unsigned short *>(&sbits[r][0])[kt] = (unsigned short)h;
+        }
+#pragma unroll
+        for (int kq = 0; kq < FW_BK / 2; ++kq) {
+            float2 a2v[8];  // 2 k-steps of this thread's 8 rows (float4 = 4 k-steps spilled at the 168-register cap)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int r = i < 4 ? ty * 4 + i : FT_BM / 2 + ty * 4 + (i - 4);
+                a2v[i] = ft_lds_f2(As + 4u * (uint32_t)(r * FW_BK + kq * 2));
+            }
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk) {
+                const uint32_t brow = Bs + 4u * (uint32_t)((kq * 2 + kk) * FW_BN);
+                const ulonglong2 b0 = ft_lds128(brow + 4u * (uint32_t)(tx * 4));
+                const ulonglong2 b1 = ft_lds128(brow + 4u * (uint32_t)(64 + tx * 4));
+                const unsigned long long b2 = ft_lds64(brow + 4u * (uint32_t)(128 + tx * 2));
+                const unsigned long long bv[5] = {b0.x, b0.y, b1.x, b1.y, b2};
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const float a = kk == 0 ? a2v[i].x : a2v[i].y;
+                        unsigned long long a2;
+                        asm("mov.b64 %0, {%1, %1};" : "=l"(a2) : "f"(a));
+                        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc[i][j]) : "l"(a2), "l"(bv[j]));
+                    }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_empty + 8 * s) : "memory");
+    }
+    if (emit) {
+        __syncthreads();
+        const int wpr = (K + 31) >> 5;
+        for (int e = tid; e < FT_BM * wpr; e += FT_THREADS) {
+            const int r = e / wpr, w = e - r * wpr;
+            if (m0 + r < M) a_bits[(size_t)(m0 + r) * wpr + w] = sbits[r][w];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int m = m0 + (i < 4 ? ty * 4 + i : FT_BM / 2 + ty * 4 + (i - 4));
+        if (m >= M) continue;
+        float *row1 = Cm + (size_t)m * ld1;
+        float *row2 = C2 + (size_t)m * ld2;
+        const int na = n0 + tx * 4, nb = n0 + 64 + tx * 4, nc = n0 + 128 + tx * 2;
+        auto relu_pair = [&](unsigned long long v) {
+            if (!relu2) return v;
+            float lo = __uint_as_float((unsigned)v), hi = __uint_as_float((unsigned)(v >> 32));
+            lo = fmaxf(lo, 0.f);
+            hi = fmaxf(hi, 0.f);
+            return ((unsigned long long)__float_as_uint(hi) << 32) | __float_as_uint(lo);
+        };
+        auto put4 = [&](int n, unsigned long long a, unsigned long long b) {
+            if (n + 3 >= N) return;
+            if (n < nsplit)
+                *reinterpret_cast<ulonglong2 *>(row1 + n) = make_ulonglong2(a, b);
+            else
+                *reinterpret_cast<ulonglong2 *>(row2 + n) = make_ulonglong2(relu_pair(a), relu_pair(b));
+        };
+        put4(na, acc[i][0], acc[i][1]);
+        put4(nb, acc[i][2], acc[i][3]);
+        if (nc + 1 < N) {
+            if (nc < nsplit)
+                *reinterpret_cast<unsigned long long *>(row1 + nc) = acc[i][4];
+            else
+                *reinterpret_cast<unsigned long long *>(row2 + nc) = relu_pair(acc[i][4]);
+        }
+    }
+}
+
+int make_tensor_map_2d(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int box_cols, int box_rows,
+                       bool swizzle);  // gemm_tf32x3.cu
+
+static unsigned long long g_ft_optin = 0ull;  // cudaFuncAttributeMaxDynamicSharedMemorySize is per device
+
+static int launch_fwd_tma(const float *X, const float *W, float *H, int64_t M, int64_t K, int64_t N, cudaStream_t st,
+                          int ld1 = 0, int nsplit = -1, float *C2 = nullptr, int ld2 = 0, int relu2 = 0,
+                          uint32_t *a_bits = nullptr) {
+    CUtensorMap map_a, map_w;
+    int rc = make_tensor_map_2d(&map_a, X, M, K, FW_BK, FT_BM, false);
+    if (rc) return rc;
+    rc = make_tensor_map_2d(&map_w, W, K, N, FW_BN, FW_BK, false);
+    if (rc) return rc;
+    if (nsplit < 0) {
+        nsplit = (int)N;
+        ld1 = (int)N;
+        C2 = H;
+        ld2 = (int)N;
+    }
+    const size_t smem = (size_t)FT_STAGES * FT_STAGE_BYTES + 128;
+    int dev = 0;
+    PTK_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev >= 64 || !((g_ft_optin >> dev) & 1ull)) {
+        PTK_CHECK_CUDA(cudaFuncSetAttribute(sgemm_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (dev < 64) g_ft_optin |= 1ull << dev;
+    }
+    dim3 grid((unsigned)ceil_div(N, FW_BN), (unsigned)ceil_div(M, FT_BM));
+    launch_pdl(sgemm_fwd_tma_kernel, grid, dim3(FT_THREADS), smem, st, map_a, map_w, H, (int)M, (int)N, (int)K, ld1, nsplit,
+               C2, ld2, relu2, K <= 32 * FW_MAXW ? a_bits : nullptr);
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Skinny layers (N <= 4: the 300 -> 3 output layer of every GCN, vision/model.py:296-301).  As GEMMs they are
 // matrix-vector shaped and HBM/L2-bound; the tiled kernels above spend 80 us on them, these take ~10 us.
 //   forward : one warp per row, 128-bit loads of X, W (K x N) in shared memory, warp reduction
@@ -414,6 +638,7 @@ extern "C" int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int
         // 136 us (BM 32) and cuBLAS FP32 127 us at M=31184, K=N=300.
         int best = 64;
         if (PTK_TUNING_ENV("PTK_FWD_BM") > 0) best = PTK_TUNING_ENV("PTK_FWD_BM");  // tools/gemm_check.py sweeps
+        if (best == 64 && !PTK_TUNING_ENV("PTK_FWD_NO_TMA")) return launch_fwd_tma(X, W, H, M, K, N, as_stream(stream));
         if (best == 32) launch_fwd<32>(X, W, H, M, K, N, as_stream(stream));
         else if (best == 64) launch_fwd<64>(X, W, H, M, K, N, as_stream(stream));
         else if (best == 128) launch_fwd<128>(X, W, H, M, K, N, as_stream(stream));
@@ -447,6 +672,8 @@ extern "C" int ptk_gcn_linear_fwd_split(const float *X, const float *W, int64_t 
     PTK_REQUIRE((((uintptr_t)X | (uintptr_t)W | (uintptr_t)head | (uintptr_t)out) % 16) == 0, PTK_ERR_ALIGN,
                 "gcn_linear_fwd_split: pointers must be 16-byte aligned");
     PTK_REQUIRE(!x_bits || K <= 32 * FW_MAXW, PTK_ERR_SHAPE, "gcn_linear_fwd_split: x_bits needs K <= %d", 32 * FW_MAXW);
+    if (!PTK_TUNING_ENV("PTK_FWD_NO_TMA"))
+        return launch_fwd_tma(X, W, head, M, K, N, as_stream(stream), (int)n_split, (int)n_split, out, (int)N, relu, x_bits);
     launch_fwd<64>(X, W, head, M, K, N, as_stream(stream), (int)n_split, (int)n_split, out, (int)N, relu, x_bits);
     PTK_CHECK_LAUNCH();
     return PTK_OK;

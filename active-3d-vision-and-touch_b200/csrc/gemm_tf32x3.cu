@@ -685,6 +685,12 @@ static int make_map_ex(CUtensorMap *map, const float *base, int64_t rows, int64_
     return PTK_OK;
 }
 
+// for the other translation units (gcn_linear.cu: TMA-staged exact forward)
+int make_tensor_map_2d(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int box_cols, int box_rows,
+                       bool swizzle) {
+    return make_map_ex(map, base, rows, cols, box_cols, box_rows, swizzle);
+}
+
 // bits[row * wpr + j] bit i = act[row, 32 j + i] > 0 (0 beyond N).  One warp per row, coalesced.
 __global__ void __launch_bounds__(256)
 relu_bits_kernel(const float *__restrict__ act, long long M, int N, int wpr, uint32_t *__restrict__ bits) {
