@@ -195,6 +195,93 @@ def nerf_embed(points):
     return _NerfEmbed.apply(points.reshape(-1, 3)).reshape(*points.shape[:-1], 63)
 
 
+# ------------------------------------------------------------------------------------- fused vertex-feature front
+VERTEX_FRONT_MAX_H1, VERTEX_FRONT_MAX_H2 = 112, 224  # csrc/vertex_front.cu
+
+
+class _VertexFront(torch.autograd.Function):
+    """positions (M,3) [, mask (M,), emb (4,S), add (M,S)] -> (M,S): NeRF embedding, the three Linear layers of
+    Positional_Encoder, the mask-token embedding row and the optional additive features in one launch
+    (ptk_vertex_front_fwd).  Backward: column sums per mask token (ptk_vertex_front_colsum: embedding-table and last
+    bias gradient), the library's own GEMM kernels for the weight / data gradients, ptk_nerf_embed_bwd."""
+
+    @staticmethod
+    def forward(ctx, pos, mask, w1, b1, w2, b2, w3, b3, emb, add):
+        _need_cuda(pos, mask, w1, b1, w2, b2, w3, b3, emb, add)
+        pos, w1, b1, w2, b2, w3, b3 = (_f32c(t) for t in (pos, w1, b1, w2, b2, w3, b3))
+        mask = _f32c(mask) if mask is not None else None
+        emb = _f32c(emb) if emb is not None else None
+        add = _f32c(add) if add is not None else None
+        M, h1, h2, S = pos.shape[0], w1.shape[0], w2.shape[0], w3.shape[0]
+        if w1.shape[1] != 63 or w2.shape[1] != h1 or w3.shape[1] != h2:
+            raise ValueError("vertex_front: weight shapes must be (h1,63), (h2,h1), (S,h2)")
+        if emb is not None and (mask is None or tuple(emb.shape) != (4, S) or mask.numel() != M):
+            raise ValueError("vertex_front: emb must be (4,S) and come with a mask of M tokens")
+        if add is not None and tuple(add.shape) != (M, S):
+            raise ValueError("vertex_front: add must be (M,S)")
+        train = any(ctx.needs_input_grad)
+        out = torch.empty(M, S, dtype=torch.float32, device=pos.device)
+        h1s = torch.empty(M, h1, dtype=torch.float32, device=pos.device) if train else None
+        h2s = torch.empty(M, h2, dtype=torch.float32, device=pos.device) if train else None
+        with torch.cuda.device(pos.device):
+            _lib.check(_lib.lib().ptk_vertex_front_fwd(_p(pos), _p(mask), _p(w1), _p(b1), _p(w2), _p(b2), _p(w3), _p(b3),
+                                                       _p(emb), _p(add), M, h1, h2, S, _p(out), _p(h1s), _p(h2s),
+                                                       _stream()), "ptk_vertex_front_fwd")
+        if train:
+            # the reference updates `vertices` in place right after encoding them (vision/model.py:250,270,283):
+            # keep a private copy of the positions for the backward
+            ctx.save_for_backward(pos.clone(), mask, w1, w2, w3, h1s, h2s)
+            ctx.has_emb = emb is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        pos, mask, w1, w2, w3, h1s, h2s = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        g = _f32c(g)
+        M, S = g.shape
+        L = _lib.lib()
+        with torch.cuda.device(g.device):
+            sums = torch.empty(4, S, dtype=torch.float32, device=g.device)
+            ws = _ws(L.ptk_vertex_front_colsum_workspace_bytes(M, S), g.device)
+            _lib.check(L.ptk_vertex_front_colsum(_p(g), _p(mask if ctx.has_emb else None), M, S, _p(sums), _p(ws),
+                                                 ws.numel(), _stream()), "ptk_vertex_front_colsum")
+            gb3 = sums.sum(0)
+            gemb = sums if ctx.has_emb else None
+            gw3 = _linear_wgrad(g, h2s)                                  # (S, h2): nn.Linear layout
+            gh2 = _linear_dgrad(g, w3.t().contiguous(), h2s)            # (M, h2), ReLU mask of hidden 2 fused
+            gb2 = _bias_grad(gh2, gh2.shape[1])
+            gw2 = _linear_wgrad(gh2, h1s)
+            gh1 = _linear_dgrad(gh2, w2.t().contiguous(), h1s)
+            gb1 = _bias_grad(gh1, gh1.shape[1])
+            x0 = torch.empty(M, 63, dtype=torch.float32, device=g.device)
+            _lib.check(L.ptk_nerf_embed_fwd(_p(pos), M, _p(x0), _stream()), "ptk_nerf_embed_fwd")
+            gw1 = _linear_wgrad(gh1, x0)
+            gpos = None
+            if need[0]:
+                gx0 = _linear_fwd(gh1, w1, algo_id=GEMM_AUTO)           # (M,h1) . (h1,63)
+                gpos = torch.empty_like(pos)
+                _lib.check(L.ptk_nerf_embed_bwd(_p(pos), _p(gx0), M, _p(gpos), _stream()), "ptk_nerf_embed_bwd")
+        return gpos, None, gw1, gb1, gw2, gb2, gw3, gb3, gemb, (g if need[9] else None)
+
+
+def vertex_front(positions, mask, w1, b1, w2, b2, w3, b3, emb=None, add=None):
+    """(B,N,3) positions [+ (B,N,1) mask tokens, (4,S) embedding table, (B,N,S) additive features] -> (B,N,S):
+    Positional_Encoder(positions) + Mask_Encoder(mask) [+ img_features] of Deformation.forward
+    (vision/model.py:229-236) in one launch."""
+    if positions.shape[-1] != 3:
+        raise ValueError(f"positions must end in a dimension of 3, got {tuple(positions.shape)}")
+    lead = positions.shape[:-1]
+    S = w3.shape[0]
+    out = _VertexFront.apply(positions.reshape(-1, 3), mask.reshape(-1) if mask is not None else None, w1, b1, w2, b2,
+                             w3, b3, emb, add.reshape(-1, S) if add is not None else None)
+    return out.reshape(*lead, S)
+
+
+def vertex_front_supported(input_size):
+    return input_size // 4 >= 1 and input_size // 4 <= VERTEX_FRONT_MAX_H1 and input_size // 2 <= VERTEX_FRONT_MAX_H2
+
+
 # ------------------------------------------------------------------------------------- surface sampling
 class _Sample(torch.autograd.Function):
     @staticmethod

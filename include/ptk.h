@@ -300,6 +300,27 @@ int ptk_nerf_embed_bwd(const float *positions, const float *grad_out, int64_t M,
                        ptk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Vertex-feature front of the deformation network in one launch (csrc/vertex_front.cu):
+ *   out (M,width) = Linear3(relu(Linear2(relu(Linear1(nerf_embed(positions)))))) + emb[(int)mask] + add
+ * Replaces Positional_Encoder.forward (pterotactyl/reconstruction/vision/model.py:393-399: embedding + cat +
+ * Linear(63,h1)+ReLU, Linear(h1,h2)+ReLU, Linear(h2,width)), Mask_Encoder.forward (model.py:410-414: Embedding(4,
+ * width) of mask.long()) and the feature additions of Deformation.forward (model.py:234-236, 266-267, 277-279).
+ * Weights in nn.Linear layout (out,in) row-major; mask (M) floats (truncated like .long(), clamped to 0..3), emb
+ * (4,width) and add (M,width) may be NULL.  h1 <= 112, h2 <= 224.  h1_save (M,h1) / h2_save (M,h2), when given,
+ * receive the hidden activations (after ReLU) for the backward.
+ * ptk_vertex_front_colsum: sums (4,width), sums[t][n] = sum of g[m][n] over rows whose mask token is t (all rows
+ * count as token 0 when mask is NULL) -- the gradient of the embedding table; its column total is the gradient of
+ * the last bias.  Fixed-order two-stage reduction (deterministic).
+ * ---------------------------------------------------------------------------------------------- */
+int ptk_vertex_front_fwd(const float *positions, const float *mask, const float *w1, const float *b1,
+                         const float *w2, const float *b2, const float *w3, const float *b3, const float *emb,
+                         const float *add, int64_t M, int32_t h1, int32_t h2, int32_t width, float *out,
+                         float *h1_save, float *h2_save, ptk_stream_t stream);
+size_t ptk_vertex_front_colsum_workspace_bytes(int64_t M, int32_t width);
+int ptk_vertex_front_colsum(const float *g, const float *mask, int64_t M, int32_t width, float *sums,
+                            void *workspace, size_t workspace_bytes, ptk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (end-to-end path: H2D + kernels + D2H inside the call).
  * All pointers are HOST pointers (pinned memory makes the copies asynchronous and faster).
  * ---------------------------------------------------------------------------------------------- */

@@ -16,7 +16,20 @@ def timeit(fn, iters):
     b.record(); torch.cuda.synchronize()
     return a.elapsed_time(b) / iters
 
-print(f"{'P':>7} {'B':>4} {'fwd ms':>10} {'fwd+bwd ms':>11} {'pairs/s':>10} {'Tevals/s':>9} {'rescued %':>9}  checks")
+def graph_time(fn, iters):
+    """GPU time of fn replayed from a CUDA graph: what the kernels cost without the eager host path (autograd
+    engine, ctypes, allocator) -- every ptk_b200 op is capture-safe."""
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        fn(); fn()
+    torch.cuda.current_stream().wait_stream(s)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    return timeit(g.replay, iters)
+
+print(f"{'P':>7} {'B':>4} {'fwd ms':>10} {'fwd+bwd ms':>11} {'graph ms':>9} {'pairs/s':>10} {'Tevals/s':>9} {'rescued %':>9}  checks")
 for P in (1000, 2000, 5000, 10000, 20000, 50000, 100000):
     for B in (1, 4, 16, 64, 256):
         if B * P * P > 256 * 20000 * 20000 * 1.1:   # keep the sweep within a few seconds per cell
@@ -33,6 +46,7 @@ for P in (1000, 2000, 5000, 10000, 20000, 50000, 100000):
             c, _, _ = ptk_b200.ops.chamfer(x, y)
             c.sum().backward()
         tf, tb = timeit(fwd, iters), timeit(both, iters)
+        tg = graph_time(both, iters) if B * P <= 64 * 10000 else float("nan")
         cham, ix, iy = fwd()
         ar = torch.arange(B, device=dev)[:, None]
         dx = ((x - y[ar, ix.long()]) ** 2).sum(-1).mean(1)
@@ -43,6 +57,6 @@ for P in (1000, 2000, 5000, 10000, 20000, 50000, 100000):
         q = x[0, :32].detach()
         ok3 = torch.equal(((q[:, None] - y[0].detach()[None]) ** 2).sum(-1).argmin(1).int(), ix[0, :32])
         resc = ptk_b200.ops.chamfer_rescued(x.detach(), y.detach()) / (2.0 * B * P)
-        print(f"{P:7d} {B:4d} {tf:10.3f} {tb:11.3f} {B / (tb * 1e-3):10.1f} {2.0 * B * P * P / (tf * 1e-3) / 1e12:9.3f} "
+        print(f"{P:7d} {B:4d} {tf:10.3f} {tb:11.3f} {tg:9.3f} {B / (tb * 1e-3):10.1f} {2.0 * B * P * P / (tf * 1e-3) / 1e12:9.3f} "
               f"{100 * resc:9.3f}  {'ok' if (ok1 and ok2 and ok3) else 'FAIL'}", flush=True)
         del x, y
