@@ -229,11 +229,9 @@ static int launch_nn(const float *x, const float *y, int64_t B, int64_t P1, int6
     NNPlan p = plan_nn(B, Pq, Pt, ndir, filter ? CH_MINB_F : CH_MINB);
     u64 *keys_x = dir_only == 1 ? nullptr : w.keys_x;
     u64 *keys_y = dir_only == 0 ? nullptr : w.keys_y;
-    if (p.n_split > 1) {
+    if (p.n_split > 1 && !filter) {  // (the filter path initialises keys and flags in chamfer_prep_kernel)
         if (keys_x) PTK_CHECK_CUDA(cudaMemsetAsync(keys_x, 0xff, sizeof(u64) * B * P1, st));
         if (keys_y) PTK_CHECK_CUDA(cudaMemsetAsync(keys_y, 0xff, sizeof(u64) * B * P2, st));
-        if (filter)  // flag_x and flag_y are adjacent
-            PTK_CHECK_CUDA(cudaMemsetAsync(w.flag_x, 0, sizeof(unsigned int) * B * (P1 + P2), st));
     }
     dim3 grid((unsigned)ceil_div(Pq, (int64_t)CH_THREADS * p.R), (unsigned)p.n_split,
               (unsigned)(B * ndir));
@@ -245,7 +243,7 @@ static int launch_nn(const float *x, const float *y, int64_t B, int64_t P1, int6
         PTK_CHECK_LAUNCH();
         const int Pp = soa_padded(iP1 > iP2 ? iP1 : iP2);
         launch_pdl(chamfer_prep_kernel, dim3((unsigned)ceil_div(Pp, 256), (unsigned)(2 * B)), dim3(256), 0, st, x, y, iP1, iP2,
-                   w.aux, w.soa_x, w.soa_y);
+                   w.aux, w.soa_x, w.soa_y, keys_x, keys_y, w.flag_x, w.flag_y, p.n_split > 1 ? 1 : 0);
         PTK_CHECK_LAUNCH();
 #define PTK_FILTER(RR)                                                                                          \
     launch_pdl(chamfer_nn_filter_tma_kernel<RR, CH_CHUNK, CH_THREADS, CH_MINB_F, CH_TT_F>, grid, dim3(CH_THREADS), 0, st, \

@@ -346,7 +346,9 @@ __host__ __device__ inline int soa_padded(int P) { return (P + SOA_PAD - 1) / SO
 // grid (ceil(Ppad_max / 256), 2 * B): blockIdx.y = 2 * b + cloud
 __global__ void __launch_bounds__(256)
 chamfer_prep_kernel(const float *__restrict__ x, const float *__restrict__ y, int P1, int P2,
-                    const PairAux *__restrict__ aux, float *__restrict__ soa_x, float *__restrict__ soa_y) {
+                    const PairAux *__restrict__ aux, float *__restrict__ soa_x, float *__restrict__ soa_y,
+                    u64 *__restrict__ keys_x, u64 *__restrict__ keys_y, unsigned int *__restrict__ flag_x,
+                    unsigned int *__restrict__ flag_y, int init_keys) {
     pdl_wait();  // launched with programmatic stream serialization (ptk_common.cuh)
     const int b = blockIdx.y >> 1, cloud = blockIdx.y & 1;
     const int P = cloud == 0 ? P1 : P2;
@@ -367,6 +369,14 @@ chamfer_prep_kernel(const float *__restrict__ x, const float *__restrict__ y, in
     dst[Pp + i] = ty;
     dst[2 * Pp + i] = tz;
     dst[3 * Pp + i] = tt;
+    // split target ranges merge by atomicMin on the key and dedup their rescue entries through the flag: this
+    // point's slots start at "nothing found" / "not queued" (three memsets per forward before)
+    if (init_keys && i < P) {
+        u64 *keys = cloud == 0 ? keys_x : keys_y;
+        unsigned int *flag = cloud == 0 ? flag_x : flag_y;
+        if (keys) keys[(size_t)b * P + i] = ~0ull;
+        if (flag) flag[(size_t)b * P + i] = 0u;
+    }
 }
 
 __device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -382,7 +382,7 @@ gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__r
                           const float *__restrict__ val, const AggHubs hb, unsigned hub_slots, int Nv,
                           const float *__restrict__ in, int B, int C, int L, const float *__restrict__ bias,
                           int relu, float *__restrict__ out, int TV, int BG, int n_tiles, int hubs_first, int ldi,
-                          int ldo, int warp_is_batch) {
+                          int ldo, int warp_is_batch, int prefetch_next) {
     // ldi / ldo: row strides (floats) of in / out; C channels are handled ([0, L) aggregated, [L, C) passed through)
     __shared__ __align__(16) uint32_t s_off[AG_WARPS][AT_STRIP];
     __shared__ __align__(16) float s_w[AG_WARPS][AT_STRIP];
@@ -576,7 +576,14 @@ gcn_aggregate_tile_kernel(const int32_t *__restrict__ rowptr, const int32_t *__r
         if (end - beg <= AT_STRIP) n4 = strip_stage(col, val, beg, end - beg, row_bytes, s_off[warp], s_w[warp]);
         const float *inb = in + b0 * bstride;
         float *outb = out + b0 * bstride_o;
+        const int row_lines = (int)((ngroups * 16 + 127) >> 7);  // 128-byte lines of one input row
         for (int bb = 0; bb < nb; ++bb, inb += bstride, outb += bstride_o) {
+            // The next batch element's copy of this row is its first touch (a DRAM miss): ask L2 for it now, one
+            // row (~2.5 us of this warp's work) ahead -- no registers held, unlike a software-pipelined load.
+            // Every row of `in` is requested this way by the warp that owns it, so the neighbour gathers of the
+            // other warps find their rows in L2 as well.
+            if (prefetch_next && bb + 1 < nb && lane < row_lines)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(inb + bstride + (size_t)i * ldi) + lane * 128));
             float acc[NG][4];
 #pragma unroll
             for (int n = 0; n < NG; ++n) acc[n][0] = acc[n][1] = acc[n][2] = acc[n][3] = 0.f;
@@ -770,13 +777,17 @@ extern "C" int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, c
         // and -3 % on the plain vision graph at L=99 -> used for the wide case only
         int warp_is_batch = TV == AG_WARPS && BG == AG_WARPS && gath > 32;
         if (PTK_TUNING_ENV("PTK_AGG_WB") > 0) warp_is_batch = PTK_TUNING_ENV("PTK_AGG_WB") == 1;
+        // L2 prefetch of the next batch element's row: only where the input does not live in L2 anyway
+        int prefetch_next = !hubs_first;
+        if (PTK_TUNING_ENV("PTK_AGG_PF") > 0) prefetch_next = PTK_TUNING_ENV("PTK_AGG_PF") == 1;
         AggHubs hb;
         hb.hubs = hubs; hb.n_hubs = have_hubs ? n_hubs : 0;
         hb.common_col = common_col; hb.common_w = common_w; hb.n_common = common ? n_common : 0;
         hb.alpha = hub_alpha; hb.row_skip = common ? row_skip : nullptr;
 #define PTK_TILE(NGv)                                                                                        \
     launch_pdl(gcn_aggregate_tile_kernel<NGv>, dim3(grid), dim3(AG_THREADS), 0, st, rowptr, col, val, hb, hub_slots, (int)Nv, in, \
-               (int)B, (int)C, (int)L, bias, relu, out, TV, BG, n_tiles, hubs_first, (int)ldi, (int)ldo, warp_is_batch)
+               (int)B, (int)C, (int)L, bias, relu, out, TV, BG, n_tiles, hubs_first, (int)ldi, (int)ldo, warp_is_batch, \
+               prefetch_next)
         if (gath <= 32) PTK_TILE(1);
         else if (gath <= 64) PTK_TILE(2);
         else PTK_TILE(3);

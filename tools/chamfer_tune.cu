@@ -174,7 +174,7 @@ void run_tma(const char *name, const float *x, const float *y, int B, int P, uns
     dim3 pgrid((Pp + 255) / 256, 2 * B);
     auto launch = [&]() {
         chamfer_bounds_kernel<<<B, 1024>>>(x, y, P, P, aux, rcount);
-        chamfer_prep_kernel<<<pgrid, 256>>>(x, y, P, P, aux, soa_x, soa_y);
+        chamfer_prep_kernel<<<pgrid, 256>>>(x, y, P, P, aux, soa_x, soa_y, nullptr, nullptr, nullptr, nullptr, 0);
         chamfer_nn_filter_tma_kernel<R, CHUNK, THREADS, MINB, TT><<<grid, THREADS>>>(x, y, P, P, split_len, 1, aux, soa_x, soa_y, kx, ky, -1, rescue, rescue + (size_t)B * P, rcount, nullptr, nullptr);
         chamfer_nn_exact2_kernel<8, 16, 128, 3><<<rgrid, 128>>>(x, y, P, P, split_len, 1, kx, ky, -1, rescue, rescue + (size_t)B * P, rcount);
     };
