@@ -18,7 +18,8 @@ class GcnCsr(C.Structure):
     """ptk_gcn_csr of include/ptk.h: one direction of the adjacency, plain CSR + kernel form."""
     _fields_ = [("rowptr", _vp), ("col", _vp), ("val", _vp), ("hubs", _vp), ("n_hubs", _i32),
                 ("k_rowptr", _vp), ("k_col", _vp), ("k_val", _vp), ("k_hubs", _vp), ("k_n_hubs", _i32),
-                ("common_col", _vp), ("common_w", _vp), ("n_common", _i32), ("alpha", _vp), ("row_skip", _vp)]
+                ("common_col", _vp), ("common_w", _vp), ("n_common", _i32), ("alpha", _vp), ("row_skip", _vp),
+                ("tile_uptr", _vp), ("tile_ucol", _vp), ("tile_lidx", _vp), ("max_union", _i32)]
 
 
 # name -> (restype, argtypes); mirrors include/ptk.h one to one (tests check the two stay in sync)
@@ -42,6 +43,8 @@ SIGNATURES = {
     "ptk_gcn_aggregate": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i64, _i64, _i64, _vp, C.c_int, _vp, _vp]),
     "ptk_gcn_aggregate_ex": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp,
                                        C.c_int, _vp, _i64, _i64, _vp]),
+    "ptk_gcn_aggregate_tiled": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp,
+                                          _i64, _i64, _i64, _vp, C.c_int, _vp, _i64, _i64, _vp]),
     "ptk_gcn_linear_fwd_split": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, C.c_int, _vp, _vp]),
     "ptk_gcn_bias_grad_workspace_bytes": (_sz, [_i64, _i64]),
     "ptk_gcn_bias_grad": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),

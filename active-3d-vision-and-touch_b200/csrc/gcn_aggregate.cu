@@ -20,13 +20,9 @@
 // they do not become the tail of the launch.
 #include <stdlib.h>
 
-#include "ptk_common.cuh"
+#include "gcn_aggregate_common.cuh"
 
 namespace ptk {
-
-constexpr int AG_THREADS = 256;
-constexpr int AG_WARPS = AG_THREADS / 32;
-constexpr int HUB_DEG = 128;
 
 // Gather for one row restricted to the warp `part` of `nparts` (nparts = 1: the whole row).
 template <bool VEC>
@@ -264,117 +260,6 @@ __device__ __forceinline__ void hub_cta(const int32_t *__restrict__ rowptr, cons
 //     neighbour rows they share (19-vertex charts) are served by L1;
 //   * rows of degree > HUB_DEG are left to dedicated hub CTAs at the front of the grid (8 warps split the
 //     neighbour list, fixed-order shared-memory reduction => deterministic).
-constexpr int AT_STRIP = 128;  // staged neighbours per warp (= HUB_DEG: a non-hub row fits)
-
-template <int NG>
-__device__ __forceinline__ void strip_gather(const uint32_t *__restrict__ s_off, const float *__restrict__ s_w,
-                                             int n4, const char *const (&base)[NG], float (&acc)[NG][4]) {
-    // n4: staged entries, a multiple of 4 (padding has weight 0 and a valid offset).  base[n] already
-    // includes the lane's channel-group offset; lanes beyond the last aggregated group are clamped onto it
-    // (same cache lines, result discarded), which keeps the loop free of divergent branches.
-    int k = 0;
-    for (; k + 8 <= n4; k += 8) {
-        const uint4 o0 = *reinterpret_cast<const uint4 *>(s_off + k), o1 = *reinterpret_cast<const uint4 *>(s_off + k + 4);
-        const float4 w0 = *reinterpret_cast<const float4 *>(s_w + k), w1 = *reinterpret_cast<const float4 *>(s_w + k + 4);
-        const uint32_t off[8] = {o0.x, o0.y, o0.z, o0.w, o1.x, o1.y, o1.z, o1.w};
-        const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-#pragma unroll
-        for (int n = 0; n < NG; ++n) {
-            float4 a[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) a[u] = *reinterpret_cast<const float4 *>(base[n] + off[u]);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                acc[n][0] = fmaf(w[u], a[u].x, acc[n][0]); acc[n][1] = fmaf(w[u], a[u].y, acc[n][1]);
-                acc[n][2] = fmaf(w[u], a[u].z, acc[n][2]); acc[n][3] = fmaf(w[u], a[u].w, acc[n][3]);
-            }
-        }
-    }
-    if (k < n4) {
-        const uint4 o0 = *reinterpret_cast<const uint4 *>(s_off + k);
-        const float4 w0 = *reinterpret_cast<const float4 *>(s_w + k);
-        const uint32_t off[4] = {o0.x, o0.y, o0.z, o0.w};
-        const float w[4] = {w0.x, w0.y, w0.z, w0.w};
-#pragma unroll
-        for (int n = 0; n < NG; ++n) {
-            float4 a[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) a[u] = *reinterpret_cast<const float4 *>(base[n] + off[u]);
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                acc[n][0] = fmaf(w[u], a[u].x, acc[n][0]); acc[n][1] = fmaf(w[u], a[u].y, acc[n][1]);
-                acc[n][2] = fmaf(w[u], a[u].z, acc[n][2]); acc[n][3] = fmaf(w[u], a[u].w, acc[n][3]);
-            }
-        }
-    }
-}
-
-// Stage entries [e0, e0+cnt) of a row into the warp's strip (cnt <= AT_STRIP), padded to a multiple of 4.
-__device__ __forceinline__ int strip_stage(const int32_t *__restrict__ col, const float *__restrict__ val, int e0,
-                                           int cnt, uint32_t row_bytes, uint32_t *s_off, float *s_w) {
-    const int lane = threadIdx.x & 31;
-    const int n4 = (cnt + 3) & ~3;
-    __syncwarp();
-    for (int e = lane; e < n4; e += 32) {
-        const bool real = e < cnt;
-        s_off[e] = (uint32_t)col[e0 + (real ? e : 0)] * row_bytes;
-        s_w[e] = real ? val[e0 + e] : 0.f;
-    }
-    __syncwarp();
-    return n4;
-}
-
-// Epilogue of one output row: aggregated groups (+bias, boundary group mixes in the pass-through channels).
-template <int NG>
-__device__ __forceinline__ void row_epilogue(const float (&acc)[NG][4], const bool (&on)[NG], const float *__restrict__ self,
-                                             float *__restrict__ o, const float *__restrict__ bias, int L, int relu) {
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int n = 0; n < NG; ++n) {
-        if (!on[n]) continue;
-        const int c0 = (lane + 32 * n) * 4;
-        float r[4] = {acc[n][0], acc[n][1], acc[n][2], acc[n][3]};
-        if (bias) {
-            const float4 bv = *reinterpret_cast<const float4 *>(bias + c0);
-            r[0] += bv.x; r[1] += bv.y; r[2] += bv.z; r[3] += bv.w;
-        }
-        if (c0 + 4 > L) {  // boundary group: channels >= L pass through
-            const float4 s = *reinterpret_cast<const float4 *>(self + c0);
-            const float sv[4] = {s.x, s.y, s.z, s.w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (c0 + k >= L) r[k] = sv[k];
-        }
-        if (relu) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) r[k] = fmaxf(r[k], 0.f);
-        }
-        __stcs(reinterpret_cast<float4 *>(o + c0), make_float4(r[0], r[1], r[2], r[3]));
-    }
-}
-
-__device__ __forceinline__ float4 relu4(float4 s, int relu) {
-    if (relu) {
-        s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f);
-    }
-    return s;
-}
-
-// Hub rows with a shared neighbour set ("common set").  The touch-chart centre vertices are each linked to
-// ALL boundary vertices (utils.py:126-128): the 5 (finger) or 20 (grasp) hub rows of the fused graph read
-// the same ~1150 neighbour rows.  When the host finds such a set S with val[h,j] = alpha[h] * cw[j] on it
-// (graph.py), one hub CTA per batch element computes  y* = sum_{j in S} cw[j] x_j  ONCE, and every hub row
-// becomes  alpha[h] * y* + (its few remaining neighbours, kept in the reduced CSR)  -- 1/n_hubs of the
-// gather traffic.  Rows flagged in row_skip are left to the hub CTAs by the tile CTAs.
-struct AggHubs {
-    const int32_t *hubs;        // hub row ids (n_hubs)
-    int n_hubs;
-    const int32_t *common_col;  // common set (n_common), may be NULL: every hub row is gathered on its own
-    const float *common_w;
-    int n_common;
-    const float *alpha;         // per hub row scale of y* (n_hubs)
-    const uint8_t *row_skip;    // Nv flags, may be NULL: rows of degree > HUB_DEG are the hub rows
-};
 
 template <int NG>
 __global__ void __launch_bounds__(AG_THREADS, 4)
@@ -819,6 +704,51 @@ extern "C" int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, c
         gcn_aggregate_kernel<false><<<grid, AG_THREADS, 0, st>>>(rowptr, col, val, hubs, n_hubs, hub_ctas, hub_stride, (int)Nv, in, rows, (int)C, (int)L, bias, relu, out);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
+}
+
+namespace ptk {
+struct AggTiles {
+    const int32_t *uptr;
+    const int32_t *ucol;
+    const uint16_t *lidx;
+};
+int aggregate_union_launch(const int32_t *rowptr, const int32_t *col, const float *val, const AggHubs &hb, const AggTiles &tl,
+                           int max_union, bool have_hubs, int64_t Nv, const float *in, int64_t B, int64_t C, int64_t L,
+                           const float *bias, int relu, float *out, int64_t ldi, int64_t ldo, int hubs_first,
+                           int prefetch_next, cudaStream_t st);  // gcn_aggregate_union.cu
+}  // namespace ptk
+
+extern "C" int ptk_gcn_aggregate_tiled(const int32_t *rowptr, const int32_t *col, const float *val,
+                                       const int32_t *hubs, int32_t n_hubs, const int32_t *common_col,
+                                       const float *common_w, int32_t n_common, const float *hub_alpha,
+                                       const uint8_t *row_skip, const int32_t *tile_uptr, const int32_t *tile_ucol,
+                                       const uint16_t *tile_lidx, int32_t max_union, int64_t Nv, const float *in,
+                                       int64_t B, int64_t C, int64_t L, const float *bias, int relu, float *out,
+                                       int64_t ldi, int64_t ldo, ptk_stream_t stream) {
+    const int64_t ldi_e = ldi <= 0 ? C : ldi, ldo_e = ldo <= 0 ? C : ldo;
+    const bool vec = rowptr && col && val && in && out && in != out && B > 0 && Nv > 0 && C > 0 && L >= 1 && L <= C &&
+                     (C % 4 == 0) && (ldi_e % 4 == 0) && (ldo_e % 4 == 0) && ldi_e >= C && ldo_e >= C &&
+                     ((((uintptr_t)in) | ((uintptr_t)out) | ((uintptr_t)bias)) % 16 == 0) && B <= 0x7fffffff &&
+                     Nv * ldi_e * 4 <= 0xffffffffLL;
+    const bool common = n_common > 0;
+    const bool common_ok = !common || (hubs && n_hubs > 0 && common_col && common_w && hub_alpha && row_skip);
+    if (vec && common_ok && tile_uptr && tile_ucol && tile_lidx && max_union > 0 && PTK_TUNING_ENV("PTK_AGG_UNION") != 2) {
+        AggHubs hb;
+        const bool have_hubs = hubs && n_hubs > 0;
+        hb.hubs = hubs; hb.n_hubs = have_hubs ? n_hubs : 0;
+        hb.common_col = common_col; hb.common_w = common_w; hb.n_common = common ? n_common : 0;
+        hb.alpha = hub_alpha; hb.row_skip = common ? row_skip : nullptr;
+        AggTiles tl;
+        tl.uptr = tile_uptr; tl.ucol = tile_ucol; tl.lidx = tile_lidx;
+        const int hubs_first = (double)B * Nv * (ldi_e + ldo_e) * 4.0 < 100e6;
+        int prefetch_next = !hubs_first;
+        if (PTK_TUNING_ENV("PTK_AGG_PF") > 0) prefetch_next = PTK_TUNING_ENV("PTK_AGG_PF") == 1;
+        const int rc = aggregate_union_launch(rowptr, col, val, hb, tl, max_union, have_hubs, Nv, in, B, C, L, bias, relu, out,
+                                              ldi_e, ldo_e, hubs_first, prefetch_next, as_stream(stream));
+        if (rc != 0) return rc < 0 ? rc : PTK_OK;
+    }
+    return ptk_gcn_aggregate_ex(rowptr, col, val, hubs, n_hubs, common_col, common_w, n_common, hub_alpha, row_skip, Nv, in,
+                                B, C, L, bias, relu, out, ldi, ldo, stream);
 }
 
 extern "C" int ptk_gcn_aggregate(const int32_t *rowptr, const int32_t *col, const float *val,

@@ -59,10 +59,11 @@ inline bool aligned16(const void *p) { return ((uintptr_t)p % 16) == 0; }
 int aggregate(const ptk_gcn_csr *g, int64_t Nv, const float *in, int64_t B, int64_t C, int64_t L, const float *bias,
               int relu, float *out, int64_t ldi, int64_t ldo, ptk_stream_t stream) {
     const bool vector_path = (C % 4 == 0) && L >= 1 && L <= 384 && aligned16(in) && aligned16(out) && aligned16(bias);
-    if (g->n_common > 0 && vector_path)
-        return ptk_gcn_aggregate_ex(g->k_rowptr, g->k_col, g->k_val, g->k_hubs, g->k_n_hubs, g->common_col, g->common_w,
-                                    g->n_common, g->alpha, g->row_skip, Nv, in, B, C, L, bias, relu, out, ldi, ldo,
-                                    stream);
+    if (vector_path && (g->n_common > 0 || g->tile_uptr))
+        // the kernel form (== the plain arrays when no common set was split off), rows staged in shared memory per tile
+        return ptk_gcn_aggregate_tiled(g->k_rowptr, g->k_col, g->k_val, g->k_hubs, g->k_n_hubs, g->common_col, g->common_w,
+                                       g->n_common, g->alpha, g->row_skip, g->tile_uptr, g->tile_ucol, g->tile_lidx,
+                                       g->max_union, Nv, in, B, C, L, bias, relu, out, ldi, ldo, stream);
     return ptk_gcn_aggregate_ex(g->rowptr, g->col, g->val, g->hubs, g->n_hubs, nullptr, nullptr, 0, nullptr, nullptr, Nv,
                                 in, B, C, L, bias, relu, out, ldi, ldo, stream);
 }

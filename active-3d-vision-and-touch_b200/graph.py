@@ -64,6 +64,38 @@ def factor_hubs(rowptr, col, val, n):
                 row_skip=row_skip)
 
 
+TILE_ROWS = 8  # rows per tile of the shared-memory union kernel (csrc/gcn_aggregate_union.cu: AU_TV)
+
+
+def tile_unions(rowptr, col, skip, n, tile_rows=TILE_ROWS):
+    """Per tile of `tile_rows` consecutive rows: the sorted union of the neighbour columns of its rows (rows flagged in
+    `skip` -- the hub rows, which dedicated CTAs process -- left out), and per CSR entry the position of its column in
+    its tile's union.  The kernel stages the union's rows in shared memory once per batch element and gathers by local
+    index (ptk_gcn_aggregate_tiled).  Returns (uptr (n_tiles+1) i32, ucol i32, lidx (nnz) u16, largest union)."""
+    n_tiles = (n + tile_rows - 1) // tile_rows
+    uptr = np.zeros(n_tiles + 1, np.int32)
+    ucols = []
+    lidx = np.zeros(len(col), np.uint16)
+    max_union = 0
+    for t in range(n_tiles):
+        r0, r1 = t * tile_rows, min(n, (t + 1) * tile_rows)
+        rows = [i for i in range(r0, r1) if not skip[i]]
+        if rows:
+            ent = np.concatenate([col[rowptr[i]:rowptr[i + 1]] for i in rows])
+            u = np.unique(ent)
+            for i in rows:
+                lidx[rowptr[i]:rowptr[i + 1]] = np.searchsorted(u, col[rowptr[i]:rowptr[i + 1]]).astype(np.uint16)
+        else:
+            u = np.zeros(0, np.int32)
+        ucols.append(u.astype(np.int32))
+        uptr[t + 1] = uptr[t] + len(u)
+        max_union = max(max_union, len(u))
+    ucol = np.concatenate(ucols) if ucols else np.zeros(0, np.int32)
+    if max_union > 65535:
+        return None
+    return uptr, (ucol if len(ucol) else np.zeros(1, np.int32)), (lidx if len(lidx) else np.zeros(1, np.uint16)), max_union
+
+
 class KernelCSR:
     """Device arrays of one direction (A^ or its transpose) in the form the aggregate kernels take."""
 
@@ -75,6 +107,20 @@ class KernelCSR:
         self.common_col, self.common_w, self.alpha, self.row_skip = (to(f[k]) for k in
                                                                       ("common_col", "common_w", "alpha", "row_skip"))
         self.n_common = 0 if f["common_col"] is None else int(len(f["common_col"]))
+        # tile unions of this form (hub rows: the flagged rows of the factored form, else every row above HUB_DEG)
+        n = len(f["rowptr"]) - 1
+        skip = f["row_skip"] if f["row_skip"] is not None else (
+            (np.diff(f["rowptr"]) > HUB_DEG) if len(f["hubs"]) else np.zeros(n, bool))
+        self.tile_uptr = self.tile_ucol = self.tile_lidx = None
+        self.max_union = 0
+        if n > 0 and len(f["col"]) and int(np.diff(f["rowptr"])[~np.asarray(skip, bool)].max(initial=0)) <= HUB_DEG:
+            tu = tile_unions(f["rowptr"], f["col"], skip, n)
+            if tu is not None:
+                uptr, ucol, lidx, self.max_union = tu
+                self.tile_uptr = torch.from_numpy(uptr).to(device)
+                self.tile_ucol = torch.from_numpy(ucol).to(device)
+                # (torch has no uint16 arithmetic, the tensor is only a device buffer: view as int16)
+                self.tile_lidx = torch.from_numpy(lidx.view(np.int16)).to(device)
 
 
 class Graph:
@@ -117,17 +163,22 @@ class Graph:
         import ctypes as C
 
         from . import _lib
+        from . import ops
         cache = self.__dict__.setdefault("_csr_structs", {})
-        hit = cache.get(bool(transpose))
+        tiles = bool(ops.use_union)  # the tile unions travel only when the shared-memory union kernel is selected
+        key = (bool(transpose), tiles)
+        hit = cache.get(key)
         if hit is None:
             if transpose:
                 rp, col, val, hubs, nh, k = self.rowptr_t, self.col_t, self.val_t, self.hubs_t, self.n_hubs_t, self.bwd_k
             else:
                 rp, col, val, hubs, nh, k = self.rowptr, self.col, self.val, self.hubs, self.n_hubs, self.fwd_k
             ptr = lambda t: None if t is None else t.data_ptr()
-            hit = cache[bool(transpose)] = _lib.GcnCsr(
+            hit = cache[key] = _lib.GcnCsr(
                 ptr(rp), ptr(col), ptr(val), ptr(hubs), nh, ptr(k.rowptr), ptr(k.col), ptr(k.val), ptr(k.hubs), k.n_hubs,
-                ptr(k.common_col), ptr(k.common_w), k.n_common, ptr(k.alpha), ptr(k.row_skip))
+                ptr(k.common_col), ptr(k.common_w), k.n_common, ptr(k.alpha), ptr(k.row_skip),
+                ptr(k.tile_uptr if tiles else None), ptr(k.tile_ucol if tiles else None),
+                ptr(k.tile_lidx if tiles else None), k.max_union if tiles else 0)
         return hit
 
     @staticmethod

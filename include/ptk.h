@@ -155,6 +155,19 @@ int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, const float 
                          const uint8_t *row_skip, int64_t Nv, const float *in, int64_t B, int64_t C,
                          int64_t L, const float *bias, int relu, float *out, int64_t ldi, int64_t ldo,
                          ptk_stream_t stream);
+/* ptk_gcn_aggregate_ex with the neighbour rows staged in shared memory (csrc/gcn_aggregate_union.cu).  The rows of a
+ * tile of 8 consecutive vertices share most of their neighbours; the caller lists, per tile, the sorted union of the
+ * neighbour columns of its non-hub rows: tile_uptr (ceil(Nv/8)+1 offsets), tile_ucol, and per CSR entry e the index
+ * tile_lidx[e] of col[e] in its tile's union; max_union = the largest union.  Per batch element a CTA copies the
+ * union's rows into shared memory (cp.async.bulk, mbarrier ring) and gathers from there.  Same results as
+ * ptk_gcn_aggregate_ex; falls back to it when the tile arrays are NULL or the shape is outside the kernel's range
+ * (unions above 256 rows, non-vector shapes). */
+int ptk_gcn_aggregate_tiled(const int32_t *rowptr, const int32_t *col, const float *val, const int32_t *hubs,
+                            int32_t n_hubs, const int32_t *common_col, const float *common_w, int32_t n_common,
+                            const float *hub_alpha, const uint8_t *row_skip, const int32_t *tile_uptr,
+                            const int32_t *tile_ucol, const uint16_t *tile_lidx, int32_t max_union, int64_t Nv,
+                            const float *in, int64_t B, int64_t C, int64_t L, const float *bias, int relu,
+                            float *out, int64_t ldi, int64_t ldo, ptk_stream_t stream);
 /* gbias[c] = sum_{rows} g[row,c] for c < L, 0 for L <= c < C  (g is (M,C)); overwrites gbias.
  * Deterministic two-stage column sum; workspace from ptk_gcn_bias_grad_workspace_bytes. */
 size_t ptk_gcn_bias_grad_workspace_bytes(int64_t M, int64_t L);
@@ -231,6 +244,8 @@ typedef struct ptk_gcn_csr {
     const int32_t *rowptr, *col; const float *val; const int32_t *hubs; int32_t n_hubs;
     const int32_t *k_rowptr, *k_col; const float *k_val; const int32_t *k_hubs; int32_t k_n_hubs;
     const int32_t *common_col; const float *common_w; int32_t n_common; const float *alpha; const uint8_t *row_skip;
+    /* tile unions of the k_* form (ptk_gcn_aggregate_tiled); NULL / 0: absent */
+    const int32_t *tile_uptr, *tile_ucol; const uint16_t *tile_lidx; int32_t max_union;
 } ptk_gcn_csr;
 
 size_t ptk_gcn_stack_fwd_workspace_bytes(int64_t B, int64_t Nv, int32_t n_layers, const int64_t *widths,
