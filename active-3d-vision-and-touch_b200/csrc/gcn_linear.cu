@@ -361,12 +361,15 @@ sgemm_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     extern __shared__ __align__(128) uint8_t ft_smem_raw[];
     const uint32_t smem = (ft_smem_u32(ft_smem_raw) + 127u) & ~127u;  // shared-space address of stage 0
     __shared__ __align__(8) uint64_t bars[2 * FT_STAGES];
-    __shared__ uint32_t sbits[FT_BM][FW_MAXW];
+
     const uint32_t bar_full = ft_smem_u32(&bars[0]), bar_empty = ft_smem_u32(&bars[FT_STAGES]);
     const int tid = threadIdx.x, lane = tid & 31;
     const int m0 = blockIdx.y * FT_BM, n0 = blockIdx.x * FW_BN;
     const int tx = tid % 16, ty = tid / 16;
-    const bool emit = a_bits != nullptr && blockIdx.x == 0;  // one column tile of CTAs is enough
+    // Packed ReLU mask of A for the backward: the column tiles of a row tile share the work -- CTA x emits the k-tiles
+    // with kt % gridDim.x == x (16 bits each, straight to global memory), so no CTA of a wave is slower than the others.
+    const bool emit_any = a_bits != nullptr;
+    const int emit_mod = (int)gridDim.x, emit_me = (int)blockIdx.x;
     const int num_kt = (K + FW_BK - 1) / FW_BK;
     pdl_launch_dependents();
     if (tid == 0) {
@@ -378,8 +381,6 @@ sgemm_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (emit)
-        for (int e = tid; e < FT_BM * FW_MAXW; e += FT_THREADS) sbits[e / FW_MAXW][e % FW_MAXW] = 0u;
     __syncthreads();
     pdl_wait();  // A is the predecessor's output
 
@@ -413,7 +414,7 @@ sgemm_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         ft_mbar_wait(bar_full + 8 * s, (kt / FT_STAGES) & 1);
         const uint32_t As = smem + (uint32_t)(s * FT_STAGE_BYTES);   // [64 rows][16 k] fp32
         const uint32_t Bs = As + FT_A_BYTES;                          // [16 k][160 columns] fp32
-        if (emit) {
+        if (emit_any && kt % emit_mod == emit_me) {
             // ReLU mask bits of this k-tile of A (see sgemm_fwd_kernel): thread = (row, 8-k half)
             const int r = tid >> 1, h8 = tid & 1;
             const float4 v0 = ft_lds_f4(As + 4u * (uint32_t)(r * FW_BK + h8 * 8));
@@ -422,7 +423,8 @@ sgemm_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                           (v1.x > 0.f ? 16u : 0u) | (v1.y > 0.f ? 32u : 0u) | (v1.z > 0.f ? 64u : 0u) |
                           (v1.w > 0.f ? 128u : 0u)) << (h8 * 8);
             h |= __shfl_xor_sync(0xffffffffu, h, 1);
-            if (h8 == 0) reinterpret_cast<unsigned short *>(&sbits[r][0])[kt] = (unsigned short)h;
+            if (h8 == 0 && m0 + r < M)
+                reinterpret_cast<unsigned short *>(a_bits + (size_t)(m0 + r) * ((K + 31) >> 5))[kt] = (unsigned short)h;
         }
 #pragma unroll
         for (int kq = 0; kq < FW_BK / 2; ++kq) {
@@ -453,13 +455,11 @@ sgemm_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         __syncwarp();
         if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_empty + 8 * s) : "memory");
     }
-    if (emit) {
-        __syncthreads();
+    if (emit_any && (num_kt & 1) && num_kt % emit_mod == emit_me) {
+        // K = 300: 19 k-tiles fill 9.5 words -- the upper half of the last word is zero (columns beyond K)
         const int wpr = (K + 31) >> 5;
-        for (int e = tid; e < FT_BM * wpr; e += FT_THREADS) {
-            const int r = e / wpr, w = e - r * wpr;
-            if (m0 + r < M) a_bits[(size_t)(m0 + r) * wpr + w] = sbits[r][w];
-        }
+        for (int r = tid; r < FT_BM; r += FT_THREADS)
+            if (m0 + r < M) reinterpret_cast<unsigned short *>(a_bits + (size_t)(m0 + r) * wpr)[num_kt] = 0;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
