@@ -4,6 +4,8 @@
 
 #include <atomic>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "ptk_common.cuh"
 
 namespace ptk {
@@ -28,6 +30,9 @@ bool pdl_enabled() {
     }();
     return on;
 }
+
+NvtxRange::NvtxRange(const char *name) { nvtxRangePushA(name); }
+NvtxRange::~NvtxRange() { nvtxRangePop(); }
 
 int sm_count() {
     static thread_local int cached_dev = -1, cached = 148;

@@ -325,6 +325,7 @@ static int check_clouds(const void *x, const void *y, int64_t B, int64_t P1, int
 extern "C" int ptk_knn1_fwd(const float *p1, const float *p2, int64_t B, int64_t P1, int64_t P2,
                             float *dist, int32_t *idx, void *workspace, size_t workspace_bytes,
                             ptk_stream_t stream) {
+    PTK_NVTX("ptk_knn1_fwd");
     int rc = check_clouds(p1, p2, B, P1, P2);
     if (rc) return rc;
     PTK_REQUIRE(workspace && workspace_bytes >= chamfer_ws_bytes(B, P1, P2), PTK_ERR_WORKSPACE,
@@ -344,6 +345,7 @@ extern "C" int ptk_chamfer_fwd(const float *x, const float *y, int64_t B, int64_
                                float *dist_x, int32_t *idx_x, float *dist_y, int32_t *idx_y,
                                float *cham, void *workspace, size_t workspace_bytes,
                                ptk_stream_t stream) {
+    PTK_NVTX("ptk_chamfer_fwd");
     int rc = check_clouds(x, y, B, P1, P2);
     if (rc) return rc;
     PTK_REQUIRE(idx_x && idx_y && cham, PTK_ERR_SHAPE, "chamfer_fwd: idx_x, idx_y and cham are required");
@@ -365,6 +367,7 @@ extern "C" int ptk_chamfer_fwd(const float *x, const float *y, int64_t B, int64_
 extern "C" int ptk_chamfer_bwd(const float *x, const float *y, const int32_t *idx_x,
                                const int32_t *idx_y, const float *grad_cham, int64_t B, int64_t P1,
                                int64_t P2, float *grad_x, float *grad_y, ptk_stream_t stream) {
+    PTK_NVTX("ptk_chamfer_bwd");
     int rc = check_clouds(x, y, B, P1, P2);
     if (rc) return rc;
     PTK_REQUIRE(idx_x && idx_y && grad_cham, PTK_ERR_SHAPE, "chamfer_bwd: null index / grad pointer");

@@ -625,6 +625,7 @@ extern "C" int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, c
                                     const uint8_t *row_skip, int64_t Nv, const float *in, int64_t B,
                                     int64_t C, int64_t L, const float *bias, int relu, float *out,
                                     int64_t ldi, int64_t ldo, ptk_stream_t stream) {
+    PTK_NVTX("ptk_gcn_aggregate_ex");
     if (ldi <= 0) ldi = C;
     if (ldo <= 0) ldo = C;
     PTK_REQUIRE(rowptr && col && val && in && out, PTK_ERR_SHAPE, "gcn_aggregate: null pointer");

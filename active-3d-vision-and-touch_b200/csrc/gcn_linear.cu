@@ -624,6 +624,7 @@ extern "C" size_t ptk_gcn_linear_workspace_bytes(int64_t M, int64_t K, int64_t N
 extern "C" int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int64_t K, int64_t N,
                                   float *H, int algo, void *workspace, size_t workspace_bytes,
                                   ptk_stream_t stream) {
+    PTK_NVTX("ptk_gcn_linear_fwd");
     int rc = check_gemm(X, W, H, M, K, N);
     if (rc) return rc;
     PTK_REQUIRE(algo >= 0 && algo <= 2, PTK_ERR_SHAPE, "gcn_linear_fwd: algo must be 0, 1 or 2");
@@ -663,6 +664,7 @@ extern "C" int ptk_gcn_linear_fwd(const float *X, const float *W, int64_t M, int
 extern "C" int ptk_gcn_linear_fwd_split(const float *X, const float *W, int64_t M, int64_t K, int64_t N,
                                         int64_t n_split, float *head, float *out, int relu, uint32_t *x_bits,
                                         ptk_stream_t stream) {
+    PTK_NVTX("ptk_gcn_linear_fwd_split");
     int rc = check_gemm(X, W, out, M, K, N);
     if (rc) return rc;
     PTK_REQUIRE(head && n_split > 0 && n_split < N && (n_split % 4) == 0, PTK_ERR_SHAPE,
@@ -682,6 +684,7 @@ extern "C" int ptk_gcn_linear_fwd_split(const float *X, const float *W, int64_t 
 extern "C" int ptk_gcn_linear_dgrad(const float *gH, const float *W, const float *act, const uint32_t *act_bits,
                                     int64_t M, int64_t K, int64_t N, float *gX, int algo, void *workspace,
                                     size_t workspace_bytes, ptk_stream_t stream) {
+    PTK_NVTX("ptk_gcn_linear_dgrad");
     int rc = check_gemm(gH, W, gX, M, K, N);
     if (rc) return rc;
     PTK_REQUIRE(algo >= 0 && algo <= 2, PTK_ERR_SHAPE, "gcn_linear_dgrad: algo must be 0, 1 or 2");
@@ -729,6 +732,7 @@ extern "C" size_t ptk_gcn_linear_wgrad_workspace_bytes(int64_t M, int64_t K, int
 extern "C" int ptk_gcn_linear_wgrad(const float *X, const float *gH, int64_t M, int64_t K, int64_t N,
                                     float *gW, int algo, void *workspace, size_t workspace_bytes,
                                     ptk_stream_t stream) {
+    PTK_NVTX("ptk_gcn_linear_wgrad");
     int rc = check_gemm(X, gH, gW, M, K, N);
     if (rc) return rc;
     PTK_REQUIRE(algo >= 0 && algo <= 2, PTK_ERR_SHAPE, "gcn_linear_wgrad: algo must be 0, 1 or 2");

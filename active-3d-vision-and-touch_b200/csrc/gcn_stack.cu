@@ -188,6 +188,7 @@ extern "C" int ptk_gcn_stack_fwd(const ptk_gcn_csr *graph, int64_t B, int64_t Nv
                                  const float *const *W, const float *const *bias, float *const *acts,
                                  uint32_t *const *x_bits, int algo, int fuse, void *workspace, size_t workspace_bytes,
                                  ptk_stream_t stream) {
+    PTK_NVTX("ptk_gcn_stack_fwd");
     PTK_REQUIRE(graph && widths && Ls && relus && X && W && bias && acts, PTK_ERR_SHAPE, "gcn_stack_fwd: null pointer");
     PTK_REQUIRE(B > 0 && Nv > 0 && n_layers > 0 && n_layers <= MAX_LAYERS, PTK_ERR_SHAPE, "gcn_stack_fwd: bad sizes");
     const int64_t M = B * Nv;
@@ -278,6 +279,7 @@ extern "C" int ptk_gcn_stack_bwd(const ptk_gcn_csr *graph_t, int64_t B, int64_t 
                                  const float *gout, float *gX, float *const *gW, float *const *gb,
                                  const uint8_t *need_gb, int batch_bias, int algo_dgrad, int algo_wgrad,
                                  void *workspace, size_t workspace_bytes, ptk_stream_t stream) {
+    PTK_NVTX("ptk_gcn_stack_bwd");
     PTK_REQUIRE(graph_t && widths && Ls && relus && X && W && acts && gout && gW && gb && need_gb, PTK_ERR_SHAPE,
                 "gcn_stack_bwd: null pointer");
     PTK_REQUIRE(B > 0 && Nv > 0 && n_layers > 0 && n_layers <= MAX_LAYERS, PTK_ERR_SHAPE, "gcn_stack_bwd: bad sizes");

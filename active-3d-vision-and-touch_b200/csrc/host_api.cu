@@ -84,6 +84,7 @@ extern "C" void ptk_host_ctx_destroy(ptk_host_ctx *c) {
 extern "C" int ptk_host_chamfer(ptk_host_ctx *c, const float *x, const float *y, int64_t B, int64_t P1,
                                 int64_t P2, float *cham, int32_t *idx_x, int32_t *idx_y,
                                 const float *grad_cham, float *grad_x, float *grad_y) {
+    PTK_NVTX("ptk_host_chamfer");
     PTK_REQUIRE(c && x && y && cham, PTK_ERR_SHAPE, "host_chamfer: null pointer");
     PTK_REQUIRE(B > 0 && P1 > 0 && P2 > 0, PTK_ERR_SHAPE, "host_chamfer: empty input");
     PTK_CHECK_CUDA(cudaSetDevice(c->device));
@@ -160,6 +161,7 @@ extern "C" int ptk_host_mesh_chamfer(ptk_host_ctx *c, const float *verts, int64_
                                      const int32_t *faces, int64_t F, const float *gt, int64_t P2,
                                      const float *u_face, const float *uv, int64_t S, int64_t repeat,
                                      float *cd, const float *grad_cd, float *grad_verts) {
+    PTK_NVTX("ptk_host_mesh_chamfer");
     PTK_REQUIRE(c && verts && faces && gt && u_face && uv && cd, PTK_ERR_SHAPE, "host_mesh_chamfer: null pointer");
     PTK_REQUIRE(B > 0 && V > 0 && F > 0 && P2 > 0 && S > 0 && repeat > 0, PTK_ERR_SHAPE,
                 "host_mesh_chamfer: empty input");

@@ -40,6 +40,14 @@ void count_launch();  // ptk_launch_count(): one tick per kernel launch of this 
 
 inline cudaStream_t as_stream(ptk_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// NVTX range around an ABI entry point (host side, header-only NVTX v3: a no-op unless a profiler is attached).
+// Timelines of Nsight Systems / `ncu --nvtx` then show ptk_chamfer_fwd, ptk_gcn_stack_bwd, ... around their kernels.
+struct NvtxRange {
+    explicit NvtxRange(const char *name);
+    ~NvtxRange();
+};
+#define PTK_NVTX(name) ::ptk::NvtxRange _ptk_nvtx_range(name)
+
 // ---- programmatic dependent launch (PDL).  The kernels of one GCN pass are 5-135 us each and follow one another
 // on a single stream; a plain launch starts a kernel ~2 us after its predecessor drained (measured: 1.0 ms of idle
 // gaps over the ~550 kernels of a reconstruction step).  Launched through launch_pdl(), a kernel may become resident

@@ -279,6 +279,7 @@ extern "C" int ptk_sample_fwd(const float *verts, int64_t B, int64_t V, const in
                               int64_t F, const float *u_face, const float *uv, int64_t S, float *pts,
                               int32_t *face_idx, void *workspace, size_t workspace_bytes,
                               ptk_stream_t stream) {
+    PTK_NVTX("ptk_sample_fwd");
     PTK_REQUIRE(verts && faces && uv && pts && face_idx, PTK_ERR_SHAPE, "sample_fwd: null pointer");
     PTK_REQUIRE(B > 0 && V > 0 && F > 0 && S > 0, PTK_ERR_SHAPE,
                 "sample_fwd: empty input (B=%lld, V=%lld, F=%lld, S=%lld)", (long long)B, (long long)V,
@@ -304,6 +305,7 @@ extern "C" int ptk_sample_fwd(const float *verts, int64_t B, int64_t V, const in
 extern "C" int ptk_sample_bwd(const float *grad_pts, const int32_t *face_idx, const float *uv,
                               const int32_t *faces, int64_t B, int64_t V, int64_t F, int64_t S,
                               float *grad_verts, ptk_stream_t stream) {
+    PTK_NVTX("ptk_sample_bwd");
     PTK_REQUIRE(grad_pts && face_idx && uv && faces && grad_verts, PTK_ERR_SHAPE, "sample_bwd: null pointer");
     PTK_REQUIRE(B > 0 && V > 0 && F > 0 && S > 0 && B <= 65535, PTK_ERR_SHAPE, "sample_bwd: bad sizes");
     cudaStream_t st = as_stream(stream);

@@ -20,6 +20,7 @@ constexpr int VF_TM = 64;        // vertices per CTA
 constexpr int VF_THREADS = 256;  // 16 row groups (4 vertices) x 16 column groups (2 x 4 outputs)
 constexpr int VF_NT = 128;       // output columns per weight tile
 constexpr int VF_KT = 16;        // reduction steps per weight tile
+constexpr int VF_WP = VF_NT + 4;  // pitch of a staged weight row (floats): the transposing stores conflict 2-way, not 4-way
 constexpr int VF_EMB = 63, VF_EMB_P = 64;
 constexpr int VF_MAX_H1 = 112, VF_MAX_H2 = 224;  // hidden widths of input_size <= 448 (+ padding to 16)
 
@@ -43,11 +44,16 @@ struct VFParams {
 //   LAST = true : out[m][n]   = res + bias[n] + emb[token[m]][n] + add[m][n]
 template <bool LAST>
 __device__ __forceinline__ void vf_layer(const float *__restrict__ W, const float *__restrict__ bias, int K, int Nout,
-                                         const float *in_t, float *out_t, float (*ws)[VF_KT][VF_NT], long long m0,
+                                         const float *in_t, float *out_t, float (*ws)[VF_KT][VF_WP], long long m0,
                                          long long M, float *__restrict__ gout, const float *__restrict__ emb,
                                          const int *s_tok, const float *__restrict__ add) {
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int sn = tid & (VF_NT - 1), sk = (tid >> 7) * 8;  // staging: this thread brings W[n0 + sn][k0 + sk .. + 7]
+    // Weight staging.  K % 4 == 0 (every layer but the first): 4 lanes bring the 16 k of one output row as float4 (64
+    // contiguous bytes per row, 2 rows per thread) and store them transposed; otherwise (K = 63) scalar loads,
+    // thread = (row, 8 consecutive k).
+    const bool vec_w = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0;
+    const int vrow = tid >> 2, vk = (tid & 3) * 4;
+    const int sn = tid & (VF_NT - 1), sk = (tid >> 7) * 8;
     const int nkt = (K + VF_KT - 1) / VF_KT;
     const bool vec_out = (Nout & 3) == 0;
     for (int n0 = 0; n0 < Nout; n0 += VF_NT) {
@@ -58,14 +64,31 @@ __device__ __forceinline__ void vf_layer(const float *__restrict__ W, const floa
             for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
         float stg[8];
         auto fetch = [&](int kt) {
-            const int n = n0 + sn;
-            const float *src = W + (size_t)n * K + kt * VF_KT + sk;
+            if (vec_w) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) stg[j] = (n < Nout && kt * VF_KT + sk + j < K) ? __ldg(src + j) : 0.f;
+                for (int h = 0; h < 2; ++h) {
+                    const int n = n0 + vrow + 64 * h, k = kt * VF_KT + vk;
+                    const float4 v = (n < Nout && k < K) ? __ldg(reinterpret_cast<const float4 *>(W + (size_t)n * K + k))
+                                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+                    stg[4 * h] = v.x; stg[4 * h + 1] = v.y; stg[4 * h + 2] = v.z; stg[4 * h + 3] = v.w;
+                }
+            } else {
+                const int n = n0 + sn;
+                const float *src = W + (size_t)n * K + kt * VF_KT + sk;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) stg[j] = (n < Nout && kt * VF_KT + sk + j < K) ? __ldg(src + j) : 0.f;
+            }
         };
         auto stash = [&](int buf) {
+            if (vec_w) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) ws[buf][sk + j][sn] = stg[j];
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) ws[buf][vk + j][vrow + 64 * h] = stg[4 * h + j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ws[buf][sk + j][sn] = stg[j];
+            }
         };
         fetch(0);
         __syncthreads();  // the previous user of ws / the producer of in_t is done
@@ -155,7 +178,7 @@ vertex_front_fwd_kernel(const VFParams p) {
     // [act A: embedding, later hidden 2][act B: hidden 1][weight tiles 2 x 16 x 128][tokens]
     float *act_a = vf_smem;                                   // max(64, ceil16(h2)) x 64
     float *act_b = act_a + (size_t)VF_MAX_H2 * VF_TM;         // ceil16(h1) x 64
-    float(*ws)[VF_KT][VF_NT] = reinterpret_cast<float(*)[VF_KT][VF_NT]>(act_b + (size_t)VF_MAX_H1 * VF_TM);
+    float(*ws)[VF_KT][VF_WP] = reinterpret_cast<float(*)[VF_KT][VF_WP]>(act_b + (size_t)VF_MAX_H1 * VF_TM);
     int *s_tok = reinterpret_cast<int *>(&ws[2][0][0]);
     const int tid = threadIdx.x;
     const long long m0 = (long long)blockIdx.x * VF_TM;
@@ -239,6 +262,7 @@ extern "C" int ptk_vertex_front_fwd(const float *positions, const float *mask, c
                                     const float *w2, const float *b2, const float *w3, const float *b3,
                                     const float *emb, const float *add, int64_t M, int32_t h1, int32_t h2,
                                     int32_t width, float *out, float *h1_save, float *h2_save, ptk_stream_t stream) {
+    PTK_NVTX("ptk_vertex_front_fwd");
     PTK_REQUIRE(M >= 0 && M < (1LL << 31), PTK_ERR_SHAPE, "vertex_front_fwd: bad M = %lld", (long long)M);
     PTK_REQUIRE(h1 >= 1 && h1 <= VF_MAX_H1 && h2 >= 1 && h2 <= VF_MAX_H2 && width >= 1, PTK_ERR_SHAPE,
                 "vertex_front_fwd: hidden widths (%d, %d) outside (1..%d, 1..%d)", h1, h2, VF_MAX_H1, VF_MAX_H2);
@@ -251,7 +275,7 @@ extern "C" int ptk_vertex_front_fwd(const float *positions, const float *mask, c
     p.pos = positions; p.mask = mask; p.w1 = w1; p.b1 = b1; p.w2 = w2; p.b2 = b2; p.w3 = w3; p.b3 = b3;
     p.emb = emb; p.add = add; p.M = M; p.h1 = h1; p.h2 = h2; p.width = width; p.out = out;
     p.h1_save = h1_save; p.h2_save = h2_save;
-    const size_t smem = sizeof(float) * ((size_t)(VF_MAX_H2 + VF_MAX_H1) * VF_TM + 2 * VF_KT * VF_NT) + sizeof(int) * VF_TM;
+    const size_t smem = sizeof(float) * ((size_t)(VF_MAX_H2 + VF_MAX_H1) * VF_TM + 2 * VF_KT * VF_WP) + sizeof(int) * VF_TM;
     int dev = 0;
     PTK_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev >= 64 || !((g_vf_optin >> dev) & 1ull)) {

@@ -718,6 +718,36 @@ def extra_measurements(torch, ptk_b200, dev, hbm_peak, hbm_src):
     ms = timeit(lambda: ptk_b200.ops.sample_points(verts, faces32, uf, uv), 20)
     out["sampler"] = {"shape": "B=16 V=1949 F=2464 S=10000", "ms": ms}
 
+    # --- fused vertex-feature front (config-3 shape: 16 x 1949 vertices, input_size 448): positions -> GCN layer-0 input in one
+    # launch, next to the same modules on the unfused path (embedding kernel + torch Linear / Embedding / adds = library GEMMs)
+    import copy
+    torch.manual_seed(1)
+    enc, menc = ptk_b200.Positional_Encoder(448).to(dev), ptk_b200.Mask_Encoder(448).to(dev)
+    enc_u, menc_u = copy.deepcopy(enc), copy.deepcopy(menc)
+    enc_u.fused = False
+    pos = verts.clone().requires_grad_(True)
+    mask = torch.randint(0, 4, (Bs, 1949, 1), device=dev).float()
+    img = torch.rand(Bs, 1949, 448, device=dev)
+    w = torch.rand(Bs, 1949, 448, device=dev)
+
+    def front(e, m, train):
+        def fn():
+            if train:
+                pos.grad = None
+                e.zero_grad(set_to_none=True)
+                m.zero_grad(set_to_none=True)
+                (ptk_b200.encoders.vertex_features(e, m, pos, mask, img) * w).sum().backward()
+            else:
+                with torch.no_grad():
+                    ptk_b200.encoders.vertex_features(e, m, pos, mask, img)
+        return fn
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out["vertex_front"] = {
+        "shape": "M = 16 x 1949 vertices, 63 -> 112 -> 224 -> 448 (+ mask-token row + image features), FP32",
+        "fwd_ms": timeit(front(enc, menc, False), 20), "fwd_bwd_ms": timeit(front(enc, menc, True), 10),
+        "unfused_fwd_ms": timeit(front(enc_u, menc_u, False), 20), "unfused_fwd_bwd_ms": timeit(front(enc_u, menc_u, True), 10),
+        "note": "fused: ptk_vertex_front_fwd (one launch); unfused: ptk_nerf_embed + three cuBLAS FP32 GEMMs + elementwise kernels"}
+
     return out
 
 
