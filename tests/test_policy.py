@@ -49,7 +49,16 @@ def test_score_candidates_equals_per_action_calls(golden):
         rows = torch.arange(E, device="cuda") * A + a
         uni = [(uf[rows].contiguous(), uv[:, rows].contiguous()) for uf, uv in uniforms]
         want = 9000.0 * ptk_b200.utils.chamfer_distance(verts[:, a].contiguous(), faces, gt, num=num, uniforms=uni)
-        assert torch.equal(scores[:, a], want)
+        assert torch.equal(scores[:, a], want)          # batching changes nothing, bit for bit
+        # ... and the score itself against the reference's get_score restated with eager torch ops
+        # (environment.py:252-257 -> utils.py:204-217 over oracle/torch_ref.py), same uniforms
+        from oracle import torch_ref as tr
+        cds = []
+        for uf, uv in uni:
+            pts, _ = tr.batch_sample(verts[:, a].contiguous(), faces, uf, uv)
+            cds.append(tr.chamfer_distance(pts, gt)[0])
+        ref_score = 9000.0 * torch.stack(cds).mean(0)
+        assert float((scores[:, a] - ref_score).abs().max() / ref_score.abs().max()) < 1e-5
     act, best = ptk_b200.policy.best_actions(scores, torch.zeros(E, A, device="cuda"))
     assert torch.equal(act, scores.argmin(1)) and torch.equal(best, scores.min(1).values)
 

@@ -21,3 +21,8 @@ timeout 600 python tools/recon_profile.py 16 > $OUT/${TAG}_recon_profile.txt 2>&
 timeout 600 python tools/gemm_check.py 31184,300,300 31184,448,300 > $OUT/${TAG}_gemm_check.txt 2>&1
 timeout 600 python tools/agg_bench.py 256 20 > $OUT/${TAG}_agg_bench.txt 2>&1
 tail -3 $OUT/${TAG}_pytest_gpu.log; cat $OUT/${TAG}_smoke.log | tail -2; cat $OUT/${TAG}_bench.json; tail -5 $OUT/${TAG}_bench.err
+timeout 600 python tools/chamfer_sweep.py > $OUT/${TAG}_chamfer_sweep.txt 2>&1
+timeout 300 python tools/vertex_front_bench.py > $OUT/${TAG}_vertex_front.txt 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:sgemm_fwd_tma -s 3 -c 1 -f -o $OUT/${TAG}_fwd \
+    python tools/fwd_one.py > $OUT/${TAG}_ncu_fwd.log 2>&1
+timeout 300 python tools/torch_gpu_baselines.py > $OUT/${TAG}_torch_gpu_baselines.txt 2>&1
