@@ -43,8 +43,8 @@ SIGNATURES = {
     "ptk_gcn_aggregate": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i64, _vp, _i64, _i64, _i64, _vp, C.c_int, _vp, _vp]),
     "ptk_gcn_aggregate_ex": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i64, _i64, _i64, _vp,
                                        C.c_int, _vp, _i64, _i64, _vp]),
-    "ptk_gcn_aggregate_tiled": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp,
-                                          _i64, _i64, _i64, _vp, C.c_int, _vp, _i64, _i64, _vp]),
+    "ptk_gcn_aggregate_tiled": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i64,
+                                          _vp, _i64, _i64, _i64, _vp, C.c_int, _vp, _i64, _i64, _vp]),
     "ptk_gcn_linear_fwd_split": (C.c_int, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _vp, C.c_int, _vp, _vp]),
     "ptk_gcn_bias_grad_workspace_bytes": (_sz, [_i64, _i64]),
     "ptk_gcn_bias_grad": (C.c_int, [_vp, _i64, _i64, _i64, _vp, _vp, _sz, _vp]),

@@ -30,6 +30,8 @@
 //     defining arithmetic, and the few queries whose runner-up chunk is within the proven error bound
 //     are re-scanned exactly (chamfer_nn_exact2_kernel, list mode).  Results are bit-identical to
 //     PTK_CHAMFER_EXACT (the 6-op scan on packed FP32x2, kept selectable for checks).
+#include <atomic>
+
 #include "chamfer_kernel2.cuh"
 
 namespace ptk {
@@ -41,7 +43,8 @@ constexpr int CH_MINB = 3;   // exact scan
 constexpr int CH_MINB_F = 4; // filter scan
 constexpr int CH_TT_F = 1024; // targets per TMA tile (double buffered: 2 x 4 x 4 KB)
 
-static int g_chamfer_algo = PTK_CHAMFER_FILTER;
+// process-wide choice of the scan (both give identical results); atomic: other host threads may launch while it is set
+static std::atomic<int> g_chamfer_algo{PTK_CHAMFER_FILTER};
 
 // workspace: [PairAux B][soa_x B*4*P1p][soa_y B*4*P2p][keys_x B*P1][keys_y B*P2][rescue_x B*P1][rescue_y B*P2]
 //            [flag_x B*P1][flag_y B*P2][count 2B]      (P?p = cloud size padded to SOA_PAD points)
@@ -225,7 +228,7 @@ static int launch_nn(const float *x, const float *y, int64_t B, int64_t P1, int6
     const int ndir = dir_only >= 0 ? 1 : 2;
     const int64_t Pq = dir_only == 0 ? P1 : (dir_only == 1 ? P2 : (P1 > P2 ? P1 : P2));
     const int64_t Pt = dir_only == 0 ? P2 : (dir_only == 1 ? P1 : (P1 > P2 ? P1 : P2));
-    const bool filter = g_chamfer_algo == PTK_CHAMFER_FILTER;
+    const bool filter = g_chamfer_algo.load(std::memory_order_relaxed) == PTK_CHAMFER_FILTER;
     NNPlan p = plan_nn(B, Pq, Pt, ndir, filter ? CH_MINB_F : CH_MINB);
     u64 *keys_x = dir_only == 1 ? nullptr : w.keys_x;
     u64 *keys_y = dir_only == 0 ? nullptr : w.keys_y;
@@ -288,11 +291,11 @@ extern "C" size_t ptk_chamfer_workspace_bytes(int64_t B, int64_t P1, int64_t P2)
 extern "C" int ptk_chamfer_set_algo(int algo) {
     PTK_REQUIRE(algo == PTK_CHAMFER_FILTER || algo == PTK_CHAMFER_EXACT, PTK_ERR_SHAPE,
                 "chamfer_set_algo: unknown algorithm %d", algo);
-    g_chamfer_algo = algo;
+    g_chamfer_algo.store(algo, std::memory_order_relaxed);
     return PTK_OK;
 }
 
-extern "C" int ptk_chamfer_get_algo(void) { return g_chamfer_algo; }
+extern "C" int ptk_chamfer_get_algo(void) { return g_chamfer_algo.load(std::memory_order_relaxed); }
 
 extern "C" int ptk_chamfer_rescued(const void *workspace, int64_t B, int64_t P1, int64_t P2,
                                    int64_t *n_rescued, ptk_stream_t stream) {
@@ -308,7 +311,7 @@ extern "C" int ptk_chamfer_rescued(const void *workspace, int64_t B, int64_t P1,
         for (int64_t i = 0; i < 2 * B; ++i) n += h[i];
     cudaFreeHost(h);
     PTK_CHECK_CUDA(e);
-    *n_rescued = g_chamfer_algo == PTK_CHAMFER_FILTER ? n : 0;
+    *n_rescued = g_chamfer_algo.load(std::memory_order_relaxed) == PTK_CHAMFER_FILTER ? n : 0;
     return PTK_OK;
 }
 

@@ -713,9 +713,9 @@ struct AggTiles {
     const int32_t *ucol;
     const uint16_t *lidx;
 };
-int aggregate_union_launch(const int32_t *rowptr, const int32_t *col, const float *val, const AggHubs &hb, const AggTiles &tl,
-                           int max_union, bool have_hubs, int64_t Nv, const float *in, int64_t B, int64_t C, int64_t L,
-                           const float *bias, int relu, float *out, int64_t ldi, int64_t ldo, int hubs_first,
+int aggregate_union_launch(int mode, const int32_t *rowptr, const int32_t *col, const float *val, const AggHubs &hb,
+                           const AggTiles &tl, int max_union, bool have_hubs, int64_t Nv, const float *in, int64_t B, int64_t C,
+                           int64_t L, const float *bias, int relu, float *out, int64_t ldi, int64_t ldo, int hubs_first,
                            int prefetch_next, cudaStream_t st);  // gcn_aggregate_union.cu
 }  // namespace ptk
 
@@ -723,9 +723,9 @@ extern "C" int ptk_gcn_aggregate_tiled(const int32_t *rowptr, const int32_t *col
                                        const int32_t *hubs, int32_t n_hubs, const int32_t *common_col,
                                        const float *common_w, int32_t n_common, const float *hub_alpha,
                                        const uint8_t *row_skip, const int32_t *tile_uptr, const int32_t *tile_ucol,
-                                       const uint16_t *tile_lidx, int32_t max_union, int64_t Nv, const float *in,
-                                       int64_t B, int64_t C, int64_t L, const float *bias, int relu, float *out,
-                                       int64_t ldi, int64_t ldo, ptk_stream_t stream) {
+                                       const uint16_t *tile_lidx, int32_t max_union, int32_t mode, int64_t Nv,
+                                       const float *in, int64_t B, int64_t C, int64_t L, const float *bias, int relu,
+                                       float *out, int64_t ldi, int64_t ldo, ptk_stream_t stream) {
     const int64_t ldi_e = ldi <= 0 ? C : ldi, ldo_e = ldo <= 0 ? C : ldo;
     const bool vec = rowptr && col && val && in && out && in != out && B > 0 && Nv > 0 && C > 0 && L >= 1 && L <= C &&
                      (C % 4 == 0) && (ldi_e % 4 == 0) && (ldo_e % 4 == 0) && ldi_e >= C && ldo_e >= C &&
@@ -733,7 +733,17 @@ extern "C" int ptk_gcn_aggregate_tiled(const int32_t *rowptr, const int32_t *col
                      Nv * ldi_e * 4 <= 0xffffffffLL;
     const bool common = n_common > 0;
     const bool common_ok = !common || (hubs && n_hubs > 0 && common_col && common_w && hub_alpha && row_skip);
-    if (vec && common_ok && tile_uptr && tile_ucol && tile_lidx && max_union > 0 && PTK_TUNING_ENV("PTK_AGG_UNION") != 2) {
+    PTK_REQUIRE(mode >= PTK_AGG_AUTO && mode <= PTK_AGG_RING, PTK_ERR_SHAPE, "gcn_aggregate_tiled: unknown mode %d", mode);
+    // PTK_AGG_AUTO: the form measured fastest on B200 (profiles/r02_gcn_aggregate_forms.txt) -- the dense-tile product for
+    // wide layers (more than 128 aggregated channels) and, when nothing is passed through (the compact head of the fused
+    // layer), at large batches or on dense graphs (largest tile union >= 48 rows); the L2 gather everywhere else.
+    int form = mode;
+    if (mode == PTK_AGG_AUTO) {
+        const bool wide = L > 128;
+        const bool no_pass = (L + 3) / 4 == C / 4;
+        form = (wide || (no_pass && (B >= 64 || max_union >= 48))) ? PTK_AGG_DENSE_TILE : PTK_AGG_L2_GATHER;
+    }
+    if (form != PTK_AGG_L2_GATHER && vec && common_ok && tile_uptr && tile_ucol && tile_lidx && max_union > 0) {
         AggHubs hb;
         const bool have_hubs = hubs && n_hubs > 0;
         hb.hubs = hubs; hb.n_hubs = have_hubs ? n_hubs : 0;
@@ -744,8 +754,9 @@ extern "C" int ptk_gcn_aggregate_tiled(const int32_t *rowptr, const int32_t *col
         const int hubs_first = (double)B * Nv * (ldi_e + ldo_e) * 4.0 < 100e6;
         int prefetch_next = !hubs_first;
         if (PTK_TUNING_ENV("PTK_AGG_PF") > 0) prefetch_next = PTK_TUNING_ENV("PTK_AGG_PF") == 1;
-        const int rc = aggregate_union_launch(rowptr, col, val, hb, tl, max_union, have_hubs, Nv, in, B, C, L, bias, relu, out,
-                                              ldi_e, ldo_e, hubs_first, prefetch_next, as_stream(stream));
+        const int rc = aggregate_union_launch(form == PTK_AGG_DENSE_TILE ? 1 : 2, rowptr, col, val, hb, tl, max_union, have_hubs, Nv,
+                                              in, B, C, L, bias, relu, out, ldi_e, ldo_e, hubs_first, prefetch_next,
+                                              as_stream(stream));
         if (rc != 0) return rc < 0 ? rc : PTK_OK;
     }
     return ptk_gcn_aggregate_ex(rowptr, col, val, hubs, n_hubs, common_col, common_w, n_common, hub_alpha, row_skip, Nv, in,

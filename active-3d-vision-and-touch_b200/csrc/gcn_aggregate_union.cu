@@ -1,4 +1,4 @@
-// GCN vertex aggregation, shared-memory union form (sm_100a).
+// GCN vertex aggregation over per-tile neighbour unions (sm_100a): the dense-tile form and the shared-memory ring form.
 //
 // Same contract as gcn_aggregate_tile_kernel (gcn_aggregate.cu; replaces the dense `torch.matmul(adj, features[:, :, :L])`
 // + cat + bias + activation of GCN_layer.forward, pterotactyl/reconstruction/vision/model.py:354-363):
@@ -6,26 +6,32 @@
 //   out[b,i,c] = act( sum_{e in row i} val[e] * in[b,col[e],c] + bias[c] )   c <  L
 //   out[b,i,c] = act( in[b,i,c] )                                             c >= L
 //
-// What the tile kernel left on the table (profiles/r01_ncu_gcn_aggregate_tile_v12.txt): DRAM traffic already equals
+// What the L2 gather leaves on the table (profiles/r01_ncu_gcn_aggregate_tile_v12.txt): DRAM traffic already equals
 // the algorithmic bytes, but every neighbour row is fetched from L2 once per edge -- 9.5 (finger graph) to 16 (grasp
-// graph) reads of each input row per batch element, each a dependent ~300-cycle load (long-scoreboard 7.3 stalls per
-// issue).  The 8 rows of a tile share most of their neighbours (19-vertex charts + their twins): the UNION of a
-// tile's neighbour columns is 2.3-3.0x smaller than the sum of its degrees.  Here the host lists that union once per
-// tile (graph.tile_unions), and per batch element the CTA brings the union's rows into shared memory with cp.async
-// (every warp copies its share of the rows, one row = one 16-byte LDGSTS per lane; completion is reported to the
-// slot's mbarrier by cp.async.mbarrier.arrive.noinc) into a 2-4 slot ring and gathers from shared memory (LDS.128 by
-// local index) while the copies of the next batch elements are in flight.  No CTA barrier in the loop: full / empty
-// mbarriers only.  Wide layers (L > 128 channels: L = C = 300) are walked in column chunks of <= 32 float4 groups.
+// graph) reads of each input row per batch element.  The 8 rows of a tile share most of their neighbours (19-vertex
+// charts + their twins): the UNION of a tile's neighbour columns is 2.3-3.0x smaller than the sum of its degrees.  The
+// host lists that union once per tile (graph.tile_unions); two kernels forms use it (mode of ptk_gcn_aggregate_tiled):
 //
-// MEASURED (B200, B = 256, C = 300, L = 99; profiles/r02_gcn_aggregate_union.txt) -- this form is SLOWER than the L2
-// gather + L2 prefetch of gcn_aggregate_tile_kernel and therefore off by default (ops.use_union):
-//     finger graph 348 us vs 257 us, grasp graph 468 us vs 393 us, plain vision graph 284 us vs 200 us; B = 16: 29 vs 18 us.
-// Three producer schemes were tried: one cp.async.bulk per row from warp 0 (458 us: the TMA unit retires a 400-byte
-// bulk copy only every ~65 cycles per SM), a dedicated 9th producer warp with cp.async (355 us) and the cooperative
-// form kept here (348 us).  ncu on the producer-warp form: DRAM traffic again equals the algorithmic bytes, long-
-// scoreboard stalls fall from 7.3 to 3.6 per issue, but every gathered value now crosses the L1 / shared-memory
-// pipe twice (LDGSTS in, LDS out) and the 8 warps of a tile move in lock step with their slot -- the L2 gather keeps
-// 32 independent warps per SM with 8 loads in flight each, which hides L2 latency better than the ring does.
+// DENSE TILE (PTK_AGG_DENSE_TILE) -- a warp owns the tile for one batch element and computes it as a small dense product
+//   out[8 x C'] = A[8 x U] . X[U x C']: every union row is read from L2 once and accumulated into up to 8 register rows;
+//   A (weights, 0 where a row does not use the column) sits in shared memory.  FMA work grows 1.6-3.5x, L2 reads fall
+//   2.3-3.0x.  Measured (profiles/r02_gcn_aggregate_forms.txt, B = 256): L = C = 300 grasp graph 826 -> 648 us, finger graph
+//   500 -> 467 us; compact head of the fused forward (no pass-through columns) 336 -> 267 us / 212 -> 195 us; SLOWER where
+//   201 pass-through columns have to be copied by the same warp (finger graph 259 -> 294 us) and at the training batch on
+//   the sparse graphs (17.7 -> 19.7 us).  PTK_AGG_AUTO picks it exactly where it wins.
+//
+// RING (PTK_AGG_RING) -- per batch element the CTA brings the union's rows into shared memory with cp.async (every warp
+//   copies its share of the rows, one row = one 16-byte LDGSTS per lane; completion is reported to the slot's mbarrier by
+//   cp.async.mbarrier.arrive.noinc) into a 2-4 slot ring and gathers from shared memory (LDS.128 by local index) while the
+//   copies of the next batch elements are in flight; no CTA barrier in the loop.  Wide layers in column chunks of <= 32
+//   float4 groups.  MEASURED SLOWER than the L2 gather everywhere (profiles/r02_gcn_aggregate_union.txt): finger graph 348
+//   vs 257 us, grasp graph 468 vs 393 us, B = 16: 29 vs 18 us.  Three producer schemes were tried: one cp.async.bulk per
+//   row from warp 0 (458 us: the TMA unit retires a 400-byte bulk copy only every ~65 cycles per SM), a dedicated ninth
+//   producer warp with cp.async (355 us) and the cooperative form kept here (348 us).  ncu: DRAM traffic again equals
+//   the algorithmic bytes, long-scoreboard stalls fall from 7.3 to 3.6 per issue, but every gathered value crosses the
+//   L1 / shared-memory pipe twice (LDGSTS in, LDS out) and the 8 warps of a tile move in lock step with their slot.
+//   Kept for comparison; never picked by PTK_AGG_AUTO.
+//
 // Hub rows (degree > HUB_DEG) and their common neighbour set are handled exactly as in the tile kernel.
 #include "gcn_aggregate_common.cuh"
 
@@ -101,7 +107,7 @@ gcn_aggregate_union_kernel(const int32_t *__restrict__ rowptr, const int32_t *__
                            const float *__restrict__ val, const AggHubs hb, const AggTiles tl, unsigned hub_slots, int Nv,
                            const float *__restrict__ in, int B, int C, int L, const float *__restrict__ bias, int relu,
                            float *__restrict__ out, int BG, int n_tiles, int hubs_first, int ldi, int ldo, int nchunks,
-                           int gc, int n_stages, int prefetch_next) {
+                           int gc, int n_stages, int prefetch_next, int dense_mode) {
     // ldi / ldo: row strides (floats) of in / out; C channels are handled ([0, L) aggregated, [L, C) passed through)
     // nchunks x gc: the aggregated float4 groups are walked in nchunks chunks of gc (<= 32) groups
     extern __shared__ __align__(128) uint8_t au_dyn[];
@@ -237,6 +243,116 @@ gcn_aggregate_union_kernel(const int32_t *__restrict__ rowptr, const int32_t *__
     const int b0 = (int)group * BG;
     const int nb = min(B, b0 + BG) - b0;
     const int u0 = tl.uptr[tile], U = tl.uptr[tile + 1] - u0;
+    if (dense_mode) {
+        // ------------------------------------------------------------------ dense-tile form (BG == 8: warp = batch element)
+        // The tile's 8 rows as one small dense product  out[8 x C'] = A[8 x U] . X[U x C']  over the tile's neighbour
+        // union: every union row is read from L2 ONCE per batch element (not once per edge) and feeds up to 8
+        // accumulator rows held in registers; A (weights, 0 where a row does not use the column) sits in shared memory
+        // as [U][8] and is read with two broadcast LDS.128 per union row.  A row's neighbours are still added in
+        // ascending column order (the union is sorted), and fma(0, x, acc) == acc for finite x, so the result is
+        // bit-identical to the sparse gather for finite inputs.
+        float *sA = reinterpret_cast<float *>(au_dyn);
+        __shared__ int s_valid[AG_WARPS];
+        const int Up = (U + 3) & ~3;
+        for (int e = threadIdx.x; e < Up * 8; e += AU_THREADS) sA[e] = 0.f;
+        for (int u = threadIdx.x; u < Up; u += AU_THREADS) s_uoff[u] = u < U ? (uint32_t)tl.ucol[u0 + u] * row_bytes : 0u;
+        __syncthreads();
+        {
+            const int i = i0 + warp;
+            bool ok = false;
+            if (i < Nv) {
+                const int beg = rowptr[i], end = rowptr[i + 1];
+                ok = !(hb.row_skip ? hb.row_skip[i] != 0 : (hub_slots > 0 && end - beg > HUB_DEG));
+                if (ok)
+                    for (int e = beg + lane; e < end; e += 32) sA[(int)tl.lidx[e] * 8 + warp] = val[e];
+            }
+            if (lane == 0) s_valid[warp] = ok ? 1 : 0;
+        }
+        __syncthreads();
+        const int b = b0 + warp;
+        if (b >= B) return;
+        const float *inb = in + (size_t)b * bstride;
+        float *outb = out + (size_t)b * bstride_o;
+        if (npass > 0) {  // pass-through columns of the 8 rows: ask L2 for them now, copy them after the product
+            const int line0 = (gath * 16) >> 7, lines = (ngroups * 16 + 127) >> 7;
+            for (int r = 0; r < AU_TV; ++r)
+                if (i0 + r < Nv && line0 + lane < lines)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(inb + (size_t)(i0 + r) * ldi) + (line0 + lane) * 128));
+        }
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int g_here = min(gc, gath - ch * gc);
+            const int gl = min(lane, g_here - 1);
+            float acc[AU_TV][4];
+#pragma unroll
+            for (int r = 0; r < AU_TV; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
+            const char *src = reinterpret_cast<const char *>(inb) + (size_t)(ch * gc + gl) * 16;
+            for (int u = 0; u < Up; u += 4) {
+                float4 x[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) x[j] = __ldg(reinterpret_cast<const float4 *>(src + s_uoff[u + j]));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 w0 = *reinterpret_cast<const float4 *>(sA + (u + j) * 8);
+                    const float4 w1 = *reinterpret_cast<const float4 *>(sA + (u + j) * 8 + 4);
+                    const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+                    for (int r = 0; r < AU_TV; ++r) {
+                        acc[r][0] = fmaf(w[r], x[j].x, acc[r][0]); acc[r][1] = fmaf(w[r], x[j].y, acc[r][1]);
+                        acc[r][2] = fmaf(w[r], x[j].z, acc[r][2]); acc[r][3] = fmaf(w[r], x[j].w, acc[r][3]);
+                    }
+                }
+            }
+            if (lane < g_here) {
+                const int c0 = (ch * gc + lane) * 4;
+                float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (bias) bv = *reinterpret_cast<const float4 *>(bias + c0);
+#pragma unroll
+                for (int r = 0; r < AU_TV; ++r) {
+                    if (!s_valid[r]) continue;
+                    const float *self = inb + (size_t)(i0 + r) * ldi;
+                    float q[4] = {acc[r][0] + bv.x, acc[r][1] + bv.y, acc[r][2] + bv.z, acc[r][3] + bv.w};
+                    if (!bias) { q[0] = acc[r][0]; q[1] = acc[r][1]; q[2] = acc[r][2]; q[3] = acc[r][3]; }
+                    if (c0 + 4 > L) {
+                        const float4 sv4 = *reinterpret_cast<const float4 *>(self + c0);
+                        const float sv[4] = {sv4.x, sv4.y, sv4.z, sv4.w};
+#pragma unroll
+                        for (int t = 0; t < 4; ++t)
+                            if (c0 + t >= L) q[t] = sv[t];
+                    }
+                    if (relu) {
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) q[t] = fmaxf(q[t], 0.f);
+                    }
+                    __stcs(reinterpret_cast<float4 *>(outb + (size_t)(i0 + r) * ldo + c0), make_float4(q[0], q[1], q[2], q[3]));
+                }
+            }
+        }
+        if (npass > 0) {
+            for (int r0 = 0; r0 < AU_TV; r0 += 2) {  // two rows (up to 4 float4 per lane) in flight
+                float4 p[2][2];
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int r = r0 + rr;
+                    const float *self = inb + (size_t)(i0 + r) * ldi;
+                    const bool ok = s_valid[r] != 0;
+                    p[rr][0] = (ok && pass0) ? __ldcs(reinterpret_cast<const float4 *>(self + pv0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    p[rr][1] = (ok && pass1) ? __ldcs(reinterpret_cast<const float4 *>(self + pv1)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+#pragma unroll
+                for (int rr = 0; rr < 2; ++rr) {
+                    const int r = r0 + rr;
+                    if (!s_valid[r]) continue;
+                    const float *self = inb + (size_t)(i0 + r) * ldi;
+                    float *o = outb + (size_t)(i0 + r) * ldo;
+                    if (pass0) __stcs(reinterpret_cast<float4 *>(o + pv0), relu4(p[rr][0], relu));
+                    if (pass1) __stcs(reinterpret_cast<float4 *>(o + pv1), relu4(p[rr][1], relu));
+                    for (int v = gath + 64 + lane; v < ngroups; v += 32)
+                        __stcs(reinterpret_cast<float4 *>(o + v * 4), relu4(__ldcs(reinterpret_cast<const float4 *>(self + v * 4)), relu));
+                }
+            }
+        }
+        return;
+    }
     const uint32_t srow = (uint32_t)gc * 16u;              // bytes of one union row in a stage
     const uint32_t stage_bytes = (uint32_t)U * srow;       // (the host sized the ring for the largest union)
     const uint32_t stage_pitch = (stage_bytes + 127u) & ~127u;
@@ -354,10 +470,11 @@ static unsigned long long g_au_optin[3] = {0ull, 0ull, 0ull};
 
 // Returns 1 when the union kernel was launched, 0 when the shape is outside its range (the caller falls back to the
 // tile kernel), < 0 on error.
-int aggregate_union_launch(const int32_t *rowptr, const int32_t *col, const float *val, const AggHubs &hb, const AggTiles &tl,
-                           int max_union, bool have_hubs, int64_t Nv, const float *in, int64_t B, int64_t C, int64_t L,
-                           const float *bias, int relu, float *out, int64_t ldi, int64_t ldo, int hubs_first,
+int aggregate_union_launch(int mode, const int32_t *rowptr, const int32_t *col, const float *val, const AggHubs &hb,
+                           const AggTiles &tl, int max_union, bool have_hubs, int64_t Nv, const float *in, int64_t B, int64_t C,
+                           int64_t L, const float *bias, int relu, float *out, int64_t ldi, int64_t ldo, int hubs_first,
                            int prefetch_next, cudaStream_t st) {
+    const int dense_mode = mode == 1 ? 1 : 0;  // 1: dense-tile product (warp = batch element), else the shared-memory ring
     const int gath = (int)((L + 3) / 4);
     if (max_union <= 0 || max_union > AU_MAXU || gath < 1 || gath > 96) return 0;
     const int nchunks = (gath + 31) / 32;
@@ -369,13 +486,16 @@ int aggregate_union_launch(const int32_t *rowptr, const int32_t *col, const floa
     int n_stages = 4;
     while (n_stages > 2 && 3 * (stat + n_stages * pitch + 128) > 225 * 1024) --n_stages;
     if (PTK_TUNING_ENV("PTK_AGG_STAGES") > 0) n_stages = PTK_TUNING_ENV("PTK_AGG_STAGES");
-    const size_t smem = (size_t)n_stages * pitch + 128;
+    size_t smem = (size_t)n_stages * pitch + 128;
+    if (dense_mode) smem = (size_t)((max_union + 3) & ~3) * 8 * sizeof(float) + 128;  // A [U][8]
     if (stat + smem > 220 * 1024) return 0;
-    int BG = 8;
+    int BG = 8;  // the dense-tile form needs exactly 8: warp = batch element
     const long long slots = 6LL * sm_count();
     const int n_tiles = (int)ceil_div(Nv, AU_TV);
-    while (BG > 1 && (long long)n_tiles * ceil_div(B, BG) < slots) BG >>= 1;
-    if (PTK_TUNING_ENV("PTK_AGG_BG") > 0) BG = PTK_TUNING_ENV("PTK_AGG_BG");
+    if (!dense_mode) {
+        while (BG > 1 && (long long)n_tiles * ceil_div(B, BG) < slots) BG >>= 1;
+        if (PTK_TUNING_ENV("PTK_AGG_BG") > 0) BG = PTK_TUNING_ENV("PTK_AGG_BG");
+    }
     const bool common = hb.n_common > 0;
     const unsigned hub_slots = have_hubs ? (unsigned)(common ? BG : BG * hb.n_hubs) : 0u;
     const unsigned grid = (unsigned)((hub_slots + n_tiles) * ceil_div(B, BG));
@@ -390,7 +510,7 @@ int aggregate_union_launch(const int32_t *rowptr, const int32_t *col, const floa
         }                                                                                                                 \
         launch_pdl(gcn_aggregate_union_kernel<NGv>, dim3(grid), dim3(AU_THREADS), smem, st, rowptr, col, val, hb, tl, hub_slots, \
                    (int)Nv, in, (int)B, (int)C, (int)L, bias, relu, out, BG, n_tiles, hubs_first, (int)ldi, (int)ldo, nchunks, \
-                   gc, n_stages, prefetch_next);                                                                          \
+                   gc, n_stages, prefetch_next, dense_mode);                                                              \
     } while (0)
     if (NG == 1) PTK_UNION(1);
     else if (NG == 2) PTK_UNION(2);

@@ -63,7 +63,7 @@ int aggregate(const ptk_gcn_csr *g, int64_t Nv, const float *in, int64_t B, int6
         // the kernel form (== the plain arrays when no common set was split off), rows staged in shared memory per tile
         return ptk_gcn_aggregate_tiled(g->k_rowptr, g->k_col, g->k_val, g->k_hubs, g->k_n_hubs, g->common_col, g->common_w,
                                        g->n_common, g->alpha, g->row_skip, g->tile_uptr, g->tile_ucol, g->tile_lidx,
-                                       g->max_union, Nv, in, B, C, L, bias, relu, out, ldi, ldo, stream);
+                                       g->max_union, PTK_AGG_AUTO, Nv, in, B, C, L, bias, relu, out, ldi, ldo, stream);
     return ptk_gcn_aggregate_ex(g->rowptr, g->col, g->val, g->hubs, g->n_hubs, nullptr, nullptr, 0, nullptr, nullptr, Nv,
                                 in, B, C, L, bias, relu, out, ldi, ldo, stream);
 }

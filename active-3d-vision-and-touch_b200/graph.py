@@ -70,8 +70,8 @@ TILE_ROWS = 8  # rows per tile of the shared-memory union kernel (csrc/gcn_aggre
 def tile_unions(rowptr, col, skip, n, tile_rows=TILE_ROWS):
     """Per tile of `tile_rows` consecutive rows: the sorted union of the neighbour columns of its rows (rows flagged in
     `skip` -- the hub rows, which dedicated CTAs process -- left out), and per CSR entry the position of its column in
-    its tile's union.  The kernel stages the union's rows in shared memory once per batch element and gathers by local
-    index (ptk_gcn_aggregate_tiled).  Returns (uptr (n_tiles+1) i32, ucol i32, lidx (nnz) u16, largest union)."""
+    its tile's union (ptk_gcn_aggregate_tiled: the dense-tile form reads every union row once per batch element, the
+    ring form stages the rows in shared memory).  Returns (uptr (n_tiles+1) i32, ucol i32, lidx (nnz) u16, largest union)."""
     n_tiles = (n + tile_rows - 1) // tile_rows
     uptr = np.zeros(n_tiles + 1, np.int32)
     ucols = []
@@ -163,10 +163,8 @@ class Graph:
         import ctypes as C
 
         from . import _lib
-        from . import ops
         cache = self.__dict__.setdefault("_csr_structs", {})
-        tiles = bool(ops.use_union)  # the tile unions travel only when the shared-memory union kernel is selected
-        key = (bool(transpose), tiles)
+        key = bool(transpose)
         hit = cache.get(key)
         if hit is None:
             if transpose:
@@ -177,8 +175,7 @@ class Graph:
             hit = cache[key] = _lib.GcnCsr(
                 ptr(rp), ptr(col), ptr(val), ptr(hubs), nh, ptr(k.rowptr), ptr(k.col), ptr(k.val), ptr(k.hubs), k.n_hubs,
                 ptr(k.common_col), ptr(k.common_w), k.n_common, ptr(k.alpha), ptr(k.row_skip),
-                ptr(k.tile_uptr if tiles else None), ptr(k.tile_ucol if tiles else None),
-                ptr(k.tile_lidx if tiles else None), k.max_union if tiles else 0)
+                ptr(k.tile_uptr), ptr(k.tile_ucol), ptr(k.tile_lidx), k.max_union)
         return hit
 
     @staticmethod

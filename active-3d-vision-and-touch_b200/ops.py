@@ -374,9 +374,11 @@ GEMM_AUTO, GEMM_FFMA, GEMM_TF32X3 = 0, 1, 2
 algo = {"fwd_train": GEMM_FFMA, "fwd_infer": GEMM_AUTO, "dgrad": GEMM_AUTO, "wgrad": GEMM_AUTO}
 batch_bias_grad = True  # one slab + two launches for the bias gradients of a GCN pass (tests flip this)
 fuse_layers = True  # training forward of 'cut' layers: split-epilogue GEMM + strided aggregate (tests flip this)
-# aggregate: stage each tile's neighbour-row union in shared memory (ptk_gcn_aggregate_tiled, gcn_aggregate_union.cu).
-# Bit-identical to the L2 gather and OFF by default: measured 25-40 % slower at every batch size on B200.
-use_union = False
+# Form of the vertex aggregation (include/ptk.h: PTK_AGG_*): "auto" lets the library pick the form measured fastest for
+# the shape (dense-tile product for wide layers and for the compact head at large batches / on dense graphs, the L2
+# gather otherwise); "l2", "dense", "ring" force one.  All forms give identical results (tests flip this).
+AGG_FORMS = {"auto": 0, "l2": 1, "dense": 2, "ring": 3}
+aggregate_form = "auto"
 
 
 def _linear_fwd(X2, W2, out=None, algo_id=GEMM_FFMA):
@@ -424,16 +426,13 @@ def _aggregate(g: Graph, H3, Lc, bias, relu, transpose=False, out=None):
     vector_path = Cc % 4 == 0 and 1 <= Lc <= 384 and H3.data_ptr() % 16 == 0 and out.data_ptr() % 16 == 0 and \
         (bias is None or bias.data_ptr() % 16 == 0)
     if vector_path and (k.n_common > 0 or k.tile_uptr is not None):
-        # kernel form (hub rows' common set split off when there is one) + the tiles' neighbour unions: the rows are
-        # staged in shared memory per tile (ptk_gcn_aggregate_tiled; falls back to the L2 gather outside its range)
-        tiles = use_union and k.tile_uptr is not None
+        # kernel form (hub rows' common set split off when there is one) + the tiles' neighbour unions
         _lib.check(_lib.lib().ptk_gcn_aggregate_tiled(_p(k.rowptr), _p(k.col), _p(k.val), _p(k.hubs), k.n_hubs,
                                                       _p(k.common_col), _p(k.common_w), k.n_common, _p(k.alpha),
-                                                      _p(k.row_skip), _p(k.tile_uptr if tiles else None),
-                                                      _p(k.tile_ucol if tiles else None),
-                                                      _p(k.tile_lidx if tiles else None), k.max_union if tiles else 0,
-                                                      Nv, _p(H3), B, Cc, Lc, _p(bias), int(relu), _p(out), 0, 0,
-                                                      _stream()), "ptk_gcn_aggregate_tiled")
+                                                      _p(k.row_skip), _p(k.tile_uptr), _p(k.tile_ucol), _p(k.tile_lidx),
+                                                      k.max_union, AGG_FORMS[aggregate_form], Nv, _p(H3), B, Cc, Lc,
+                                                      _p(bias), int(relu), _p(out), 0, 0, _stream()),
+                   "ptk_gcn_aggregate_tiled")
         return out
     if transpose:
         rp, col, val, hubs, nh = g.rowptr_t, g.col_t, g.val_t, g.hubs_t, g.n_hubs_t
@@ -463,11 +462,9 @@ def _fused_layer_fwd(g: Graph, X2, W2, Lc, bias, B, Nv, head_buf, x_bits=None):
     _lib.check(L.ptk_gcn_linear_fwd_split(_p(X2), _p(W2), M, K, N, Lp, _p(head_buf), _p(out), 1, _p(x_bits),
                                           _stream()), "ptk_gcn_linear_fwd_split")
     k = g.fwd_k
-    tiles = use_union and k.tile_uptr is not None
     _lib.check(L.ptk_gcn_aggregate_tiled(_p(k.rowptr), _p(k.col), _p(k.val), _p(k.hubs), k.n_hubs, _p(k.common_col),
-                                         _p(k.common_w), k.n_common, _p(k.alpha), _p(k.row_skip),
-                                         _p(k.tile_uptr if tiles else None), _p(k.tile_ucol if tiles else None),
-                                         _p(k.tile_lidx if tiles else None), k.max_union if tiles else 0, Nv,
+                                         _p(k.common_w), k.n_common, _p(k.alpha), _p(k.row_skip), _p(k.tile_uptr),
+                                         _p(k.tile_ucol), _p(k.tile_lidx), k.max_union, AGG_FORMS[aggregate_form], Nv,
                                          _p(head_buf), B, Lp, Lc, _p(bias), 1, _p(out), Lp, N, _stream()),
                "ptk_gcn_aggregate_tiled")
     return out

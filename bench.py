@@ -699,6 +699,11 @@ def extra_measurements(torch, ptk_b200, dev, hbm_peak, hbm_src):
     out["gcn_aggregate"] = {"shape": f"B={Bh} N={g.n} C={C_} L={L_} (fwd, bias+ReLU fused)", "ms": ms,
                             "achieved_gbs": alg / (ms * 1e-3) / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
                             "frac": alg / (ms * 1e-3) / 1e9 / hbm_peak, "algorithmic_bytes": alg}
+    # ... and the full-propagate layer (L = C = 300: output layer of the autoencoder encoder / the DDQN graph model)
+    ms_w = timeit(lambda: ptk_b200.ops._aggregate(g, H, C_, bias, False, out=o), 20)
+    out["gcn_aggregate"]["wide_layer"] = {"shape": f"B={Bh} N={g.n} C=L={C_}", "ms": ms_w,
+                                          "achieved_gbs": alg / (ms_w * 1e-3) / 1e9,
+                                          "frac": alg / (ms_w * 1e-3) / 1e9 / hbm_peak}
     del H, o
 
     # (the config-3-shaped reconstruction step is measured by recon_step_measurement() on every rank)

@@ -155,18 +155,26 @@ int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, const float 
                          const uint8_t *row_skip, int64_t Nv, const float *in, int64_t B, int64_t C,
                          int64_t L, const float *bias, int relu, float *out, int64_t ldi, int64_t ldo,
                          ptk_stream_t stream);
-/* ptk_gcn_aggregate_ex with the neighbour rows staged in shared memory (csrc/gcn_aggregate_union.cu).  The rows of a
- * tile of 8 consecutive vertices share most of their neighbours; the caller lists, per tile, the sorted union of the
- * neighbour columns of its non-hub rows: tile_uptr (ceil(Nv/8)+1 offsets), tile_ucol, and per CSR entry e the index
- * tile_lidx[e] of col[e] in its tile's union; max_union = the largest union.  Per batch element a CTA copies the
- * union's rows into shared memory (cp.async.bulk, mbarrier ring) and gathers from there.  Same results as
- * ptk_gcn_aggregate_ex; falls back to it when the tile arrays are NULL or the shape is outside the kernel's range
- * (unions above 256 rows, non-vector shapes). */
+/* ptk_gcn_aggregate_ex with per-tile neighbour unions (csrc/gcn_aggregate_union.cu).  The rows of a tile of 8
+ * consecutive vertices share most of their neighbours; the caller lists, per tile, the sorted union of the neighbour
+ * columns of its non-hub rows: tile_uptr (ceil(Nv/8)+1 offsets), tile_ucol, and per CSR entry e the index
+ * tile_lidx[e] of col[e] in its tile's union; max_union = the largest union.  mode:
+ *   PTK_AGG_AUTO        the form measured fastest for the shape (dense tile for > 128 aggregated channels and, without
+ *                       pass-through columns, at batch >= 64 or on dense graphs; the L2 gather otherwise)
+ *   PTK_AGG_L2_GATHER   ptk_gcn_aggregate_ex
+ *   PTK_AGG_DENSE_TILE  a warp owns the tile for one batch element: out[8 x C'] = A[8 x U] . X[U x C'], every union row
+ *                       read from L2 once and accumulated into up to 8 register rows, A (0 where unused) in shared memory
+ *   PTK_AGG_RING        union rows staged in shared memory by cp.async through an mbarrier ring, gathered with LDS
+ *                       (measured slower than the L2 gather on B200; kept for comparison)
+ * All forms add a row's neighbours in ascending column order: identical results (for finite inputs in the dense form,
+ * where an unused column contributes fma(0, x, acc)).  Falls back to ptk_gcn_aggregate_ex when the tile arrays are NULL
+ * or the shape is outside the kernels' range (unions above 256 rows, non-vector shapes). */
+enum { PTK_AGG_AUTO = 0, PTK_AGG_L2_GATHER = 1, PTK_AGG_DENSE_TILE = 2, PTK_AGG_RING = 3 };
 int ptk_gcn_aggregate_tiled(const int32_t *rowptr, const int32_t *col, const float *val, const int32_t *hubs,
                             int32_t n_hubs, const int32_t *common_col, const float *common_w, int32_t n_common,
                             const float *hub_alpha, const uint8_t *row_skip, const int32_t *tile_uptr,
-                            const int32_t *tile_ucol, const uint16_t *tile_lidx, int32_t max_union, int64_t Nv,
-                            const float *in, int64_t B, int64_t C, int64_t L, const float *bias, int relu,
+                            const int32_t *tile_ucol, const uint16_t *tile_lidx, int32_t max_union, int32_t mode,
+                            int64_t Nv, const float *in, int64_t B, int64_t C, int64_t L, const float *bias, int relu,
                             float *out, int64_t ldi, int64_t ldo, ptk_stream_t stream);
 /* gbias[c] = sum_{rows} g[row,c] for c < L, 0 for L <= c < C  (g is (M,C)); overwrites gbias.
  * Deterministic two-stage column sum; workspace from ptk_gcn_bias_grad_workspace_bytes. */

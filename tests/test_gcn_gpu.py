@@ -199,30 +199,32 @@ def test_full_size_config3_properties(golden):
 
 @pytest.mark.parametrize("name", ["p_adj", "g_adj", "p_origional"])
 @pytest.mark.parametrize("B,C,L,relu", [(3, 300, 99, True), (9, 100, 99, True), (2, 300, 300, False), (17, 132, 33, True),
-                                        (1, 448, 448, False), (5, 300, 3, False)])
-def test_shared_memory_union_gather_is_bit_identical_to_the_l2_gather(golden, name, B, C, L, relu):
-    """ptk_gcn_aggregate_tiled (neighbour-row unions staged in shared memory by cp.async.bulk, gcn_aggregate_union.cu)
-    against the tile kernel that gathers from L2: same neighbour order, same FMA chain => identical bits; forward and
-    transposed graph, batch groups that do not divide B, wide layers walked in column chunks."""
+                                        (1, 448, 448, False), (5, 300, 3, False), (70, 100, 99, True)])
+def test_aggregate_forms_are_bit_identical(golden, name, B, C, L, relu):
+    """ptk_gcn_aggregate_tiled: the dense-tile product (every union row of a tile read once, 8 accumulator rows in
+    registers) and the shared-memory ring (rows staged by cp.async behind mbarriers) against the L2 gather -- same
+    neighbour order, same FMA chain => identical bits; forward and transposed graph, batch groups that do not divide B,
+    wide layers walked in column chunks; "auto" must equal them too."""
     adj = golden("adjacency")
     gr = Graph.from_csr(adj[name + "_rowptr"], adj[name + "_col"], "cuda")
     assert gr.fwd_k.tile_uptr is not None and 0 < gr.fwd_k.max_union <= 256
     gen = torch.Generator(device="cuda").manual_seed(B * 1000 + C + L)
     H = torch.randn(B, gr.n, C, device="cuda", generator=gen)
     bias = torch.randn(C, device="cuda", generator=gen)
-    res = []
-    for flag in (True, False):
-        ptk_b200.ops.use_union = flag
-        try:
+    res = {}
+    try:
+        for form in ("l2", "dense", "ring", "auto"):
+            ptk_b200.ops.aggregate_form = form
             before = ptk_b200._lib.launch_count()
             a = ptk_b200.ops._aggregate(gr, H, L, bias, relu)
             b = ptk_b200.ops._aggregate(gr, H, L, None, False, transpose=True)
             assert ptk_b200._lib.launch_count() - before == 2
-        finally:
-            ptk_b200.ops.use_union = False
-        res.append((a, b))
-    assert torch.equal(res[0][0], res[1][0])
-    assert torch.equal(res[0][1], res[1][1])
+            res[form] = (a, b)
+    finally:
+        ptk_b200.ops.aggregate_form = "auto"
+    for form in ("dense", "ring", "auto"):
+        assert torch.equal(res[form][0], res["l2"][0]), form
+        assert torch.equal(res[form][1], res["l2"][1]), form
 
 
 def test_random_graphs_with_and_without_common_hub_sets(oracle):
