@@ -735,13 +735,13 @@ extern "C" int ptk_gcn_aggregate_tiled(const int32_t *rowptr, const int32_t *col
     const bool common_ok = !common || (hubs && n_hubs > 0 && common_col && common_w && hub_alpha && row_skip);
     PTK_REQUIRE(mode >= PTK_AGG_AUTO && mode <= PTK_AGG_RING, PTK_ERR_SHAPE, "gcn_aggregate_tiled: unknown mode %d", mode);
     // PTK_AGG_AUTO: the form measured fastest on B200 (profiles/r02_gcn_aggregate_forms.txt) -- the dense-tile product for
-    // wide layers (more than 128 aggregated channels) and, when nothing is passed through (the compact head of the fused
-    // layer), at large batches or on dense graphs (largest tile union >= 48 rows); the L2 gather everywhere else.
+    // wide layers (more than 128 aggregated channels) and when nothing is passed through (the compact head of the fused
+    // layer); the L2 gather where the same warp would also have to copy pass-through columns.
     int form = mode;
     if (mode == PTK_AGG_AUTO) {
         const bool wide = L > 128;
         const bool no_pass = (L + 3) / 4 == C / 4;
-        form = (wide || (no_pass && (B >= 64 || max_union >= 48))) ? PTK_AGG_DENSE_TILE : PTK_AGG_L2_GATHER;
+        form = (wide || no_pass) ? PTK_AGG_DENSE_TILE : PTK_AGG_L2_GATHER;
     }
     if (form != PTK_AGG_L2_GATHER && vec && common_ok && tile_uptr && tile_ucol && tile_lidx && max_union > 0) {
         AggHubs hb;

@@ -17,8 +17,10 @@
 //   A (weights, 0 where a row does not use the column) sits in shared memory.  FMA work grows 1.6-3.5x, L2 reads fall
 //   2.3-3.0x.  Measured (profiles/r02_gcn_aggregate_forms.txt, B = 256): L = C = 300 grasp graph 826 -> 648 us, finger graph
 //   500 -> 467 us; compact head of the fused forward (no pass-through columns) 336 -> 267 us / 212 -> 195 us; SLOWER where
-//   201 pass-through columns have to be copied by the same warp (finger graph 259 -> 294 us) and at the training batch on
-//   the sparse graphs (17.7 -> 19.7 us).  PTK_AGG_AUTO picks it exactly where it wins.
+//   201 pass-through columns have to be copied by the same warp (finger graph 259 -> 294 us).  At the training batch
+//   (B <= 32) it keeps 8 union rows in flight per lane at 2 CTAs per SM instead of 4 at 3 (17.7 -> 17.0 us on the finger
+//   graph's compact head, 26.7 -> 21.3 us on the grasp graph's).  PTK_AGG_AUTO picks it where it wins: wide layers and
+//   inputs without pass-through columns.
 //
 // RING (PTK_AGG_RING) -- per batch element the CTA brings the union's rows into shared memory with cp.async (every warp
 //   copies its share of the rows, one row = one 16-byte LDGSTS per lane; completion is reported to the slot's mbarrier by
@@ -101,8 +103,10 @@ struct AggTiles {
     const uint16_t *lidx;  // per CSR entry: index of col[e] in its row's tile union
 };
 
-template <int NG>
-__global__ void __launch_bounds__(AU_THREADS, 3)
+// XW: union rows a lane of the dense-tile form keeps in flight -- 4 at three CTAs per SM (large batches: occupancy
+// matters), 8 at two CTAs per SM (training batch: few CTAs per SM exist anyway, memory-level parallelism per warp matters)
+template <int NG, int XW>
+__global__ void __launch_bounds__(AU_THREADS, XW == 8 ? 2 : 3)
 gcn_aggregate_union_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                            const float *__restrict__ val, const AggHubs hb, const AggTiles tl, unsigned hub_slots, int Nv,
                            const float *__restrict__ in, int B, int C, int L, const float *__restrict__ bias, int relu,
@@ -253,7 +257,7 @@ gcn_aggregate_union_kernel(const int32_t *__restrict__ rowptr, const int32_t *__
         // bit-identical to the sparse gather for finite inputs.
         float *sA = reinterpret_cast<float *>(au_dyn);
         __shared__ int s_valid[AG_WARPS];
-        const int Up = (U + 3) & ~3;
+        const int Up = (U + XW - 1) & ~(XW - 1);
         for (int e = threadIdx.x; e < Up * 8; e += AU_THREADS) sA[e] = 0.f;
         for (int u = threadIdx.x; u < Up; u += AU_THREADS) s_uoff[u] = u < U ? (uint32_t)tl.ucol[u0 + u] * row_bytes : 0u;
         __syncthreads();
@@ -286,12 +290,12 @@ gcn_aggregate_union_kernel(const int32_t *__restrict__ rowptr, const int32_t *__
 #pragma unroll
             for (int r = 0; r < AU_TV; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.f;
             const char *src = reinterpret_cast<const char *>(inb) + (size_t)(ch * gc + gl) * 16;
-            for (int u = 0; u < Up; u += 4) {
-                float4 x[4];
+            for (int u = 0; u < Up; u += XW) {
+                float4 x[XW];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) x[j] = __ldg(reinterpret_cast<const float4 *>(src + s_uoff[u + j]));
+                for (int j = 0; j < XW; ++j) x[j] = __ldg(reinterpret_cast<const float4 *>(src + s_uoff[u + j]));
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < XW; ++j) {
                     const float4 w0 = *reinterpret_cast<const float4 *>(sA + (u + j) * 8);
                     const float4 w1 = *reinterpret_cast<const float4 *>(sA + (u + j) * 8 + 4);
                     const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
@@ -466,7 +470,7 @@ gcn_aggregate_union_kernel(const int32_t *__restrict__ rowptr, const int32_t *__
     }
 }
 
-static unsigned long long g_au_optin[3] = {0ull, 0ull, 0ull};
+static unsigned long long g_au_optin[6] = {0ull, 0ull, 0ull, 0ull, 0ull, 0ull};
 
 // Returns 1 when the union kernel was launched, 0 when the shape is outside its range (the caller falls back to the
 // tile kernel), < 0 on error.
@@ -487,7 +491,7 @@ int aggregate_union_launch(int mode, const int32_t *rowptr, const int32_t *col, 
     while (n_stages > 2 && 3 * (stat + n_stages * pitch + 128) > 225 * 1024) --n_stages;
     if (PTK_TUNING_ENV("PTK_AGG_STAGES") > 0) n_stages = PTK_TUNING_ENV("PTK_AGG_STAGES");
     size_t smem = (size_t)n_stages * pitch + 128;
-    if (dense_mode) smem = (size_t)((max_union + 3) & ~3) * 8 * sizeof(float) + 128;  // A [U][8]
+    if (dense_mode) smem = (size_t)((max_union + 7) & ~7) * 8 * sizeof(float) + 128;  // A [U][8]
     if (stat + smem > 220 * 1024) return 0;
     int BG = 8;  // the dense-tile form needs exactly 8: warp = batch element
     const long long slots = 6LL * sm_count();
@@ -501,20 +505,22 @@ int aggregate_union_launch(int mode, const int32_t *rowptr, const int32_t *col, 
     const unsigned grid = (unsigned)((hub_slots + n_tiles) * ceil_div(B, BG));
     int dev = 0;
     PTK_CHECK_CUDA(cudaGetDevice(&dev));
-#define PTK_UNION(NGv)                                                                                                    \
+    const bool xw8 = dense_mode && B <= 32;
+#define PTK_UNION(NGv, XWv)                                                                                               \
     do {                                                                                                                  \
-        if (dev >= 64 || !((g_au_optin[NGv - 1] >> dev) & 1ull)) {                                                        \
-            PTK_CHECK_CUDA(cudaFuncSetAttribute(gcn_aggregate_union_kernel<NGv>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                                200 * 1024));                                                             \
-            if (dev < 64) g_au_optin[NGv - 1] |= 1ull << dev;                                                             \
+        const int slot = (NGv - 1) * 2 + (XWv == 8 ? 1 : 0);                                                              \
+        if (dev >= 64 || !((g_au_optin[slot] >> dev) & 1ull)) {                                                           \
+            PTK_CHECK_CUDA(cudaFuncSetAttribute(gcn_aggregate_union_kernel<NGv, XWv>,                                      \
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));                \
+            if (dev < 64) g_au_optin[slot] |= 1ull << dev;                                                                \
         }                                                                                                                 \
-        launch_pdl(gcn_aggregate_union_kernel<NGv>, dim3(grid), dim3(AU_THREADS), smem, st, rowptr, col, val, hb, tl, hub_slots, \
-                   (int)Nv, in, (int)B, (int)C, (int)L, bias, relu, out, BG, n_tiles, hubs_first, (int)ldi, (int)ldo, nchunks, \
-                   gc, n_stages, prefetch_next, dense_mode);                                                              \
+        launch_pdl(gcn_aggregate_union_kernel<NGv, XWv>, dim3(grid), dim3(AU_THREADS), smem, st, rowptr, col, val, hb, tl,  \
+                   hub_slots, (int)Nv, in, (int)B, (int)C, (int)L, bias, relu, out, BG, n_tiles, hubs_first, (int)ldi,   \
+                   (int)ldo, nchunks, gc, n_stages, prefetch_next, dense_mode);                                           \
     } while (0)
-    if (NG == 1) PTK_UNION(1);
-    else if (NG == 2) PTK_UNION(2);
-    else PTK_UNION(3);
+    if (NG == 1) { if (xw8) PTK_UNION(1, 8); else PTK_UNION(1, 4); }
+    else if (NG == 2) { if (xw8) PTK_UNION(2, 8); else PTK_UNION(2, 4); }
+    else { if (xw8) PTK_UNION(3, 8); else PTK_UNION(3, 4); }
 #undef PTK_UNION
     PTK_CHECK_LAUNCH();
     return 1;

@@ -159,8 +159,8 @@ int ptk_gcn_aggregate_ex(const int32_t *rowptr, const int32_t *col, const float 
  * consecutive vertices share most of their neighbours; the caller lists, per tile, the sorted union of the neighbour
  * columns of its non-hub rows: tile_uptr (ceil(Nv/8)+1 offsets), tile_ucol, and per CSR entry e the index
  * tile_lidx[e] of col[e] in its tile's union; max_union = the largest union.  mode:
- *   PTK_AGG_AUTO        the form measured fastest for the shape (dense tile for > 128 aggregated channels and, without
- *                       pass-through columns, at batch >= 64 or on dense graphs; the L2 gather otherwise)
+ *   PTK_AGG_AUTO        the form measured fastest for the shape (dense tile for > 128 aggregated channels and for
+ *                       inputs without pass-through columns; the L2 gather otherwise)
  *   PTK_AGG_L2_GATHER   ptk_gcn_aggregate_ex
  *   PTK_AGG_DENSE_TILE  a warp owns the tile for one batch element: out[8 x C'] = A[8 x U] . X[U x C'], every union row
  *                       read from L2 once and accumulated into up to 8 register rows, A (0 where unused) in shared memory
