@@ -74,6 +74,22 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+// the same load delivered to the CTAs of `mask` (same shared-memory offset and mbarrier offset in each of them)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1,
+                                               uint16_t mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
@@ -85,6 +101,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// completion of the MMAs issued so far reported to the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
 }
 // hi = x rounded to TF32 (nearest, ties away -- what cvt.rna.tf32.f32 returns for finite x) in two integer
 // instructions; the PTX cvt expands to ~4 ALU instructions with its NaN/Inf handling and made the converter
@@ -135,7 +156,11 @@ struct TGParams {
     int *flags;           // (gridDim.x) 1 once part[c] is complete (zeroed by the weight-split kernel before)
 };
 
-template <bool MASK>
+// PAIR: launched as clusters of two CTAs that work on the two 128-row tiles of a 256-row pair with the SAME column tile
+// and k-block sequence.  Each CTA loads its own A tile and HALF of the split weight tiles (80 of the 160 rows of B_hi and
+// B_lo), multicast to both: 36 instead of 56 KB per CTA and k-block come out of L2.  A stage is reused once BOTH CTAs'
+// MMAs have read it (tcgen05.commit multicast onto both empty barriers).
+template <bool MASK, bool PAIR>
 __global__ void __launch_bounds__(TG_THREADS, 1)
 gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
                    const __grid_constant__ CUtensorMap map_blo, const TGParams p) {
@@ -163,9 +188,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // tile t -> (m-tile t / tiles_n, n-tile t % tiles_n).  All pipeline counters (smem stage, TMEM buffer) run
     // across tiles, so the epilogue stores of one tile overlap the TMA / MMA work of the next.
     const int tiles_n = (p.N + TG_BN - 1) / TG_BN;
-    const int num_tiles = ((p.M + TG_BM - 1) / TG_BM) * tiles_n;
+    const int tiles_m = (p.M + TG_BM - 1) / TG_BM;
+    // PAIR: the work items are (256-row pair, column tile) x k-block, dealt out to the CLUSTERS; rank r of a cluster takes
+    // the pair's r-th 128-row tile (rows beyond M: TMA zero-fill, no stores)
+    const int crank = PAIR ? (int)cluster_ctarank() : 0;
+    const int step = PAIR ? 2 : 1;                                   // predecessor / successor CTA distance
+    const int workers = PAIR ? (int)gridDim.x / 2 : (int)gridDim.x;
+    const int me = PAIR ? (int)blockIdx.x / 2 : (int)blockIdx.x;
+    const int num_tiles = (PAIR ? (tiles_m + 1) / 2 : tiles_m) * tiles_n;
     const long long units = (long long)num_tiles * num_kb;
-    const int u0 = (int)(units * blockIdx.x / gridDim.x), u1 = (int)(units * (blockIdx.x + 1) / gridDim.x);
+    const int u0 = (int)(units * me / workers), u1 = (int)(units * (me + 1) / workers);
+    auto tile_m0 = [&](int tile) { return ((PAIR ? 2 * (tile / tiles_n) + crank : tile / tiles_n)) * TG_BM; };
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -174,7 +207,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int s = 0; s < TG_STAGES; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_conv + 8 * s, TG_CONV_WARPS);
-            mbar_init(bar_empty + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, PAIR ? 2 : 1);
         }
         for (int b = 0; b < TG_NBUF; ++b) {
             mbar_init(bar_tfull + 8 * b, 1);
@@ -190,6 +223,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
+    if (PAIR) cluster_sync_all();  // the peer's barriers exist before anything is multicast onto them
     pdl_wait();  // barriers + TMEM are set up; from here on global memory of the predecessors is read
 
     if (warp == 0) {
@@ -200,7 +234,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 const int tile = (hi - 1) / num_kb;
                 const int kb_begin = max(u0 - tile * num_kb, 0), kb_end = hi - tile * num_kb;
                 hi = tile * num_kb + kb_begin;
-                const int m0 = (tile / tiles_n) * TG_BM, n_base = (tile % tiles_n) * TG_BN;
+                const int m0 = tile_m0(tile), n_base = (tile % tiles_n) * TG_BN;
                 for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
                     const int s = it % TG_STAGES;
                     const uint32_t ph = (it / TG_STAGES) & 1;
@@ -208,8 +242,17 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     const uint32_t sa = smem_u32(smem + (size_t)s * TG_STAGE_BYTES);
                     mbar_expect_tx(bar_full + 8 * s, TG_A_BYTES + 2 * TG_B_BYTES);
                     tma_load_2d(sa, &map_a, bar_full + 8 * s, kb * TG_BK, m0);
-                    tma_load_2d(sa + 2 * TG_A_BYTES, &map_bhi, bar_full + 8 * s, kb * TG_BK, n_base);
-                    tma_load_2d(sa + 2 * TG_A_BYTES + TG_B_BYTES, &map_blo, bar_full + 8 * s, kb * TG_BK, n_base);
+                    if (PAIR) {
+                        // this CTA's half of the weight tiles (80 rows = 10 swizzle atoms of 1 KB), delivered to both CTAs
+                        const uint32_t hoff = (uint32_t)crank * (TG_B_BYTES / 2);
+                        tma_load_2d_mc(sa + 2 * TG_A_BYTES + hoff, &map_bhi, bar_full + 8 * s, kb * TG_BK,
+                                       n_base + crank * (TG_BN / 2), 3);
+                        tma_load_2d_mc(sa + 2 * TG_A_BYTES + TG_B_BYTES + hoff, &map_blo, bar_full + 8 * s, kb * TG_BK,
+                                       n_base + crank * (TG_BN / 2), 3);
+                    } else {
+                        tma_load_2d(sa + 2 * TG_A_BYTES, &map_bhi, bar_full + 8 * s, kb * TG_BK, n_base);
+                        tma_load_2d(sa + 2 * TG_A_BYTES + TG_B_BYTES, &map_blo, bar_full + 8 * s, kb * TG_BK, n_base);
+                    }
                 }
             }
         }
@@ -242,10 +285,11 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                     const uint64_t ko = (uint64_t)(ks * 32 >> 4);
                     umma_tf32(d_tmem, d_ahi + ko, d_bhi + ko, idesc, 1);
                 }
-                umma_commit(bar_empty + 8 * s);   // smem stage free once these MMAs have read it
+                // smem stage free once these MMAs have read it (PAIR: the peer may then overwrite its half too)
+                if (PAIR) umma_commit_mc(bar_empty + 8 * s, 3); else umma_commit(bar_empty + 8 * s);
                 umma_commit(bar_tfull + 8 * b);   // accumulator chunk complete
             } else if (lane == 0) {
-                umma_commit(bar_empty + 8 * s);
+                if (PAIR) umma_commit_mc(bar_empty + 8 * s, 3); else umma_commit(bar_empty + 8 * s);
                 umma_commit(bar_tfull + 8 * b);
             }
             __syncwarp();
@@ -290,7 +334,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         hi = tile * num_kb + kb_begin;
         const bool head_part = kb_end < num_kb;    // the tile's last k-blocks belong to CTA blockIdx.x + 1: publish
         const bool tail_part = kb_begin > 0;       // the tile's first k-blocks came from CTA blockIdx.x - 1: combine
-        const int m0 = (tile / tiles_n) * TG_BM, n_base = (tile % tiles_n) * TG_BN;
+        const int m0 = tile_m0(tile), n_base = (tile % tiles_n) * TG_BN;
         const int row = m0 + q * 32 + lane;
         float acc[80];
 #pragma unroll
@@ -346,10 +390,10 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             continue;
         }
         if (tail_part) {
-            const volatile int *flag = p.flags + blockIdx.x - 1;
+            const volatile int *flag = p.flags + blockIdx.x - step;
             while (*flag == 0) __nanosleep(64);
             __threadfence();
-            const float4 *slot = reinterpret_cast<const float4 *>(p.part) + (size_t)(blockIdx.x - 1) * (TG_BM * TG_BN / 4);
+            const float4 *slot = reinterpret_cast<const float4 *>(p.part) + (size_t)(blockIdx.x - step) * (TG_BM * TG_BN / 4);
 #pragma unroll
             for (int v = 0; v < 20; ++v) {
                 const float4 t = __ldcg(slot + v * 256 + dt);
@@ -381,6 +425,7 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (PAIR) cluster_sync_all();  // no CTA leaves while its peer may still signal its barriers
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
@@ -736,14 +781,54 @@ size_t tf32x3_workspace_bytes(int64_t M, int64_t K, int64_t N) {
            tf32x3_part_bytes();
 }
 
+// PTK_TG_PAIR=1 selects the 2-CTA cluster form (weight tiles multicast over the pair).  Measured on B200 at M = 31184,
+// K = N = 300 (tools/tc_gemm_probe.py): the operand floor (TMA only: split, MMAs and drain disabled) falls from 48.5 to
+// 37.1 us, the kernel itself stays at 53.3 us (53.6 us single) -- with 3 stages of 72 KB it is bound by the depth of the
+// TMA -> split -> MMA -> release ring, not by L2 reads any more (MMAs disabled: 40.0 us).  Left off: no gain without a
+// deeper ring, which needs cta_group::2 MMAs (half of B per CTA: 52 KB stages, 4 of them).
+static bool tg_pair_mode() { return PTK_TUNING_ENV("PTK_TG_PAIR") == 1; }
+
+// CTAs to launch: one per SM at most; PAIR: whole clusters of two, one per 256-row pair x column tile at most
+static int tg_num_ctas(int64_t M, int64_t N) {
+    const int64_t tiles_m = ceil_div(M, TG_BM), tiles_n = ceil_div(N, TG_BN);
+    if (tg_pair_mode()) {
+        const int64_t ptiles = ceil_div(tiles_m, 2) * tiles_n;
+        const int64_t clusters = ptiles < sm_count() / 2 ? ptiles : sm_count() / 2;
+        return (int)(2 * clusters);
+    }
+    const int64_t tiles = tiles_m * tiles_n;
+    return (int)(tiles < sm_count() ? tiles : sm_count());
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl_cluster2(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                       Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 static int tg_launch(const float *A, const float *b_hi, const float *b_lo, const uint32_t *mask, int64_t M, int64_t K,
                      int64_t N, float *D, float *part, int *flags, int n_ctas, cudaStream_t st) {
+    const bool pair = tg_pair_mode();
     CUtensorMap map_a, map_bhi, map_blo;
     int rc = make_map(&map_a, A, M, K, TG_BM);
     if (rc) return rc;
-    rc = make_map(&map_bhi, b_hi, N, K, TG_BN);  // (N x K) K-major; rows beyond N are zero-filled
+    rc = make_map(&map_bhi, b_hi, N, K, pair ? TG_BN / 2 : TG_BN);  // (N x K) K-major; rows beyond N are zero-filled
     if (rc) return rc;
-    rc = make_map(&map_blo, b_lo, N, K, TG_BN);
+    rc = make_map(&map_blo, b_lo, N, K, pair ? TG_BN / 2 : TG_BN);
     if (rc) return rc;
 
     TGParams p;
@@ -756,14 +841,20 @@ static int tg_launch(const float *A, const float *b_hi, const float *b_lo, const
     const size_t smem = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024;
     dim3 grid((unsigned)n_ctas);
     if (!smem_optin_done(0)) {  // the attribute is per device
-        PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         smem_optin_mark(0);
     }
-    if (mask)
-        launch_pdl(gemm_tf32x3_kernel<true>, grid, dim3(TG_THREADS), smem, st, map_a, map_bhi, map_blo, p);
+    cudaError_t le;
+    if (pair)
+        le = mask ? launch_pdl_cluster2(gemm_tf32x3_kernel<true, true>, grid, dim3(TG_THREADS), smem, st, map_a, map_bhi, map_blo, p)
+                  : launch_pdl_cluster2(gemm_tf32x3_kernel<false, true>, grid, dim3(TG_THREADS), smem, st, map_a, map_bhi, map_blo, p);
     else
-        launch_pdl(gemm_tf32x3_kernel<false>, grid, dim3(TG_THREADS), smem, st, map_a, map_bhi, map_blo, p);
+        le = mask ? launch_pdl(gemm_tf32x3_kernel<true, false>, grid, dim3(TG_THREADS), smem, st, map_a, map_bhi, map_blo, p)
+                  : launch_pdl(gemm_tf32x3_kernel<false, false>, grid, dim3(TG_THREADS), smem, st, map_a, map_bhi, map_blo, p);
+    PTK_CHECK_CUDA(le);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }
@@ -782,8 +873,7 @@ int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act
     float *part = reinterpret_cast<float *>(
         ((uintptr_t)(mask + (size_t)M * (size_t)ceil_div(K > N ? K : N, 32)) + 255) & ~(uintptr_t)255);
     int *flags = reinterpret_cast<int *>(part + (size_t)sm_count() * (TG_BM * TG_BN));
-    const int64_t num_tiles = ceil_div(M, TG_BM) * ceil_div(N, TG_BN);
-    const int n_ctas = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
+    const int n_ctas = tg_num_ctas(M, N);
     if (act && act_bits) {
         mask = const_cast<uint32_t *>(act_bits);  // packed by the forward GEMM that consumed `act` (same layout)
     } else if (act) {
@@ -805,8 +895,7 @@ int gemm_tf32x3(const float *A, const float *Bsrc, int b_is_kn, const float *act
 int gemm_tf32x3_presplit(const float *A, const float *b_hi, const float *b_lo, const float *act, const uint32_t *act_bits,
                          int64_t M, int64_t K, int64_t N, float *D, uint32_t *mask_ws, float *part, int *flags,
                          cudaStream_t st) {
-    const int64_t num_tiles = ceil_div(M, TG_BM) * ceil_div(N, TG_BN);
-    const int n_ctas = (int)(num_tiles < sm_count() ? num_tiles : sm_count());
+    const int n_ctas = tg_num_ctas(M, N);
     const uint32_t *mask = nullptr;
     if (act && act_bits) {
         mask = act_bits;
