@@ -433,6 +433,314 @@ gemm_tf32x3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 }
 
 // =================================================================================================
+// 2-SM form of the kernel above: cta_group::2 MMAs.
+//
+// What the probes showed (tools/tc_gemm_probe.py): the single-CTA kernel sits on its operand floor (273 MB of tiles
+// through L2 -> shared memory), and the multicast pair form removes a third of those bytes but gains nothing because
+// three 72 KB stages -- all of shared memory -- do not cover the TMA -> split -> MMA -> release chain.  Here the two CTAs
+// of a cluster form ONE 256 x 160 tile: each keeps its 128 rows of A (raw -> a_hi in place, a_lo) and only HALF of the
+// split weight tile (80 of the 160 rows of B_hi / B_lo); the leader CTA issues tcgen05.mma.cta_group::2 (M = 256), which
+// reads A from both CTAs' shared memory and the two B halves from their owners, and writes each CTA's 128 accumulator
+// rows into that CTA's own TMEM.  A stage is 52 KB: FOUR stages fit, and 36 instead of 56 KB per CTA and k-block come
+// out of L2 AND into the SM.  Everything downstream (drain warps adding each k-block's chunk in FP32 registers, the
+// k-block work split with partial tiles and flags, the masked epilogue) is per CTA exactly as above.
+// MEASURED (PTK_TG_PAIR=3, M = 31184, K = N = 300): same results (2.2e-7 vs fp64), but 62.1 us against 53.0 us for the
+// single-CTA kernel, and 52.2 us with split, MMAs and drain all disabled: every k-block now crosses the pair three times
+// (the peer's B half and split report to the leader, the leader's commit releases the peer, both drains report back) and
+// the accumulator ring is still 3 deep (3 x 160 of 512 TMEM columns), so the fourth shared-memory stage cannot fill.
+// With 32-wide k-blocks that chain costs more than the saved bytes.  Kept selectable, off by default.
+//   barriers (same offsets in both CTAs; "leader's" = the copy in CTA rank 0, reached through mapa):
+//     bar_a[s]      local     own A tile landed (TMA)                          -> the CTA's converter warps
+//     bar_b[s]      leader's  both B halves landed (each CTA's TMA signals it) -> leader's MMA warp
+//     bar_conv[s]   leader's  A split done in both CTAs (2 x 4 warps)          -> leader's MMA warp
+//     bar_empty[s]  local     MMAs have read the stage (commit, multicast)     -> the CTA's TMA producer
+//     bar_tfull[b]  local     accumulator chunk complete (commit, multicast)   -> the CTA's drain warps
+//     bar_tempty[b] leader's  chunk drained in both CTAs (2 x 8 warps)         -> leader's MMA warp
+constexpr int T2_STAGES = 4;
+constexpr int T2_BH_BYTES = TG_B_BYTES / 2;                           // 10 KB: 80 rows of B_hi (or B_lo)
+constexpr int T2_STAGE_BYTES = 2 * TG_A_BYTES + 2 * T2_BH_BYTES;      // 52 KB
+
+__device__ __forceinline__ uint32_t mapa_rank0(uint32_t addr) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, 0;" : "=r"(r) : "r"(addr));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load into THIS CTA's shared memory whose bytes are counted on a barrier given by its cluster address (the leader's)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+// kind::tf32 instruction descriptor of the pair: M = 256 (128 rows per CTA), N = n
+__host__ __device__ constexpr uint32_t make_idesc_tf32_m256(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}
+
+template <bool MASK>
+__global__ void __launch_bounds__(TG_THREADS, 1)
+gemm_tf32x3_2sm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_bhi,
+                       const __grid_constant__ CUtensorMap map_blo, const TGParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // per stage: [A_hi (raw) 16 KB][A_lo 16 KB][B_hi half 10 KB][B_lo half 10 KB], every piece 1024-B aligned
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bars[4 * T2_STAGES + 2 * TG_NBUF];
+    __shared__ uint32_t tmem_base_slot;
+    const uint32_t bar_a = smem_u32(&bars[0]);
+    const uint32_t bar_b = smem_u32(&bars[T2_STAGES]);
+    const uint32_t bar_conv = smem_u32(&bars[2 * T2_STAGES]);
+    const uint32_t bar_empty = smem_u32(&bars[3 * T2_STAGES]);
+    const uint32_t bar_tfull = smem_u32(&bars[4 * T2_STAGES]);
+    const uint32_t bar_tempty = smem_u32(&bars[4 * T2_STAGES + TG_NBUF]);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = (p.K + TG_BK - 1) / TG_BK;
+    pdl_launch_dependents();
+    const int tiles_n = (p.N + TG_BN - 1) / TG_BN;
+    const int tiles_m = (p.M + TG_BM - 1) / TG_BM;
+    const int crank = (int)cluster_ctarank();
+    const bool leader = crank == 0;
+    const int workers = (int)gridDim.x / 2, me = (int)blockIdx.x / 2;
+    const int num_tiles = ((tiles_m + 1) / 2) * tiles_n;            // (256-row pair, column tile)
+    const long long units = (long long)num_tiles * num_kb;
+    const int u0 = (int)(units * me / workers), u1 = (int)(units * (me + 1) / workers);
+    auto tile_m0 = [&](int tile) { return (2 * (tile / tiles_n) + crank) * TG_BM; };
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_bhi) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_blo) : "memory");
+        for (int s = 0; s < T2_STAGES; ++s) {
+            mbar_init(bar_a + 8 * s, 1);
+            mbar_init(bar_b + 8 * s, 1);
+            mbar_init(bar_conv + 8 * s, 2 * TG_CONV_WARPS);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int b = 0; b < TG_NBUF; ++b) {
+            mbar_init(bar_tfull + 8 * b, 1);
+            mbar_init(bar_tempty + 8 * b, 2 * 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: all 512 columns in both CTAs of the pair
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&tmem_base_slot)) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+    cluster_sync_all();  // both CTAs' barriers and TMEM exist before anything is signalled across
+    pdl_wait();
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int it = 0;
+            for (int hi = u1; hi > u0;) {
+                const int tile = (hi - 1) / num_kb;
+                const int kb_begin = max(u0 - tile * num_kb, 0), kb_end = hi - tile * num_kb;
+                hi = tile * num_kb + kb_begin;
+                const int m0 = tile_m0(tile), n_half = (tile % tiles_n) * TG_BN + crank * (TG_BN / 2);
+                for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+                    const int s = it % T2_STAGES;
+                    const uint32_t ph = (it / T2_STAGES) & 1;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                    const uint32_t sa = smem_u32(smem + (size_t)s * T2_STAGE_BYTES);
+                    mbar_expect_tx(bar_a + 8 * s, TG_A_BYTES);
+                    tma_load_2d(sa, &map_a, bar_a + 8 * s, kb * TG_BK, m0);
+                    if (leader) mbar_expect_tx(bar_b + 8 * s, 4 * T2_BH_BYTES);  // hi + lo halves of both CTAs
+                    const uint32_t bb = mapa_rank0(bar_b + 8 * s);
+                    tma_load_2d_2sm(sa + 2 * TG_A_BYTES, &map_bhi, bb, kb * TG_BK, n_half);
+                    tma_load_2d_2sm(sa + 2 * TG_A_BYTES + T2_BH_BYTES, &map_blo, bb, kb * TG_BK, n_half);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA only) =====================
+        if (leader) {
+            const uint32_t idesc = make_idesc_tf32_m256(TG_BN);
+            const int total_kb = u1 - u0;
+            for (int kb = 0; kb < total_kb; ++kb) {
+                const int s = kb % T2_STAGES, b = kb % TG_NBUF;
+                mbar_wait(bar_b + 8 * s, (kb / T2_STAGES) & 1);           // both B halves landed
+                mbar_wait(bar_conv + 8 * s, (kb / T2_STAGES) & 1);        // A split done in both CTAs
+                mbar_wait(bar_tempty + 8 * b, ((kb / TG_NBUF) & 1) ^ 1);  // accumulator buffer drained in both CTAs
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (lane == 0) {
+                    if (!(p.dbg & 4)) {
+                        const uint32_t sa = smem_u32(smem + (size_t)s * T2_STAGE_BYTES);
+                        const uint64_t d_ahi = make_kmajor_sw128_desc(sa);
+                        const uint64_t d_alo = make_kmajor_sw128_desc(sa + TG_A_BYTES);
+                        const uint64_t d_bhi = make_kmajor_sw128_desc(sa + 2 * TG_A_BYTES);
+                        const uint64_t d_blo = make_kmajor_sw128_desc(sa + 2 * TG_A_BYTES + T2_BH_BYTES);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)(b * TG_BN);
+#pragma unroll
+                        for (int ks = 0; ks < TG_BK / 8; ++ks) {
+                            const uint64_t ko = (uint64_t)(ks * 32 >> 4);
+                            umma_tf32_2sm(d_tmem, d_ahi + ko, d_blo + ko, idesc, ks != 0);
+                            umma_tf32_2sm(d_tmem, d_alo + ko, d_bhi + ko, idesc, 1);
+                        }
+#pragma unroll
+                        for (int ks = 0; ks < TG_BK / 8; ++ks) {
+                            const uint64_t ko = (uint64_t)(ks * 32 >> 4);
+                            umma_tf32_2sm(d_tmem, d_ahi + ko, d_bhi + ko, idesc, 1);
+                        }
+                    }
+                    umma_commit_2sm(bar_empty + 8 * s, 3);   // stage free in both CTAs
+                    umma_commit_2sm(bar_tfull + 8 * b, 3);   // chunk complete in both CTAs
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4 && warp < 4 + TG_CONV_WARPS) {
+        // ===================== converter warps (both CTAs: own A rows) =====================
+        const int ct = threadIdx.x - 128;
+        const int total_kb = u1 - u0;
+        for (int kb = 0; kb < total_kb; ++kb) {
+            const int s = kb % T2_STAGES;
+            mbar_wait(bar_a + 8 * s, (kb / T2_STAGES) & 1);
+            const uint32_t stage = smem_u32(smem + (size_t)s * T2_STAGE_BYTES);
+            constexpr int CA = TG_A_BYTES / 16;
+#pragma unroll
+            for (int i = 0; i < CA / (32 * TG_CONV_WARPS); ++i) {
+                if (p.dbg & 1) break;
+                const uint32_t hi = stage + 16u * (uint32_t)(ct + i * 32 * TG_CONV_WARPS);
+                const uint32_t lo = hi + (uint32_t)TG_A_BYTES;
+                const uint4 v = lds128(hi);
+                uint4 h, l;
+                split_tf32(__uint_as_float(v.x), h.x, l.x);
+                split_tf32(__uint_as_float(v.y), h.y, l.y);
+                split_tf32(__uint_as_float(v.z), h.z, l.z);
+                split_tf32(__uint_as_float(v.w), h.w, l.w);
+                sts128(hi, h);
+                sts128(lo, l);
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_rank0(bar_conv + 8 * s));
+        }
+    } else if (warp >= 8) {
+        // ===================== drain + epilogue warps (both CTAs: own 128 rows) =====================
+        const int q = warp & 3;
+        const int half = (warp - 8) >> 2;
+        int it = 0;
+        const int dt = threadIdx.x - 256;
+        for (int hi = u1; hi > u0;) {
+        const int tile = (hi - 1) / num_kb;
+        const int kb_begin = max(u0 - tile * num_kb, 0), kb_end = hi - tile * num_kb;
+        hi = tile * num_kb + kb_begin;
+        const bool head_part = kb_end < num_kb;
+        const bool tail_part = kb_begin > 0;
+        const int m0 = tile_m0(tile), n_base = (tile % tiles_n) * TG_BN;
+        const int row = m0 + q * 32 + lane;
+        float acc[80];
+#pragma unroll
+        for (int j = 0; j < 80; ++j) acc[j] = 0.f;
+        uint32_t mbits[3] = {0u, 0u, 0u};
+        if (MASK && row < p.M && !head_part) {
+            const int nb0 = n_base + half * 80;
+            const int w0 = nb0 >> 5, sh = nb0 & 31;
+            const uint32_t *mr = p.mask + (size_t)row * p.wpr;
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) w[i] = (w0 + i < p.wpr) ? __ldg(mr + w0 + i) : 0u;
+#pragma unroll
+            for (int i = 0; i < 3; ++i) mbits[i] = __funnelshift_r(w[i], w[i + 1], sh);
+        }
+        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+            const int b = it % TG_NBUF;
+            mbar_wait(bar_tfull + 8 * b, (it / TG_NBUF) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(b * TG_BN + half * 80);
+#pragma unroll
+            for (int c0 = 0; c0 < 80; c0 += 16) {
+                if (p.dbg & 2) break;
+                uint32_t r[16];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr + (uint32_t)c0));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 16; ++j) acc[c0 + j] += __uint_as_float(r[j]);
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(mapa_rank0(bar_tempty + 8 * b));
+        }
+        if (head_part) {
+            float4 *slot = reinterpret_cast<float4 *>(p.part) + (size_t)blockIdx.x * (TG_BM * TG_BN / 4);
+#pragma unroll
+            for (int v = 0; v < 20; ++v)
+                __stcg(slot + v * 256 + dt, make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]));
+            __threadfence();
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (dt == 0) {
+                __threadfence();
+                *reinterpret_cast<volatile int *>(p.flags + blockIdx.x) = 1;
+            }
+            continue;
+        }
+        if (tail_part) {
+            const volatile int *flag = p.flags + blockIdx.x - 2;
+            while (*flag == 0) __nanosleep(64);
+            __threadfence();
+            const float4 *slot = reinterpret_cast<const float4 *>(p.part) + (size_t)(blockIdx.x - 2) * (TG_BM * TG_BN / 4);
+#pragma unroll
+            for (int v = 0; v < 20; ++v) {
+                const float4 t = __ldcg(slot + v * 256 + dt);
+                acc[4 * v] = t.x + acc[4 * v]; acc[4 * v + 1] = t.y + acc[4 * v + 1];
+                acc[4 * v + 2] = t.z + acc[4 * v + 2]; acc[4 * v + 3] = t.w + acc[4 * v + 3];
+            }
+        }
+        const int nb = n_base + half * 80;
+        if (row < p.M) {
+            float *dst = p.D + (size_t)row * p.N + nb;
+            if (MASK) {
+#pragma unroll
+                for (int j = 0; j < 80; ++j) acc[j] = (mbits[j >> 5] >> (j & 31)) & 1u ? acc[j] : 0.f;
+            }
+            if ((p.N & 3) == 0) {
+#pragma unroll
+                for (int v = 0; v < 20; ++v)
+                    if (nb + 4 * v + 4 <= p.N)
+                        *reinterpret_cast<float4 *>(dst + 4 * v) =
+                            make_float4(acc[4 * v], acc[4 * v + 1], acc[4 * v + 2], acc[4 * v + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 80; ++j)
+                    if (nb + j < p.N) dst[j] = acc[j];
+            }
+        }
+        }  // tile loop
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();  // no CTA leaves (or frees TMEM) while its peer may still signal it or the MMAs still write
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// =================================================================================================
 // wgrad:  gW (K_in x N_out) = X^T (K_in x M) . gH (M x N_out)      -- reduction over the M rows.
 //
 // Both operands are activations that are row-major over the REDUCTION index (X[row][k_in],
@@ -785,8 +1093,9 @@ size_t tf32x3_workspace_bytes(int64_t M, int64_t K, int64_t N) {
 // K = N = 300 (tools/tc_gemm_probe.py): the operand floor (TMA only: split, MMAs and drain disabled) falls from 48.5 to
 // 37.1 us, the kernel itself stays at 53.3 us (53.6 us single) -- with 3 stages of 72 KB it is bound by the depth of the
 // TMA -> split -> MMA -> release ring, not by L2 reads any more (MMAs disabled: 40.0 us).  Left off: no gain without a
-// deeper ring, which needs cta_group::2 MMAs (half of B per CTA: 52 KB stages, 4 of them).
-static bool tg_pair_mode() { return PTK_TUNING_ENV("PTK_TG_PAIR") == 1; }
+// deeper ring; the cta_group::2 form below (PTK_TG_PAIR=3) has that ring but pays for it in cross-CTA barrier hops.
+static bool tg_pair_mode() { return PTK_TUNING_ENV("PTK_TG_PAIR") == 1 || PTK_TUNING_ENV("PTK_TG_PAIR") == 3; }
+static bool tg_2sm_mode() { return PTK_TUNING_ENV("PTK_TG_PAIR") == 3; }  // cta_group::2 MMAs (gemm_tf32x3_2sm_kernel)
 
 // CTAs to launch: one per SM at most; PAIR: whole clusters of two, one per 256-row pair x column tile at most
 static int tg_num_ctas(int64_t M, int64_t N) {
@@ -840,6 +1149,23 @@ static int tg_launch(const float *A, const float *b_hi, const float *b_lo, const
     p.flags = flags;
     const size_t smem = (size_t)TG_STAGES * TG_STAGE_BYTES + 1024;
     dim3 grid((unsigned)n_ctas);
+    if (tg_2sm_mode()) {
+        const size_t smem2 = (size_t)T2_STAGES * T2_STAGE_BYTES + 1024;
+        static unsigned long long optin2 = 0ull;
+        int dev = 0;
+        PTK_CHECK_CUDA(cudaGetDevice(&dev));
+        if (dev >= 64 || !((optin2 >> dev) & 1ull)) {
+            PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_2sm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_2sm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+            if (dev < 64) optin2 |= 1ull << dev;
+        }
+        const cudaError_t le2 =
+            mask ? launch_pdl_cluster2(gemm_tf32x3_2sm_kernel<true>, grid, dim3(TG_THREADS), smem2, st, map_a, map_bhi, map_blo, p)
+                 : launch_pdl_cluster2(gemm_tf32x3_2sm_kernel<false>, grid, dim3(TG_THREADS), smem2, st, map_a, map_bhi, map_blo, p);
+        PTK_CHECK_CUDA(le2);
+        PTK_CHECK_LAUNCH();
+        return PTK_OK;
+    }
     if (!smem_optin_done(0)) {  // the attribute is per device
         PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PTK_CHECK_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

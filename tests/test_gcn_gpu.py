@@ -452,3 +452,18 @@ def test_native_stack_runner_is_bit_identical_to_the_per_layer_calls(golden, hid
         assert la <= lb and la >= lb - 3 * layers, (la, lb)
         for u, v in zip(a, b):
             assert torch.equal(u, v)
+
+
+@pytest.mark.parametrize("mode", ["1", "3"])
+def test_cluster_forms_of_the_tensor_core_gemm(mode):
+    """The 2-CTA cluster forms of the tcgen05 forward / dgrad GEMM (PTK_TG_PAIR=1: weight tiles multicast over the pair,
+    3: cta_group::2 MMAs over a 256-row tile; both off by default, DESIGN.md K5) give the single-CTA kernel's accuracy
+    against fp64 on ragged and full-size shapes.  The switch is read once per process: run in a child interpreter."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PTK_TG_PAIR=mode)
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "tc_2sm_check.py")], env=env, capture_output=True,
+                         text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
