@@ -199,3 +199,36 @@ def test_faces_cache_never_serves_a_stale_copy_and_checks_the_id_range():
         _faces_i32(torch.tensor([[0, 1, -1]]), 5)
     with pytest.raises(ValueError):
         _faces_i32(torch.zeros(4, 2, dtype=torch.int64), 5)
+
+
+def test_tile_unions_index_every_entry_of_the_kernel_csr(golden):
+    """graph.tile_unions (host side of ptk_gcn_aggregate_tiled): per tile of 8 rows the union is the sorted set of the
+    non-hub rows' columns, every CSR entry's local index points back at its column, hub rows are left out, and the
+    union is 2-3x smaller than the sum of the degrees on the real graphs (what the dense-tile kernel lives on)."""
+    from ptk_b200 import graph as G
+    adj = golden("adjacency")
+    for name in ("p_adj", "g_adj", "p_origional"):
+        rp, col = adj[name + "_rowptr"], adj[name + "_col"]
+        n = len(rp) - 1
+        deg = np.diff(rp)
+        val = np.repeat((1.0 / deg).astype(np.float32), deg)
+        f = G.factor_hubs(rp, col, val, n)
+        skip = f["row_skip"] if f["row_skip"] is not None else (np.diff(f["rowptr"]) > G.HUB_DEG)
+        uptr, ucol, lidx, max_union = G.tile_unions(f["rowptr"], f["col"], skip, n)
+        krp, kcol = f["rowptr"], f["col"]
+        n_tiles = (n + G.TILE_ROWS - 1) // G.TILE_ROWS
+        assert len(uptr) == n_tiles + 1 and uptr[-1] == len(ucol) and max_union == np.diff(uptr).max() <= 256
+        total_deg = 0
+        for t in range(n_tiles):
+            u = ucol[uptr[t]:uptr[t + 1]]
+            assert np.all(np.diff(u) > 0)                                   # sorted, unique
+            want = set()
+            for i in range(t * G.TILE_ROWS, min(n, (t + 1) * G.TILE_ROWS)):
+                if skip[i]:
+                    continue
+                c = kcol[krp[i]:krp[i + 1]]
+                assert np.array_equal(u[lidx[krp[i]:krp[i + 1]]], c)        # local index -> the entry's column
+                want.update(c.tolist())
+                total_deg += len(c)
+            assert set(u.tolist()) == want
+        assert 2.0 < total_deg / len(ucol) < 3.5, (name, total_deg / len(ucol))
