@@ -523,6 +523,52 @@ def _recon_setup(torch, ptk_b200, dev, rank, Bs, seed=0):
     return net, adj_info, vision, touch, feats, gt
 
 
+def _recon_e2e(torch, ptk_b200, dev, net, adj_info, vision, img_feats, Bs, time):
+    """The reconstruction step the way the reference's loop runs it (vision/train.py:120-157): per step the batch the
+    loader delivers -- touch charts (B,5,25,4: positions + mask token) and ground-truth clouds (B,10000,3) -- is copied
+    from pinned host memory, the vertex features come from the fused front (positional MLP + mask-token embedding +
+    pooled image features; the image features stand in for the CNN, which is out of scope, and stay on the device), the
+    loss is read back (`loss.item()`, train.py:151).  Host clock around K steps."""
+    torch.manual_seed(3)
+    enc, menc = ptk_b200.Positional_Encoder(448).to(dev), ptk_b200.Mask_Encoder(448).to(dev)
+    params = list(net.parameters()) + list(enc.parameters()) + list(menc.parameters())
+    opt = torch.optim.Adam(params, lr=3e-4, fused=True)
+    h_touch = torch.rand(Bs, 125, 4).pin_memory()
+    h_touch[..., :3] = h_touch[..., :3] * 0.02 + 0.2
+    h_touch[..., 3] = torch.randint(0, 3, (Bs, 125)).float()
+    h_gt = (torch.nn.functional.normalize(torch.randn(Bs, 10000, 3), dim=-1) * 0.25).pin_memory()
+    d_touch, d_gt = torch.empty(Bs, 125, 4, device=dev), torch.empty(Bs, 10000, 3, device=dev)
+    vmask = 3 * torch.ones(Bs, 1824, 1, device=dev)
+
+    def step():
+        d_touch.copy_(h_touch, non_blocking=True)
+        d_gt.copy_(h_gt, non_blocking=True)
+        masks = [vmask, torch.cat((vmask, d_touch[..., 3:]), dim=1)]
+        opt.zero_grad(set_to_none=True)
+        verts = net(vision, d_touch[..., :3], lambda it, v: ptk_b200.encoders.vertex_features(
+            enc, menc, v, masks[0 if it == 0 else 1], img_feats[it]))
+        loss, _ = ptk_b200.recon.recon_loss(verts, adj_info["faces"], d_gt, number_points=10000)
+        loss.backward()
+        opt.step()
+        return float(loss.item())
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    K = 10
+    t0 = time.perf_counter()
+    for _ in range(K):
+        last = step()
+    el = time.perf_counter() - t0
+    return {"ms": 1e3 * el / K, "steps_per_s": K / el, "objects_per_s": Bs * K / el,
+            "h2d_bytes_per_step": int(h_touch.numel() * 4 + h_gt.numel() * 4), "d2h_bytes_per_step": 4,
+            "loss_last": last,
+            "note": "pinned host batch (touch charts + mask tokens + 10k-point clouds) -> device, fused vertex front "
+                    "(positional MLP + mask embedding + resident image features), 3 GCN passes, Chamfer loss, backward, "
+                    "Adam, loss.item(); includes the front's forward + backward, which the device-timed step above "
+                    "replaces by synthetic features"}
+
+
 def recon_step_measurement(torch, ptk_b200, dev, rank, world):
     """BASELINE configs[2]-shaped reconstruction step on EVERY rank: 3 GCN passes (448 -> 300 x 18 -> 3,
     N = 1824/1949/1949) + 3 x 10k-point Chamfer loss + backward + Adam; for world > 1 the parameter gradients go
@@ -611,6 +657,11 @@ def recon_step_measurement(torch, ptk_b200, dev, rank, world):
             out["tensor_core_forward"] = {"error": repr(exc)[:300]}
         finally:
             ptk_b200.ops.algo["fwd_train"] = saved
+        try:  # end to end: what a data loader delivers starts in pinned host memory, the loss is read back every step
+            import time
+            out["e2e"] = _recon_e2e(torch, ptk_b200, dev, net, adj_info, vision, feats, Bs, time)
+        except Exception as exc:
+            out["e2e"] = {"error": repr(exc)[:300]}
     del state
     torch.cuda.empty_cache()
     if world > 1 and 16 % world == 0:
