@@ -72,6 +72,11 @@ SIGNATURES = {
     "ptk_vertex_front_fwd": (C.c_int, [_vp] * 10 + [_i64, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "ptk_vertex_front_colsum_workspace_bytes": (_sz, [_i64, _i32]),
     "ptk_vertex_front_colsum": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _sz, _vp]),
+    "ptk_mesh_chamfer_workspace_bytes": (_sz, [_i64, _i64, _i64, _i64, _i64]),
+    "ptk_mesh_chamfer_fwd": (C.c_int, [_vp, _i64, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _i64, _i64, _vp, _vp, _vp, _vp, _vp,
+                                       _vp, _sz, _vp]),
+    "ptk_mesh_chamfer_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _vp,
+                                       _vp, _sz, _vp]),
     "ptk_host_ctx_create": (_vp, [C.c_int]),
     "ptk_host_ctx_destroy": (None, [_vp]),
     "ptk_host_chamfer": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp, _vp]),

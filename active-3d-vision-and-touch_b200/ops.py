@@ -338,6 +338,71 @@ def sample_points(verts, faces_i32, u_face, uv, face_idx=None):
     return _Sample.apply(verts, faces_i32, u_face, uv, face_idx)
 
 
+class _MeshChamfer(torch.autograd.Function):
+    """utils.chamfer_distance as ONE autograd node (ptk_mesh_chamfer_fwd / bwd): `repeat` samplings of the mesh, the
+    Chamfer distance of each against gt, the mean -- instead of 2 x repeat + 2 nodes with torch tensors in between."""
+
+    @staticmethod
+    def forward(ctx, verts, gt, faces_i32, u_face, uv, given_idx):
+        _need_cuda(verts, gt, faces_i32, u_face, uv, given_idx)
+        verts, gt, uv = _f32c(verts), _f32c(gt), _f32c(uv)
+        if verts.dim() != 3 or verts.shape[2] != 3 or gt.dim() != 3 or gt.shape[2] != 3 or gt.shape[0] != verts.shape[0]:
+            raise ValueError(f"Expected verts (B,V,3) and gt (B,P,3), got {tuple(verts.shape)} and {tuple(gt.shape)}")
+        if faces_i32.dtype != torch.int32 or faces_i32.dim() != 2 or faces_i32.shape[1] != 3:
+            raise ValueError("faces must be an (F,3) int32 tensor")
+        B, V, _ = verts.shape
+        P2, F = gt.shape[1], faces_i32.shape[0]
+        if uv.dim() != 4 or uv.shape[1] != 2 or uv.shape[2] != B:
+            raise ValueError("uv must be (repeat,2,B,S)")
+        R, S = uv.shape[0], uv.shape[3]
+        dev = verts.device
+        if given_idx is None:
+            u_face = _f32c(u_face)
+            if tuple(u_face.shape) != (R, B, S):
+                raise ValueError("u_face must be (repeat,B,S)")
+            fidx = torch.empty(R, B, S, dtype=torch.int32, device=dev)
+        else:
+            if tuple(given_idx.shape) != (R, B, S):
+                raise ValueError("face_idx must be (repeat,B,S)")
+            fidx, u_face = given_idx.to(torch.int32).contiguous(), None
+        faces_i32 = faces_i32.contiguous()
+        L = _lib.lib()
+        cd = torch.empty(B, dtype=torch.float32, device=dev)
+        pts = torch.empty(R, B, S, 3, dtype=torch.float32, device=dev)
+        idx_x = torch.empty(R, B, S, dtype=torch.int32, device=dev)
+        idx_y = torch.empty(R, B, P2, dtype=torch.int32, device=dev)
+        ws = _ws(L.ptk_mesh_chamfer_workspace_bytes(B, V, F, S, P2), dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.ptk_mesh_chamfer_fwd(_p(verts), B, V, _p(faces_i32), F, _p(gt), P2, _p(u_face), _p(uv), S, R,
+                                              _p(cd), _p(pts), _p(fidx), _p(idx_x), _p(idx_y), _p(ws), ws.numel(),
+                                              _stream()), "ptk_mesh_chamfer_fwd")
+        ctx.save_for_backward(gt, pts, fidx, idx_x, idx_y, uv, faces_i32)
+        ctx.dims = (B, V, F, S, P2, R)
+        return cd
+
+    @staticmethod
+    def backward(ctx, g):
+        gt, pts, fidx, idx_x, idx_y, uv, faces_i32 = ctx.saved_tensors
+        B, V, F, S, P2, R = ctx.dims
+        g = _f32c(g)
+        dev = g.device
+        gv = torch.empty(B, V, 3, dtype=torch.float32, device=dev) if ctx.needs_input_grad[0] else None
+        gg = torch.empty(B, P2, 3, dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
+        L = _lib.lib()
+        ws = _ws(L.ptk_mesh_chamfer_workspace_bytes(B, V, F, S, P2), dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.ptk_mesh_chamfer_bwd(_p(gt), _p(pts), _p(fidx), _p(idx_x), _p(idx_y), _p(uv), _p(faces_i32), _p(g),
+                                              B, V, F, S, P2, R, _p(gv), _p(gg), _p(ws), ws.numel(), _stream()),
+                       "ptk_mesh_chamfer_bwd")
+        return gv, gg, None, None, None, None
+
+
+def mesh_chamfer(verts, gt, faces_i32, u_face, uv, face_idx=None):
+    """cd (B,): mean over the repeats of chamfer(sample(verts, faces), gt).  u_face (repeat,B,S), uv (repeat,2,B,S);
+    with `face_idx` (repeat,B,S) given, u_face is ignored (the caller drew the faces).  Differentiable w.r.t. verts and gt."""
+    return _MeshChamfer.apply(verts, gt, faces_i32, u_face, uv, face_idx)
+
+
 def mesh_face_areas(verts, faces_i32):
     """(B,V,3), (F,3) int32 -> areas (B,F): utils.py:163-164 for a batch sharing one face list (no grad)."""
     _need_cuda(verts, faces_i32)

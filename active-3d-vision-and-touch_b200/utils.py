@@ -93,19 +93,53 @@ def batch_sample(verts, faces, num=10000, generator=None, uniforms=None, face_dr
     return pts
 
 
+fused_mesh_chamfer = True  # chamfer_distance as one autograd node (ops.mesh_chamfer); tests flip this
+
+
 def chamfer_distance(verts, faces, gt_points, num=1000, repeat=3, generator=None, uniforms=None, face_draw=None):
     """Chamfer distance between a predicted mesh and a ground-truth cloud: mean over `repeat`
     independent surface samplings of pytorch3d-style chamfer(pred_points, gt_points,
-    batch_reduction=None).  Returns (B,) (utils.py:204-217)."""
-    cds = []
-    for r in range(max(int(repeat), 1)):
-        uni = uniforms[r] if uniforms is not None else None
-        pred_points = batch_sample(verts, faces, num=num, generator=generator, uniforms=uni, face_draw=face_draw)
-        cd, _, _ = ops.chamfer(pred_points, gt_points)
-        cds.append(cd)
-    if len(cds) == 1:
-        return cds[0]
-    return torch.stack(cds).mean(dim=0)
+    batch_reduction=None).  Returns (B,) (utils.py:204-217).
+
+    The random draws are made here, repeat by repeat, in the reference's consumption order (face draw, then
+    torch.rand(2,bs,num): utils.py:170,179); sampling, Chamfer and the mean then run as ONE call / one autograd node
+    (ptk_mesh_chamfer_fwd / bwd)."""
+    R = max(int(repeat), 1)
+    if not fused_mesh_chamfer:
+        cds = []
+        for r in range(R):
+            uni = uniforms[r] if uniforms is not None else None
+            pred_points = batch_sample(verts, faces, num=num, generator=generator, uniforms=uni, face_draw=face_draw)
+            cd, _, _ = ops.chamfer(pred_points, gt_points)
+            cds.append(cd)
+        return cds[0] if len(cds) == 1 else torch.stack(cds).mean(dim=0)
+    f32 = _faces_i32(faces, verts.shape[-2])
+    mode = face_draw or globals()["face_draw"]
+    if mode not in ("uniform", "multinomial"):
+        raise ValueError(f"face_draw must be 'uniform' or 'multinomial', got {mode!r}")
+    bs, dev = verts.shape[0], verts.device
+    ufs, uvs, fis = [], [], []
+    for r in range(R):
+        if uniforms is not None:
+            uf, uv = uniforms[r]
+            ufs.append(uf)
+            uvs.append(uv)
+        elif mode == "multinomial":
+            with torch.no_grad():
+                Ar = ops.mesh_face_areas(verts, f32)                       # utils.py:163-164
+                Ar[Ar != Ar] = 0                                           # utils.py:165
+                Ar = torch.abs(Ar / Ar.sum(1).unsqueeze(1))                # utils.py:166
+                Ar[Ar != Ar] = 1                                           # utils.py:167
+                fis.append(Ar.multinomial(num, replacement=True, generator=generator))   # utils.py:170
+            uvs.append(torch.rand(2, bs, num, dtype=torch.float32, device=dev, generator=generator))  # :179
+        else:
+            uf, uv = draw_uniforms(bs, num, dev, generator)
+            ufs.append(uf)
+            uvs.append(uv)
+    uv = torch.stack(uvs)
+    if fis:
+        return ops.mesh_chamfer(verts, gt_points, f32, None, uv, face_idx=torch.stack(fis))
+    return ops.mesh_chamfer(verts, gt_points, f32, torch.stack(ufs), uv)
 
 
 # ------------------------------------------------------------------------------------- adjacency

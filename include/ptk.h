@@ -344,6 +344,26 @@ int ptk_vertex_front_colsum(const float *g, const float *mask, int64_t M, int32_
                             void *workspace, size_t workspace_bytes, ptk_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * utils.chamfer_distance(verts, faces, gt_points, num, repeat) (pterotactyl/utility/utils.py:204-217) on device
+ * pointers, one call per pass: repeat x (ptk_sample_fwd -> ptk_chamfer_fwd), cd (B) = the mean over the repeats
+ * (sum in repeat order, one multiply by 1/repeat -- torch.stack(cds).mean(0)); backward: repeat x (ptk_chamfer_bwd ->
+ * ptk_sample_bwd) accumulated in repeat order.  u_face (repeat,B,S) / uv (repeat,2,B,S): the uniform draws of the
+ * repeats in consumption order; u_face may be NULL, face_idx (repeat,B,S) is then the caller's draw (see
+ * ptk_sample_fwd).  pts (repeat,B,S,3), face_idx, idx_x (repeat,B,S), idx_y (repeat,B,P2) are what the backward
+ * needs.  grad_verts (B,V,3) / grad_gt (B,P2,3) are overwritten; either may be NULL (autoencoder: only grad_gt,
+ * autoencoder/train.py:145-150).  workspace: 256-byte aligned, ptk_mesh_chamfer_workspace_bytes.
+ * ---------------------------------------------------------------------------------------------- */
+size_t ptk_mesh_chamfer_workspace_bytes(int64_t B, int64_t V, int64_t F, int64_t S, int64_t P2);
+int ptk_mesh_chamfer_fwd(const float *verts, int64_t B, int64_t V, const int32_t *faces, int64_t F, const float *gt,
+                         int64_t P2, const float *u_face, const float *uv, int64_t S, int64_t repeat, float *cd,
+                         float *pts, int32_t *face_idx, int32_t *idx_x, int32_t *idx_y, void *workspace,
+                         size_t workspace_bytes, ptk_stream_t stream);
+int ptk_mesh_chamfer_bwd(const float *gt, const float *pts, const int32_t *face_idx, const int32_t *idx_x,
+                         const int32_t *idx_y, const float *uv, const int32_t *faces, const float *grad_cd, int64_t B,
+                         int64_t V, int64_t F, int64_t S, int64_t P2, int64_t repeat, float *grad_verts,
+                         float *grad_gt, void *workspace, size_t workspace_bytes, ptk_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Host-buffer entry points (end-to-end path: H2D + kernels + D2H inside the call).
  * All pointers are HOST pointers (pinned memory makes the copies asynchronous and faster).
  * ---------------------------------------------------------------------------------------------- */

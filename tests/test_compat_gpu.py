@@ -152,3 +152,40 @@ def test_config2_touch_chart_loss_full_size(oracle, golden):
     assert rel_err(cd.detach().cpu().numpy(), want_cd) < TOL
     assert abs(float(loss) - 9000.0 * want_cd.mean()) < TOL * abs(9000.0 * want_cd.mean())
     assert rel_err(vt.grad.cpu().numpy(), want_g) < TOL
+
+
+@pytest.mark.parametrize("mode", ["uniform", "multinomial"])
+def test_fused_mesh_chamfer_equals_the_per_repeat_composition(golden, mode):
+    """utils.chamfer_distance as one autograd node (ptk_mesh_chamfer_fwd / bwd) against the same function composed of
+    batch_sample + chamfer per repeat + stack + mean (utils.py:204-217): same RNG consumption (same seed => same draws),
+    values, vertex gradient and -- the autoencoder's case (autoencoder/train.py:145-150) -- the gradient of the second cloud."""
+    m = golden("meshes")
+    verts0 = torch.from_numpy(m["obj0_verts"]).cuda()
+    faces = torch.from_numpy(m["obj0_faces"].astype(np.int64)).cuda()
+    B, num, P2 = 3, 1700, 2100
+    scale = 1.0 + 0.1 * torch.arange(B, device="cuda", dtype=torch.float32)[:, None, None]
+    w = torch.tensor([1.0, -2.0, 0.5], device="cuda")
+    res = []
+    try:
+        for fused in (True, False):
+            ptk_b200.utils.fused_mesh_chamfer = fused
+            g = torch.Generator(device="cuda").manual_seed(11)
+            verts = (verts0[None] * scale).clone().requires_grad_(True)
+            gt = (torch.rand(B, P2, 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(5)) * 0.2 - 0.1).requires_grad_(True)
+            before = ptk_b200._lib.launch_count()
+            cd = ptk_b200.utils.chamfer_distance(verts, faces, gt, num=num, repeat=3, generator=g, face_draw=mode)
+            (cd * w).sum().backward()
+            res.append((cd.detach(), verts.grad.clone(), gt.grad.clone(), ptk_b200._lib.launch_count() - before,
+                        torch.rand(4, device="cuda", generator=g)))
+    finally:
+        ptk_b200.utils.fused_mesh_chamfer = True
+    (c1, gv1, gg1, _, tail1), (c2, gv2, gg2, _, tail2) = res
+    assert torch.equal(tail1, tail2)                                   # the generator was advanced identically
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    assert rel(c1, c2) < 1e-6 and rel(gv1, gv2) < 1e-6 and rel(gg1, gg2) < 1e-6
+    # only the second cloud needs a gradient (the sampled cloud is detached in the autoencoder's loss)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    gt = gg1.detach().clone().requires_grad_(True)
+    cd = ptk_b200.utils.chamfer_distance((verts0[None] * scale).detach(), faces, gt, num=num, repeat=2, generator=g, face_draw=mode)
+    cd.sum().backward()
+    assert gt.grad is not None and torch.isfinite(gt.grad).all()
