@@ -1,7 +1,7 @@
-"""Dev tool: the bars on the same box -- the reference's own formulation of the GCN part
+"""Checker-side tool (lives under tests/: it runs the oracle's torch restatement): the bars on the same box -- the reference's own formulation of the GCN part
 (dense row-normalised adjacency, torch.matmul: vision/model.py:351-363) and a brute-force torch Chamfer, run with
 torch on the GPU (FP32, TF32 off as torch defaults), next to the ptk_b200 kernels on the same inputs.
-    python tools/torch_gpu_baselines.py > profiles/rNN_torch_gpu_baselines.txt
+    python tests/torch_gpu_baselines.py > profiles/rNN_torch_gpu_baselines.txt
 PyTorch3D's CUDA knn is not installed here, so the Chamfer bar is torch.cdist + min, not the reference's kernel."""
 import os, sys, types
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -25,4 +25,4 @@ timeout 600 python tools/chamfer_sweep.py > $OUT/${TAG}_chamfer_sweep.txt 2>&1
 timeout 300 python tools/vertex_front_bench.py > $OUT/${TAG}_vertex_front.txt 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:sgemm_fwd_tma -s 3 -c 1 -f -o $OUT/${TAG}_fwd \
     python tools/fwd_one.py > $OUT/${TAG}_ncu_fwd.log 2>&1
-timeout 300 python tools/torch_gpu_baselines.py > $OUT/${TAG}_torch_gpu_baselines.txt 2>&1
+timeout 300 python tests/torch_gpu_baselines.py > $OUT/${TAG}_torch_gpu_baselines.txt 2>&1
