@@ -57,11 +57,12 @@ __device__ __forceinline__ void vf_layer(const float *__restrict__ W, const floa
     const int nkt = (K + VF_KT - 1) / VF_KT;
     const bool vec_out = (Nout & 3) == 0;
     for (int n0 = 0; n0 < Nout; n0 += VF_NT) {
-        float acc[4][8];
+        // accumulators as packed FP32x2 pairs along n: fma.rn.f32x2 = the same IEEE FMA per element, half the issue slots
+        unsigned long long acc2[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+            for (int j = 0; j < 4; ++j) acc2[i][j] = 0ull;
         float stg[8];
         auto fetch = [&](int kt) {
             if (vec_w) {
@@ -100,20 +101,31 @@ __device__ __forceinline__ void vf_layer(const float *__restrict__ W, const floa
 #pragma unroll
             for (int kk = 0; kk < VF_KT; ++kk) {
                 const float4 a = *reinterpret_cast<const float4 *>(in_t + (size_t)(kt * VF_KT + kk) * VF_TM + ty * 4);
-                const float4 b0 = *reinterpret_cast<const float4 *>(&ws[buf][kk][tx * 4]);
-                const float4 b1 = *reinterpret_cast<const float4 *>(&ws[buf][kk][64 + tx * 4]);
+                const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(&ws[buf][kk][tx * 4]);
+                const ulonglong2 b1 = *reinterpret_cast<const ulonglong2 *>(&ws[buf][kk][64 + tx * 4]);
                 const float av[4] = {a.x, a.y, a.z, a.w};
-                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const unsigned long long bv[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
-                for (int i = 0; i < 4; ++i)
+                for (int i = 0; i < 4; ++i) {
+                    unsigned long long a2;
+                    asm("mov.b64 %0, {%1, %1};" : "=l"(a2) : "f"(av[i]));
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                    for (int j = 0; j < 4; ++j) asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(acc2[i][j]) : "l"(a2), "l"(bv[j]));
+                }
             }
             if (kt + 1 < nkt) {
                 stash(buf ^ 1);
                 __syncthreads();
             }
         }
+        float acc[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                acc[i][2 * j] = __uint_as_float((unsigned)acc2[i][j]);
+                acc[i][2 * j + 1] = __uint_as_float((unsigned)(acc2[i][j] >> 32));
+            }
         // epilogue: this thread holds vertices ty*4 .. +3, columns n0 + tx*4 .. +3 and n0 + 64 + tx*4 .. +3
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
