@@ -599,7 +599,7 @@ def recon_step_measurement(torch, ptk_b200, dev, rank, world):
         step()
         launches = ptk_b200._lib.launch_count() - n0
         ms = _timeit_ranks(torch, step, 5, 2, dev, world)
-        return ms, launches, len(reducer.buckets), (net, adj_info, vision, touch, feats, gt)
+        return ms, launches, len(reducer.buckets), (net, adj_info, vision, touch, feats, gt, reducer)
 
     Bs = 16
     ms, launches, nb, state = measure(Bs, Bs * world)
@@ -614,26 +614,34 @@ def recon_step_measurement(torch, ptk_b200, dev, rank, world):
     # pipe utilisation; aggregation, Chamfer and optimizer time count against it.
     out["fp32_peak_tflops"] = fp32_peak
     out["fp32_roofline_frac"] = out["gemm_tflops_per_gpu"] / fp32_peak
+    net, adj_info, vision, touch, feats, gt, reducer = state
+    graphed = None
+    try:  # the same step replayed from one CUDA graph per rank (launch gaps and Python overhead removed); for world > 1
+        # the bucketed NCCL all-reduces are captured with it (tools/graph_ddp_check.py: gradients equal the eager step's)
+        opt_g = torch.optim.Adam(net.parameters(), lr=3e-4, fused=True, capturable=True)
+
+        def step_g():
+            opt_g.zero_grad(set_to_none=True)
+            verts = net(vision, touch, lambda it, v: feats[it])
+            _, cd = ptk_b200.recon.recon_loss(verts, adj_info["faces"], gt, number_points=10000)
+            loss = 9000.0 * cd.sum() / (Bs * world)
+            loss.backward()
+            reducer.finish()
+            opt_g.step()
+            return loss
+
+        graphed = ptk_b200.recon.GraphedStep(step_g)
+        msg = _timeit_ranks(torch, graphed, 10, 2, dev, world)
+        out["ms_cuda_graph"] = msg
+        out["steps_per_s_cuda_graph"] = 1e3 / msg
+        out["objects_per_s_cuda_graph"] = world * Bs * 1e3 / msg
+        out["fp32_roofline_frac_cuda_graph"] = Bs * flop_per_object / (msg * 1e-3) / 1e12 / fp32_peak
+    except Exception as exc:
+        out["cuda_graph_error"] = repr(exc)[:300]
+    finally:
+        graphed = None          # a live graph with captured NCCL kernels blocks destroy_process_group()
+        torch.cuda.synchronize()
     if world == 1:
-        net, adj_info, vision, touch, feats, gt = state
-        try:  # the same step replayed from one CUDA graph (launch gaps and Python overhead removed)
-            opt_g = torch.optim.Adam(net.parameters(), lr=3e-4, fused=True, capturable=True)
-
-            def step_g():
-                opt_g.zero_grad(set_to_none=True)
-                verts = net(vision, touch, lambda it, v: feats[it])
-                loss, _ = ptk_b200.recon.recon_loss(verts, adj_info["faces"], gt, number_points=10000)
-                loss.backward()
-                opt_g.step()
-                return loss
-
-            graphed = ptk_b200.recon.GraphedStep(step_g)
-            msg = _timeit_ranks(torch, graphed, 10, 2, dev, world)
-            out["ms_cuda_graph"] = msg
-            out["steps_per_s_cuda_graph"] = 1e3 / msg
-            out["fp32_roofline_frac_cuda_graph"] = Bs * flop_per_object / (msg * 1e-3) / 1e12 / fp32_peak
-        except Exception as exc:
-            out["cuda_graph_error"] = repr(exc)[:300]
         try:  # what bit-level ReLU-mask parity costs: the same step with the tensor-core (3xTF32) training forward
             saved = ptk_b200.ops.algo["fwd_train"]
             ptk_b200.ops.algo["fwd_train"] = ptk_b200.ops.GEMM_AUTO  # tcgen05 wherever the kernel accepts the shape
@@ -662,7 +670,7 @@ def recon_step_measurement(torch, ptk_b200, dev, rank, world):
             out["e2e"] = _recon_e2e(torch, ptk_b200, dev, net, adj_info, vision, feats, Bs, time)
         except Exception as exc:
             out["e2e"] = {"error": repr(exc)[:300]}
-    del state
+    del state, net, adj_info, vision, touch, feats, gt, reducer
     torch.cuda.empty_cache()
     if world > 1 and 16 % world == 0:
         try:

@@ -115,6 +115,54 @@ def test_cuda_graph_capture_of_forward():
     assert torch.equal(cham, ref) and torch.equal(ix, rix)
 
 
+def test_graphed_step_replays_the_eager_step(golden):
+    """recon.GraphedStep: forward + loss + backward + (capturable) Adam of a small chart deformer captured in one CUDA
+    graph; with the learning rate held at 0 both arms see the same weights, so a replay's loss and parameter gradients
+    must equal the eager step's (atomics in the Chamfer backward: 1e-5).  tools/graph_ddp_check.py is the same check
+    at world 2 with the NCCL gradient all-reduce inside the capture."""
+    import copy
+    from ptk_b200.graph import Graph
+    adj, meshes = golden("adjacency"), golden("meshes")
+    g = Graph.from_csr(adj["p_adj_rowptr"], adj["p_adj_col"], "cuda")
+    adj_info = {"origional": Graph.from_csr(adj["p_origional_rowptr"], adj["p_origional_col"], "cuda").dense(),
+                "adj": g.dense(), "faces": torch.from_numpy(adj["p_faces"]).cuda().long()}
+    args = types.SimpleNamespace(use_img=True, use_touch=True, finger=True, num_grasps=5, num_GCN_layers=5,
+                                 hidden_GCN_size=96, cut=0.33)
+    B, width, npts = 3, 40, 2000
+    torch.manual_seed(0)
+    net_e = ptk_b200.recon.ChartDeformer(adj_info, args, width).cuda()
+    net_g = copy.deepcopy(net_e)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    vision = torch.from_numpy(meshes["vision_verts"]).cuda()[None].repeat(B, 1, 1)
+    touch = torch.rand(B, 125, 3, device="cuda", generator=gen) * 0.02 + 0.2
+    feats = [torch.rand(B, n, width, device="cuda", generator=gen) for n in (1824, 1949, 1949)]
+    gt = torch.nn.functional.normalize(torch.randn(B, npts, 3, device="cuda", generator=gen), dim=-1) * 0.25
+    uni = [ptk_b200.utils.draw_uniforms(B, npts, torch.device("cuda"), gen) for _ in range(3)]
+    lr = torch.zeros((), device="cuda")
+
+    def make(net):
+        opt = torch.optim.Adam(net.parameters(), lr=lr, fused=True, capturable=True)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            verts = net(vision, touch, lambda it, v: feats[it])
+            loss, _ = ptk_b200.recon.recon_loss(verts, adj_info["faces"], gt, number_points=npts, uniforms=uni)
+            loss.backward()
+            opt.step()
+            return loss
+        return step
+
+    le = make(net_e)()
+    graphed = ptk_b200.recon.GraphedStep(make(net_g), warmup=2)
+    for _ in range(2):
+        lg = graphed()
+    torch.cuda.synchronize()
+    assert abs(float(lg.detach()) - float(le.detach())) <= 1e-6 * abs(float(le.detach()))
+    for a, b in zip(net_g.parameters(), net_e.parameters()):
+        assert torch.equal(a, b)                 # lr = 0: untouched
+        assert float((a.grad - b.grad).abs().max()) <= 1e-5 * float(b.grad.abs().max()) + 1e-12
+
+
 def test_config2_touch_chart_loss_full_size(oracle, golden):
     """BASELINE config 2 shape (touch/train.py:226-240): 64 touch charts (25 vertices, 32 faces) moved by random
     rigid frames, 4000 sampled points vs 4000 ground-truth points, repeat = 3, loss = 9000 * mean.  Loss, per-chart
