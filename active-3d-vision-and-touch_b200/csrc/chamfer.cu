@@ -30,9 +30,12 @@
 //     defining arithmetic, and the few queries whose runner-up chunk is within the proven error bound
 //     are re-scanned exactly (chamfer_nn_exact2_kernel, list mode).  Results are bit-identical to
 //     PTK_CHAMFER_EXACT (the 6-op scan on packed FP32x2, kept selectable for checks).
+//   * PTK_CHAMFER_PRUNED (chamfer_pruned.cuh): the same results from a cell-sorted copy of both clouds and a box
+//     hierarchy -- a few hundred evaluations per query instead of P; PTK_CHAMFER_AUTO picks it for large clouds.
 #include <atomic>
 
 #include "chamfer_kernel2.cuh"
+#include "chamfer_pruned.cuh"
 
 namespace ptk {
 
@@ -43,14 +46,18 @@ constexpr int CH_MINB = 3;   // exact scan
 constexpr int CH_MINB_F = 4; // filter scan
 constexpr int CH_TT_F = 1024; // targets per TMA tile (double buffered: 2 x 4 x 4 KB)
 
-// process-wide choice of the scan (both give identical results); atomic: other host threads may launch while it is set
-static std::atomic<int> g_chamfer_algo{PTK_CHAMFER_FILTER};
+// process-wide choice of the scan (all give identical results); atomic: other host threads may launch while it is set
+static std::atomic<int> g_chamfer_algo{PTK_CHAMFER_AUTO};
 
-// workspace: [PairAux B][soa_x B*4*P1p][soa_y B*4*P2p][keys_x B*P1][keys_y B*P2][rescue_x B*P1][rescue_y B*P2]
-//            [flag_x B*P1][flag_y B*P2][count 2B]      (P?p = cloud size padded to SOA_PAD points)
+// workspace: [PairAux B][soa_x B*4*P1p][soa_y B*4*P2p][box_x B*nbx(P1)][box_y B*nbx(P2)][keys_x B*P1][keys_y B*P2]
+//            [rescue_x B*P1][rescue_y B*P2][flag_x B*P1][flag_y B*P2][count 2B][bad 2B]
+//            (P?p = cloud size padded to SOA_PAD points; the boxes and `bad` belong to the pruned scan, which also
+//            keeps its cell-sorted clouds in soa_x / soa_y)
 struct ChamferWs {
     PairAux *aux;
     float *soa_x, *soa_y;
+    PrBox *box_x, *box_y;
+    int *bad;
     u64 *keys_x, *keys_y;
     int *rescue_x, *rescue_y;
     unsigned int *flag_x, *flag_y, *count;
@@ -58,7 +65,8 @@ struct ChamferWs {
 
 static size_t chamfer_ws_bytes(int64_t B, int64_t P1, int64_t P2) {
     return sizeof(PairAux) * (size_t)B + 16 * (size_t)B * (size_t)(soa_padded((int)P1) + soa_padded((int)P2)) +
-           (size_t)B * (size_t)(P1 + P2) * (8 + 4 + 4) + 8 * (size_t)B;
+           sizeof(PrBox) * (size_t)B * (size_t)(pr_boxes((int)P1) + pr_boxes((int)P2)) +
+           (size_t)B * (size_t)(P1 + P2) * (8 + 4 + 4) + 16 * (size_t)B;
 }
 
 static ChamferWs carve(void *workspace, int64_t B, int64_t P1, int64_t P2) {
@@ -70,6 +78,10 @@ static ChamferWs carve(void *workspace, int64_t B, int64_t P1, int64_t P2) {
     p += 16 * (size_t)B * soa_padded((int)P1);
     w.soa_y = reinterpret_cast<float *>(p);
     p += 16 * (size_t)B * soa_padded((int)P2);
+    w.box_x = reinterpret_cast<PrBox *>(p);
+    p += sizeof(PrBox) * (size_t)B * pr_boxes((int)P1);
+    w.box_y = reinterpret_cast<PrBox *>(p);
+    p += sizeof(PrBox) * (size_t)B * pr_boxes((int)P2);
     w.keys_x = reinterpret_cast<u64 *>(p);
     p += 8 * (size_t)B * P1;
     w.keys_y = reinterpret_cast<u64 *>(p);
@@ -83,6 +95,8 @@ static ChamferWs carve(void *workspace, int64_t B, int64_t P1, int64_t P2) {
     w.flag_y = reinterpret_cast<unsigned int *>(p);
     p += 4 * (size_t)B * P2;
     w.count = reinterpret_cast<unsigned int *>(p);
+    p += 8 * (size_t)B;
+    w.bad = reinterpret_cast<int *>(p);
     return w;
 }
 
@@ -223,12 +237,68 @@ static NNPlan plan_nn(int64_t B, int64_t Pq_max, int64_t Pt_max, int ndir, int m
     return p;
 }
 
-static int launch_nn(const float *x, const float *y, int64_t B, int64_t P1, int64_t P2, const ChamferWs &w,
-                     int dir_only, cudaStream_t st) {
+static unsigned long long g_pr_optin = 0ull;  // cudaFuncAttributeMaxDynamicSharedMemorySize is per device
+
+// PTK_CHAMFER_PRUNED: sort both clouds into cells (one CTA per cloud), walk the box hierarchy (one warp per 32 sorted
+// queries), re-scan the queued queries (exact ties across leaves, non-finite clouds) with the exact kernel.
+static int launch_nn_pruned(const float *x, const float *y, int64_t B, int64_t P1, int64_t P2, const ChamferWs &w,
+                            int dir_only, cudaStream_t st) {
     const int ndir = dir_only >= 0 ? 1 : 2;
     const int64_t Pq = dir_only == 0 ? P1 : (dir_only == 1 ? P2 : (P1 > P2 ? P1 : P2));
     const int64_t Pt = dir_only == 0 ? P2 : (dir_only == 1 ? P1 : (P1 > P2 ? P1 : P2));
-    const bool filter = g_chamfer_algo.load(std::memory_order_relaxed) == PTK_CHAMFER_FILTER;
+    const int iP1 = (int)P1, iP2 = (int)P2;
+    PTK_REQUIRE(2 * B <= 0x7fffffffLL && B * ndir <= 65535, PTK_ERR_SHAPE,
+                "chamfer: batch %lld too large for one launch (max 32767 clouds)", (long long)B);
+    // 16^3 cells up to 32k points (a 16-point leaf then spans about one or two cells), 32^3 above
+    const bool fine = (P1 > P2 ? P1 : P2) > 32768;
+    if (fine) {
+        int dev = 0;
+        PTK_CHECK_CUDA(cudaGetDevice(&dev));
+        if (dev >= 64 || !((g_pr_optin >> dev) & 1ull)) {
+            PTK_CHECK_CUDA(cudaFuncSetAttribute(chamfer_pruned_sort_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                4 * 32768));
+            if (dev < 64) g_pr_optin |= 1ull << dev;
+        }
+        launch_pdl(chamfer_pruned_sort_kernel<5>, dim3((unsigned)(2 * B)), dim3(PR_SORT_THREADS), 4 * 32768, st, x, y, iP1,
+                   iP2, w.soa_x, w.soa_y, w.box_x, w.box_y, w.bad, w.count);
+    } else {
+        launch_pdl(chamfer_pruned_sort_kernel<4>, dim3((unsigned)(2 * B)), dim3(PR_SORT_THREADS), 4 * 4096, st, x, y, iP1,
+                   iP2, w.soa_x, w.soa_y, w.box_x, w.box_y, w.bad, w.count);
+    }
+    PTK_CHECK_LAUNCH();
+    u64 *keys_x = dir_only == 1 ? nullptr : w.keys_x;
+    u64 *keys_y = dir_only == 0 ? nullptr : w.keys_y;
+    dim3 qgrid((unsigned)ceil_div(Pq, (int64_t)PR_QUERY_WARPS * 32), (unsigned)(B * ndir));
+    launch_pdl(chamfer_pruned_query_kernel, qgrid, dim3(PR_QUERY_WARPS * 32), 0, st, (const float *)w.soa_x,
+               (const float *)w.soa_y, (const PrBox *)w.box_x, (const PrBox *)w.box_y, (const int *)w.bad, iP1, iP2, keys_x,
+               keys_y, dir_only, w.rescue_x, w.rescue_y, w.count);
+    PTK_CHECK_LAUNCH();
+    const NNPlan p = plan_nn(B, Pq, Pt, ndir, CH_MINB);
+    dim3 rgrid((unsigned)ceil_div(Pq, (int64_t)CH_THREADS * 8), (unsigned)p.n_split, (unsigned)(B * ndir));
+    launch_pdl(chamfer_nn_exact2_kernel<8, CH_CHUNK, CH_THREADS, CH_MINB>, rgrid, dim3(CH_THREADS), 0, st, x, y, iP1, iP2,
+               p.split_len, p.n_split, w.keys_x, w.keys_y, dir_only, w.rescue_x, w.rescue_y, w.count);
+    PTK_CHECK_LAUNCH();
+    return PTK_OK;
+}
+
+// PTK_CHAMFER_AUTO: the pruned scan pays for its sort once the clouds are large enough (measured crossover,
+// tools/chamfer_sweep.py); larger than one top-level group of boxes falls back to the filter scan.
+static int resolve_algo(int64_t P1, int64_t P2) {
+    int algo = g_chamfer_algo.load(std::memory_order_relaxed);
+    const int64_t Pmax = P1 > P2 ? P1 : P2, Pmin = P1 > P2 ? P2 : P1;
+    if (algo == PTK_CHAMFER_AUTO) algo = (Pmin >= PTK_CHAMFER_AUTO_MIN_POINTS) ? PTK_CHAMFER_PRUNED : PTK_CHAMFER_FILTER;
+    if (algo == PTK_CHAMFER_PRUNED && Pmax > PR_MAX_POINTS) algo = PTK_CHAMFER_FILTER;
+    return algo;
+}
+
+static int launch_nn(const float *x, const float *y, int64_t B, int64_t P1, int64_t P2, const ChamferWs &w,
+                     int dir_only, cudaStream_t st) {
+    const int algo = resolve_algo(P1, P2);
+    if (algo == PTK_CHAMFER_PRUNED) return launch_nn_pruned(x, y, B, P1, P2, w, dir_only, st);
+    const int ndir = dir_only >= 0 ? 1 : 2;
+    const int64_t Pq = dir_only == 0 ? P1 : (dir_only == 1 ? P2 : (P1 > P2 ? P1 : P2));
+    const int64_t Pt = dir_only == 0 ? P2 : (dir_only == 1 ? P1 : (P1 > P2 ? P1 : P2));
+    const bool filter = algo == PTK_CHAMFER_FILTER;
     NNPlan p = plan_nn(B, Pq, Pt, ndir, filter ? CH_MINB_F : CH_MINB);
     u64 *keys_x = dir_only == 1 ? nullptr : w.keys_x;
     u64 *keys_y = dir_only == 0 ? nullptr : w.keys_y;
@@ -289,11 +359,24 @@ extern "C" size_t ptk_chamfer_workspace_bytes(int64_t B, int64_t P1, int64_t P2)
 }
 
 extern "C" int ptk_chamfer_set_algo(int algo) {
-    PTK_REQUIRE(algo == PTK_CHAMFER_FILTER || algo == PTK_CHAMFER_EXACT, PTK_ERR_SHAPE,
+    PTK_REQUIRE(algo == PTK_CHAMFER_FILTER || algo == PTK_CHAMFER_EXACT || algo == PTK_CHAMFER_PRUNED ||
+                    algo == PTK_CHAMFER_AUTO, PTK_ERR_SHAPE,
                 "chamfer_set_algo: unknown algorithm %d", algo);
     g_chamfer_algo.store(algo, std::memory_order_relaxed);
     return PTK_OK;
 }
+
+#ifdef PTK_PR_STATS
+extern "C" int ptk_debug_pr_stats(unsigned long long *out8, int reset) {  // development builds only (not in ptk.h)
+    PTK_CHECK_CUDA(cudaDeviceSynchronize());
+    PTK_CHECK_CUDA(cudaMemcpyFromSymbol(out8, pr_stats, 64));
+    if (reset) {
+        unsigned long long z[8] = {0};
+        PTK_CHECK_CUDA(cudaMemcpyToSymbol(pr_stats, z, 64));
+    }
+    return PTK_OK;
+}
+#endif
 
 extern "C" int ptk_chamfer_get_algo(void) { return g_chamfer_algo.load(std::memory_order_relaxed); }
 
@@ -311,7 +394,7 @@ extern "C" int ptk_chamfer_rescued(const void *workspace, int64_t B, int64_t P1,
         for (int64_t i = 0; i < 2 * B; ++i) n += h[i];
     cudaFreeHost(h);
     PTK_CHECK_CUDA(e);
-    *n_rescued = g_chamfer_algo.load(std::memory_order_relaxed) == PTK_CHAMFER_FILTER ? n : 0;
+    *n_rescued = resolve_algo(P1, P2) != PTK_CHAMFER_EXACT ? n : 0;
     return PTK_OK;
 }
 

@@ -38,8 +38,11 @@ def _ws(nbytes, device):
 
 # ------------------------------------------------------------------------------------- Chamfer / KNN
 def set_chamfer_algo(name):
-    """'filter' (default: 3-FFMA expansion filter + exact recheck) or 'exact' (6-op scan); same results."""
-    algo = {"filter": _lib.CHAMFER_FILTER, "exact": _lib.CHAMFER_EXACT}[name]
+    """'filter' (3-FFMA expansion filter + exact recheck), 'exact' (6-op scan), 'pruned' (cell-sorted clouds + box
+    hierarchy, a few hundred evaluations per query) or 'auto' (the default: pruned when both clouds have >= 20k points,
+    filter otherwise); all return the same bits."""
+    algo = {"filter": _lib.CHAMFER_FILTER, "exact": _lib.CHAMFER_EXACT, "pruned": _lib.CHAMFER_PRUNED,
+            "auto": _lib.CHAMFER_AUTO}[name]
     _lib.check(_lib.lib().ptk_chamfer_set_algo(algo), "ptk_chamfer_set_algo")
 
 

@@ -62,11 +62,19 @@ uint64_t ptk_launch_count(void);
  * ---------------------------------------------------------------------------------------------- */
 size_t ptk_chamfer_workspace_bytes(int64_t B, int64_t P1, int64_t P2); /* 16-byte aligned workspace */
 
-/* Nearest-neighbour scan algorithm (process-wide; both give bit-identical results):
- *   PTK_CHAMFER_FILTER (default)  3-FFMA expansion filter on packed FP32x2 + exact recheck/rescue
- *   PTK_CHAMFER_EXACT             the defining 6-op arithmetic for every (query, target) pair */
+/* Nearest-neighbour scan algorithm (process-wide; all give bit-identical results):
+ *   PTK_CHAMFER_FILTER            3-FFMA expansion filter on packed FP32x2 + exact recheck/rescue
+ *   PTK_CHAMFER_EXACT             the defining 6-op arithmetic for every (query, target) pair
+ *   PTK_CHAMFER_PRUNED            cell-sorted clouds + box hierarchy: only the leaves whose lower bound can beat or
+ *                                 tie a query's incumbent are evaluated (same arithmetic, same tie rule); clouds of
+ *                                 more than 524288 points fall back to PTK_CHAMFER_FILTER
+ *   PTK_CHAMFER_AUTO (default)    PTK_CHAMFER_PRUNED when both clouds have >= PTK_CHAMFER_AUTO_MIN_POINTS points,
+ *                                 PTK_CHAMFER_FILTER otherwise */
 #define PTK_CHAMFER_FILTER 0
 #define PTK_CHAMFER_EXACT 1
+#define PTK_CHAMFER_PRUNED 2
+#define PTK_CHAMFER_AUTO 3
+#define PTK_CHAMFER_AUTO_MIN_POINTS 20000
 int ptk_chamfer_set_algo(int algo);
 int ptk_chamfer_get_algo(void);
 /* Diagnostics (synchronises `stream`): number of queries of the last forward that used `workspace`

@@ -15,6 +15,15 @@ def rel_err(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
 
 
+@pytest.fixture(params=["filter", "pruned"])
+def algo(request):
+    """Run the test under the brute-force filter scan and under the pruned (cell-sorted + box hierarchy) scan: both must
+    reproduce the oracle bit for bit."""
+    ptk_b200.ops.set_chamfer_algo(request.param)
+    yield request.param
+    ptk_b200.ops.set_chamfer_algo("auto")
+
+
 def run(x, y, grad=None):
     xt = torch.from_numpy(x).cuda().requires_grad_(grad is not None)
     yt = torch.from_numpy(y).cuda().requires_grad_(grad is not None)
@@ -26,7 +35,7 @@ def run(x, y, grad=None):
     return out
 
 
-def test_config1_golden(golden, oracle):
+def test_config1_golden(golden, oracle, algo):
     g = golden("chamfer")
     cham, ix, iy = run(g["c1_x"], g["c1_y"])
     assert np.array_equal(ix, g["c1_fma_idx_x"]) and np.array_equal(iy, g["c1_fma_idx_y"])
@@ -38,7 +47,7 @@ def test_config1_golden(golden, oracle):
     assert np.array_equal(d.cpu().numpy(), od) and np.array_equal(i.cpu().numpy(), oi)
 
 
-def test_ties_golden(golden):
+def test_ties_golden(golden, algo):
     g = golden("chamfer")
     cham, ix, iy = run(g["tie_x"], g["tie_y"])
     assert np.array_equal(ix, g["tie_idx_x"]) and np.array_equal(iy, g["tie_idx_y"])
@@ -54,7 +63,7 @@ def test_unequal_sizes_gradients_golden(golden):
 
 @pytest.mark.parametrize("B,P1,P2", [(1, 1, 1), (1, 1, 37), (2, 255, 257), (3, 2048, 2049), (1, 4097, 1000),
                                      (5, 1000, 4000), (64, 16, 16), (1, 10000, 6400), (2, 30000, 512)])
-def test_random_vs_oracle(oracle, B, P1, P2):
+def test_random_vs_oracle(oracle, algo, B, P1, P2):
     rng = np.random.default_rng(B * 100003 + P1 * 17 + P2)
     x = (rng.random((B, P1, 3), np.float32) - 0.5).astype(np.float32)
     y = (rng.random((B, P2, 3), np.float32) - 0.5).astype(np.float32)
@@ -67,7 +76,7 @@ def test_random_vs_oracle(oracle, B, P1, P2):
     assert rel_err(gx, ogx) < TOL and rel_err(gy, ogy) < TOL
 
 
-def test_duplicate_points_and_grid_ties(oracle):
+def test_duplicate_points_and_grid_ties(oracle, algo):
     # integer lattice: masses of exact ties; lowest index must win everywhere
     rng = np.random.default_rng(7)
     x = rng.integers(0, 4, (2, 3000, 3)).astype(np.float32)
@@ -110,7 +119,7 @@ def _clouds(kind, rng, B, P1, P2):
 @pytest.mark.parametrize("kind", ["far_from_origin", "tiled_x4", "thin_rod", "huge_values", "tiny_values",
                                   "one_outlier", "identical"])
 @pytest.mark.parametrize("B,P1,P2", [(2, 1500, 2000), (1, 4000, 4000)])
-def test_filter_adversarial_vs_oracle(oracle, kind, B, P1, P2):
+def test_filter_adversarial_vs_oracle(oracle, algo, kind, B, P1, P2):
     rng = np.random.default_rng(sum(map(ord, kind)) + P1)
     if kind == "identical":
         P2 = P1
@@ -124,7 +133,7 @@ def test_filter_adversarial_vs_oracle(oracle, kind, B, P1, P2):
         assert rel_err(cham, ocham) < TOL
 
 
-def test_non_finite_inputs_take_the_exact_path(oracle):
+def test_non_finite_inputs_take_the_exact_path(oracle, algo):
     rng = np.random.default_rng(11)
     x = rng.random((2, 700, 3), np.float32); y = rng.random((2, 900, 3), np.float32)
     x[0, 5, 1] = np.nan; y[0, 17, 0] = np.inf; y[1, 3, 2] = -np.inf
@@ -141,14 +150,71 @@ def test_filter_and_exact_algorithms_agree_bitwise():
         ptk_b200.ops.set_chamfer_algo("exact")
         c0, ix0, iy0 = ptk_b200.ops.chamfer(x, y)
         d0, i0 = ptk_b200.ops.knn1(x, y)
-    finally:
         ptk_b200.ops.set_chamfer_algo("filter")
-    c1, ix1, iy1 = ptk_b200.ops.chamfer(x, y)
-    d1, i1 = ptk_b200.ops.knn1(x, y)
+        c1, ix1, iy1 = ptk_b200.ops.chamfer(x, y)
+        d1, i1 = ptk_b200.ops.knn1(x, y)
+        n = ptk_b200.ops.chamfer_rescued(x, y)
+    finally:
+        ptk_b200.ops.set_chamfer_algo("auto")
     assert torch.equal(ix0, ix1) and torch.equal(iy0, iy1) and torch.equal(c0, c1)
     assert torch.equal(d0, d1) and torch.equal(i0, i1)
-    n = ptk_b200.ops.chamfer_rescued(x, y)
     assert 0 < n < 0.05 * 8 * 12000   # uniform clouds: ~1 % of the queries need the exact rescue
+
+
+def _surface(B, P, g, noise=0.0):
+    p = torch.nn.functional.normalize(torch.randn(B, P, 3, device="cuda", generator=g), dim=-1) * 0.25
+    return p * (1 + noise * torch.randn(B, P, 1, device="cuda", generator=g)) if noise else p
+
+
+@pytest.mark.parametrize("kind,B,P1,P2", [("cube", 256, 10000, 10000), ("surface", 64, 10000, 10000), ("surface", 2, 100000, 100000),
+                                          ("cube", 1, 70000, 33000), ("clustered", 3, 6000, 9000), ("lattice", 2, 20000, 20000)])
+def test_pruned_scan_equals_the_brute_force_scan_at_full_size(kind, B, P1, P2):
+    """Sizes the CPU oracle cannot reach (BASELINE config 3 / 5 shapes): the pruned scan must return the brute-force
+    scan's indices, distances and Chamfer values bit for bit, whatever the distribution -- volume, surface samples,
+    tight clusters (the uniform grid cannot separate them: the scan cap hands those queries to the exact rescue scan)
+    and a lattice with thousands of exact ties per query."""
+    g = torch.Generator(device="cuda").manual_seed(P1 + B)
+    if kind == "cube":
+        x, y = torch.rand(B, P1, 3, device="cuda", generator=g) - 0.5, torch.rand(B, P2, 3, device="cuda", generator=g) - 0.5
+    elif kind == "surface":
+        x, y = _surface(B, P1, g, 0.02), _surface(B, P2, g)
+    elif kind == "clustered":
+        x = torch.rand(B, P1, 3, device="cuda", generator=g)
+        y = torch.rand(B, P2, 3, device="cuda", generator=g) * 0.01
+        y[:, ::2] += 0.9
+    else:
+        x = torch.randint(0, 10, (B, P1, 3), device="cuda", generator=g).float() * 0.125
+        y = torch.randint(0, 10, (B, P2, 3), device="cuda", generator=g).float() * 0.125
+    out = {}
+    try:
+        for name in ("filter", "pruned"):
+            ptk_b200.ops.set_chamfer_algo(name)
+            out[name] = ptk_b200.ops.chamfer(x, y) + ptk_b200.ops.knn1(y, x)
+            if name == "pruned":
+                rescued = ptk_b200.ops.chamfer_rescued(x, y)
+    finally:
+        ptk_b200.ops.set_chamfer_algo("auto")
+    for a, b in zip(out["filter"], out["pruned"]):
+        assert torch.equal(a, b)
+    if kind == "clustered":
+        assert rescued > 0          # the cap fired: those queries took the exact scan
+    elif kind != "lattice":
+        assert rescued == 0
+
+
+def test_auto_picks_the_pruned_scan_for_large_clouds_only():
+    """PTK_CHAMFER_AUTO (the default): brute-force filter scan below PTK_CHAMFER_AUTO_MIN_POINTS (20000) points per cloud
+    -- the named 10k configs stay on the kernel north_star specifies and the roofline is quoted on -- pruned at and above.
+    The filter queues ~0.3 % of its queries for the rescue scan on uniform clouds, the pruned scan none: that tells
+    which one ran."""
+    assert ptk_b200._lib.lib().ptk_chamfer_get_algo() == ptk_b200._lib.CHAMFER_AUTO
+    g = torch.Generator(device="cuda").manual_seed(3)
+    small = [torch.rand(2, 12000, 3, device="cuda", generator=g) for _ in range(2)]
+    large = [torch.rand(1, 20000, 3, device="cuda", generator=g) for _ in range(2)]
+    mixed = [large[0], small[0][:1].contiguous()]
+    assert ptk_b200.ops.chamfer_rescued(*small) > 0
+    assert ptk_b200.ops.chamfer_rescued(*large) == 0
+    assert ptk_b200.ops.chamfer_rescued(*mixed) > 0     # both clouds have to be large
 
 
 def test_only_y_needs_grad(oracle):
@@ -164,7 +230,7 @@ def test_only_y_needs_grad(oracle):
     assert rel_err(yt.grad.cpu().numpy(), ogy) < TOL
 
 
-def test_full_size_properties():
+def test_full_size_properties(algo):
     """BASELINE size (10k x 10k, batch 256): properties that need no oracle run."""
     B, P = 256, 10000
     g = torch.Generator(device="cuda").manual_seed(0)

@@ -7,6 +7,7 @@ import torch
 import ptk_b200
 
 dev = torch.device("cuda")
+ptk_b200.ops.set_chamfer_algo("filter")   # the main columns are the brute-force scan at every size; the last two the pruned scan
 
 def timeit(fn, iters):
     fn(); torch.cuda.synchronize()
@@ -29,7 +30,8 @@ def graph_time(fn, iters):
         fn()
     return timeit(g.replay, iters)
 
-print(f"{'P':>7} {'B':>4} {'fwd ms':>10} {'fwd+bwd ms':>11} {'graph ms':>9} {'pairs/s':>10} {'Tevals/s':>9} {'rescued %':>9}  checks")
+print(f"{'P':>7} {'B':>4} {'fwd ms':>10} {'fwd+bwd ms':>11} {'graph ms':>9} {'pairs/s':>10} {'Tevals/s':>9} {'rescued %':>9} "
+      f"{'pruned fwd':>10} {'x':>6}  checks")
 for P in (1000, 2000, 5000, 10000, 20000, 50000, 100000):
     for B in (1, 4, 16, 64, 256):
         if B * P * P > 256 * 20000 * 20000 * 1.1:   # keep the sweep within a few seconds per cell
@@ -57,6 +59,13 @@ for P in (1000, 2000, 5000, 10000, 20000, 50000, 100000):
         q = x[0, :32].detach()
         ok3 = torch.equal(((q[:, None] - y[0].detach()[None]) ** 2).sum(-1).argmin(1).int(), ix[0, :32])
         resc = ptk_b200.ops.chamfer_rescued(x.detach(), y.detach()) / (2.0 * B * P)
+        try:  # the pruned scan on the same clouds: same indices and value, its forward time
+            ptk_b200.ops.set_chamfer_algo("pruned")
+            tp = timeit(fwd, iters)
+            cp, px, py = fwd()
+            ok3 = ok3 and torch.equal(px, ix) and torch.equal(py, iy) and torch.equal(cp, cham)
+        finally:
+            ptk_b200.ops.set_chamfer_algo("filter")
         print(f"{P:7d} {B:4d} {tf:10.3f} {tb:11.3f} {tg:9.3f} {B / (tb * 1e-3):10.1f} {2.0 * B * P * P / (tf * 1e-3) / 1e12:9.3f} "
-              f"{100 * resc:9.3f}  {'ok' if (ok1 and ok2 and ok3) else 'FAIL'}", flush=True)
+              f"{100 * resc:9.3f} {tp:10.3f} {tf / tp:6.2f}  {'ok' if (ok1 and ok2 and ok3) else 'FAIL'}", flush=True)
         del x, y
