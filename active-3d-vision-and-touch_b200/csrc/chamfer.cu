@@ -49,13 +49,15 @@ constexpr int CH_TT_F = 1024; // targets per TMA tile (double buffered: 2 x 4 x 
 // process-wide choice of the scan (all give identical results); atomic: other host threads may launch while it is set
 static std::atomic<int> g_chamfer_algo{PTK_CHAMFER_AUTO};
 
-// workspace: [PairAux B][soa_x B*4*P1p][soa_y B*4*P2p][box_x B*nbx(P1)][box_y B*nbx(P2)][keys_x B*P1][keys_y B*P2]
+// workspace: [PairAux B][soa_x B*4*P1p][soa_y B*4*P2p][stage_x B*4*P1p][stage_y B*4*P2p][box_x B*nbx(P1)][box_y B*nbx(P2)]
+//            [keys_x B*P1][keys_y B*P2]
 //            [rescue_x B*P1][rescue_y B*P2][flag_x B*P1][flag_y B*P2][count 2B][bad 2B]
-//            (P?p = cloud size padded to SOA_PAD points; the boxes and `bad` belong to the pruned scan, which also
+//            (P?p = cloud size padded to SOA_PAD points; stage, boxes and `bad` belong to the pruned scan, which also
 //            keeps its cell-sorted clouds in soa_x / soa_y)
 struct ChamferWs {
     PairAux *aux;
     float *soa_x, *soa_y;
+    float4 *stage_x, *stage_y;
     PrBox *box_x, *box_y;
     int *bad;
     u64 *keys_x, *keys_y;
@@ -64,7 +66,7 @@ struct ChamferWs {
 };
 
 static size_t chamfer_ws_bytes(int64_t B, int64_t P1, int64_t P2) {
-    return sizeof(PairAux) * (size_t)B + 16 * (size_t)B * (size_t)(soa_padded((int)P1) + soa_padded((int)P2)) +
+    return sizeof(PairAux) * (size_t)B + 32 * (size_t)B * (size_t)(soa_padded((int)P1) + soa_padded((int)P2)) +
            sizeof(PrBox) * (size_t)B * (size_t)(pr_boxes((int)P1) + pr_boxes((int)P2)) +
            (size_t)B * (size_t)(P1 + P2) * (8 + 4 + 4) + 16 * (size_t)B;
 }
@@ -77,6 +79,10 @@ static ChamferWs carve(void *workspace, int64_t B, int64_t P1, int64_t P2) {
     w.soa_x = reinterpret_cast<float *>(p);
     p += 16 * (size_t)B * soa_padded((int)P1);
     w.soa_y = reinterpret_cast<float *>(p);
+    p += 16 * (size_t)B * soa_padded((int)P2);
+    w.stage_x = reinterpret_cast<float4 *>(p);
+    p += 16 * (size_t)B * soa_padded((int)P1);
+    w.stage_y = reinterpret_cast<float4 *>(p);
     p += 16 * (size_t)B * soa_padded((int)P2);
     w.box_x = reinterpret_cast<PrBox *>(p);
     p += sizeof(PrBox) * (size_t)B * pr_boxes((int)P1);
@@ -260,10 +266,13 @@ static int launch_nn_pruned(const float *x, const float *y, int64_t B, int64_t P
             if (dev < 64) g_pr_optin |= 1ull << dev;
         }
         launch_pdl(chamfer_pruned_sort_kernel<5>, dim3((unsigned)(2 * B)), dim3(PR_SORT_THREADS), 4 * 32768, st, x, y, iP1,
-                   iP2, w.soa_x, w.soa_y, w.box_x, w.box_y, w.bad, w.count);
+                   iP2, w.soa_x, w.soa_y, w.stage_x, w.stage_y, w.box_x, w.box_y, w.bad, w.count, 0);
     } else {
-        launch_pdl(chamfer_pruned_sort_kernel<4>, dim3((unsigned)(2 * B)), dim3(PR_SORT_THREADS), 4 * 4096, st, x, y, iP1,
-                   iP2, w.soa_x, w.soa_y, w.box_x, w.box_y, w.bad, w.count);
+        // <= 32768 points: 16 KB histogram + up to 64 KB of 16-bit cell ranks (the 48 KB default limit covers 16k points)
+        const size_t smem = 4 * 4096 + 2 * (size_t)((P1 > P2 ? P1 : P2) + 8);
+        int keep = smem <= 48 * 1024 ? 1 : 0;
+        launch_pdl(chamfer_pruned_sort_kernel<4>, dim3((unsigned)(2 * B)), dim3(PR_SORT_THREADS), keep ? smem : 4 * 4096, st, x,
+                   y, iP1, iP2, w.soa_x, w.soa_y, w.stage_x, w.stage_y, w.box_x, w.box_y, w.bad, w.count, keep);
     }
     PTK_CHECK_LAUNCH();
     u64 *keys_x = dir_only == 1 ? nullptr : w.keys_x;
@@ -349,6 +358,8 @@ static int launch_nn(const float *x, const float *y, int64_t B, int64_t P1, int6
     return PTK_OK;
 }
 
+int chamfer_resolve_algo(int64_t P1, int64_t P2) { return resolve_algo(P1, P2); }  // for the host pipeline (host_api.cu)
+
 }  // namespace ptk
 
 using namespace ptk;
@@ -367,12 +378,12 @@ extern "C" int ptk_chamfer_set_algo(int algo) {
 }
 
 #ifdef PTK_PR_STATS
-extern "C" int ptk_debug_pr_stats(unsigned long long *out8, int reset) {  // development builds only (not in ptk.h)
+extern "C" int ptk_debug_pr_stats(unsigned long long *out16, int reset) {  // development builds only (not in ptk.h)
     PTK_CHECK_CUDA(cudaDeviceSynchronize());
-    PTK_CHECK_CUDA(cudaMemcpyFromSymbol(out8, pr_stats, 64));
+    PTK_CHECK_CUDA(cudaMemcpyFromSymbol(out16, pr_stats, 128));
     if (reset) {
-        unsigned long long z[8] = {0};
-        PTK_CHECK_CUDA(cudaMemcpyToSymbol(pr_stats, z, 64));
+        unsigned long long z[16] = {0};
+        PTK_CHECK_CUDA(cudaMemcpyToSymbol(pr_stats, z, 128));
     }
     return PTK_OK;
 }

@@ -40,10 +40,12 @@ constexpr int PR_MAX_POINTS = PR_CHUNK * PR_FAN * PR_FAN * PR_FAN;  // 524288: o
 
 #ifdef PTK_PR_STATS
 // development counters: [0] warps, [1] level-2 pops, [2] level-1 pops, [3] leaf pops (per-query tests), [4] leaf scans, [5] bails
-__device__ unsigned long long pr_stats[8];
+__device__ unsigned long long pr_stats[16];  // [8..15]: sort-kernel phase cycles (thread 0 of every CTA)
+#define PR_PHASE(i) do { if (threadIdx.x == 0) { const long long t_ = clock64(); atomicAdd(&pr_stats[8 + (i)], (unsigned long long)(t_ - t_phase)); t_phase = t_; } } while (0)
 #define PR_STAT(i, n) do { if (lane == 0) atomicAdd(&pr_stats[i], (unsigned long long)(n)); } while (0)
 #else
 #define PR_STAT(i, n) do { } while (0)
+#define PR_PHASE(i) do { } while (0)
 #endif
 
 struct PrBox {
@@ -85,12 +87,13 @@ __device__ __forceinline__ unsigned pr_cell_rank(int cx, int cy, int cz) {
     return code;
 }
 
-// grid = 2 * B (blockIdx.x = 2 * b + cloud), block = 1024, dynamic shared memory = 4 * 8^BITS bytes (the histogram).
+// grid = 2 * B (blockIdx.x = 2 * b + cloud), block = 1024, dynamic shared memory = 4 * 8^BITS bytes (the histogram)
+// + 2 * max(P1, P2) bytes when keep_codes.
 template <int BITS>
 __global__ void __launch_bounds__(PR_SORT_THREADS)
 chamfer_pruned_sort_kernel(const float *__restrict__ x, const float *__restrict__ y, int P1, int P2, float *soa_x,
-                           float *soa_y, PrBox *box_x, PrBox *box_y, int *__restrict__ bad_flags,
-                           unsigned int *__restrict__ rescue_count) {
+                           float *soa_y, float4 *stage_x, float4 *stage_y, PrBox *box_x, PrBox *box_y,
+                           int *__restrict__ bad_flags, unsigned int *__restrict__ rescue_count, int keep_codes) {
     constexpr int G = 1 << BITS, NC = G * G * G, PER = NC / PR_SORT_THREADS;
     static_assert(NC % PR_SORT_THREADS == 0, "histogram must split evenly over the threads");
     extern __shared__ unsigned int pr_hist[];
@@ -99,12 +102,15 @@ chamfer_pruned_sort_kernel(const float *__restrict__ x, const float *__restrict_
     __shared__ unsigned int swsum[32];
     __shared__ int sbad;
     pdl_wait();
+    long long t_phase = clock64();
+    (void)t_phase;
     const int b = blockIdx.x >> 1, cloud = blockIdx.x & 1;
     const int tid = threadIdx.x;
     const int P = cloud == 0 ? P1 : P2;
     const int Pp = soa_padded(P);
     const float *__restrict__ src = cloud == 0 ? x + (size_t)b * P1 * 3 : y + (size_t)b * P2 * 3;
     float *out = cloud == 0 ? soa_x + (size_t)b * 4 * Pp : soa_y + (size_t)b * 4 * Pp;
+    float4 *stage = cloud == 0 ? stage_x + (size_t)b * Pp : stage_y + (size_t)b * Pp;
     PrBox *box0 = (cloud == 0 ? box_x : box_y) + (size_t)b * pr_boxes(P);
     const int nb0 = pr_nb0(P), nb1 = pr_nb1(P), nb2 = pr_nb2(P);
     PrBox *box1 = box0 + nb0, *box2 = box1 + nb1;
@@ -161,6 +167,7 @@ chamfer_pruned_sort_kernel(const float *__restrict__ x, const float *__restrict_
         sbox[3 + tid] = h;
     }
     __syncthreads();
+    PR_PHASE(0);  // bounding box
     const bool cloud_bad = sbad != 0;
     float org[3], scl[3];
 #pragma unroll
@@ -180,11 +187,29 @@ chamfer_pruned_sort_kernel(const float *__restrict__ x, const float *__restrict_
         return pr_cell_rank<BITS>(cx, cy, cz);
     };
 
-    // ---- histogram over the cells
-    for (int i = tid; i < P; i += PR_SORT_THREADS)
-        atomicAdd(&pr_hist[cell_of(src[3 * i], src[3 * i + 1], src[3 * i + 2])], 1u);
+    // ---- histogram over the cells; four points (twelve loads) in flight per thread.  The cell rank of a point is
+    // computed once and kept as 16 bits in shared memory when the launch reserved room for it (keep_codes).
+    unsigned short *codes = reinterpret_cast<unsigned short *>(pr_hist + NC);
+    for (int i0 = tid; i0 < P; i0 += 4 * PR_SORT_THREADS) {
+        float v[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = min(i0 + u * PR_SORT_THREADS, P - 1);
+            v[u][0] = src[3 * i], v[u][1] = src[3 * i + 1], v[u][2] = src[3 * i + 2];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * PR_SORT_THREADS;
+            if (i < P) {
+                const unsigned code = cell_of(v[u][0], v[u][1], v[u][2]);
+                if (keep_codes) codes[i] = (unsigned short)code;
+                atomicAdd(&pr_hist[code], 1u);
+            }
+        }
+    }
     __syncthreads();
 
+    PR_PHASE(1);  // histogram
     // ---- exclusive scan of the histogram (thread owns PER consecutive cells)
     {
         unsigned int sum = 0;
@@ -218,38 +243,46 @@ chamfer_pruned_sort_kernel(const float *__restrict__ x, const float *__restrict_
     }
     __syncthreads();
 
-    // ---- scatter into cell order, leaf-blocked: chunk c = [x16 | y16 | z16 | idx16]
-    for (int i = tid; i < P; i += PR_SORT_THREADS) {
-        const float px = src[3 * i], py = src[3 * i + 1], pz = src[3 * i + 2];
-        const unsigned int pos = atomicAdd(&pr_hist[cell_of(px, py, pz)], 1u);
-        float *o = out + (size_t)(pos >> 4) * 64 + (pos & 15);
-        o[0] = px;
-        o[16] = py;
-        o[32] = pz;
-        o[48] = __int_as_float(i);
-    }
-    for (int pos = P + tid; pos < Pp; pos += PR_SORT_THREADS) {  // padding: never a minimum, inert as a query
-        float *o = out + (size_t)(pos >> 4) * 64 + (pos & 15);
-        o[0] = PINF;
-        o[16] = PINF;
-        o[32] = PINF;
-        o[48] = __int_as_float(0x7fffffff);
+    PR_PHASE(2);  // scan
+    // ---- scatter into cell order: ONE 16-byte store per point (x, y, z, original index) into the staging array --
+    // four scalar stores per point into the leaf-blocked layout cost four 32-byte sectors each and were 60 % of this
+    // kernel.  The leaf pass below transposes the staged points into the layout the query kernel reads.
+    for (int i0 = tid; i0 < P; i0 += 4 * PR_SORT_THREADS) {
+        float v[4][3];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = min(i0 + u * PR_SORT_THREADS, P - 1);
+            v[u][0] = src[3 * i], v[u][1] = src[3 * i + 1], v[u][2] = src[3 * i + 2];
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * PR_SORT_THREADS;
+            if (i < P) {
+                const unsigned code = keep_codes ? (unsigned)codes[i] : cell_of(v[u][0], v[u][1], v[u][2]);
+                const unsigned int pos = atomicAdd(&pr_hist[code], 1u);
+                stage[pos] = make_float4(v[u][0], v[u][1], v[u][2], __int_as_float(i));
+            }
+        }
     }
     __syncthreads();
+    PR_PHASE(3);  // scatter
 
-    // ---- boxes: a half-warp per leaf (lane = point), then a warp per inner node (lane = child), shuffle reductions
+    // ---- leaves: a half-warp per leaf (lane = point) reads 256 staged bytes, writes the leaf [x16 | y16 | z16 | idx16]
+    // (padding: +inf coordinates -- never a minimum, inert as a query) and reduces the leaf's box by shuffles; then a
+    // warp per inner node (lane = child)
     {
         const int lane = tid & 31, hw = tid >> 4, l16 = tid & 15;
-        for (int c = hw; c < nb0; c += PR_SORT_THREADS / 16) {  // loop bounds are uniform per half-warp only:
-            const float *o = out + (size_t)c * 64;                 // shuffles below stay inside a half (xor < 16)
+        const int nleaf_all = Pp / PR_CHUNK;  // including the all-padding leaves up to the padded cloud size
+        for (int c = hw; c < nleaf_all; c += PR_SORT_THREADS / 16) {  // loop bounds are uniform per half-warp only:
+            float *o = out + (size_t)c * 64;                             // shuffles below stay inside a half (xor < 16)
             const bool live = c * PR_CHUNK + l16 < P;
-            float l[3], h[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float v = o[16 * k + l16];
-                l[k] = live ? v : PINF;
-                h[k] = live ? v : NINF;
-            }
+            float4 pt = make_float4(PINF, PINF, PINF, __int_as_float(0x7fffffff));
+            if (live) pt = stage[c * PR_CHUNK + l16];
+            o[l16] = pt.x;
+            o[16 + l16] = pt.y;
+            o[32 + l16] = pt.z;
+            o[48 + l16] = pt.w;
+            float l[3] = {pt.x, pt.y, pt.z}, h[3] = {live ? pt.x : NINF, live ? pt.y : NINF, live ? pt.z : NINF};
             const unsigned hmask = 0xffffu << (lane & 16);
 #pragma unroll
             for (int off = 8; off > 0; off >>= 1)
@@ -258,7 +291,7 @@ chamfer_pruned_sort_kernel(const float *__restrict__ x, const float *__restrict_
                     l[k] = fminf(l[k], __shfl_xor_sync(hmask, l[k], off));
                     h[k] = fmaxf(h[k], __shfl_xor_sync(hmask, h[k], off));
                 }
-            if (l16 == 0) {
+            if (l16 == 0 && c < nb0) {
                 box0[c].lo = make_float4(l[0], l[1], l[2], 0.f);
                 box0[c].hi = make_float4(h[0], h[1], h[2], 0.f);
             }
@@ -292,6 +325,7 @@ chamfer_pruned_sort_kernel(const float *__restrict__ x, const float *__restrict_
             __syncthreads();
         }
     }
+    PR_PHASE(4);  // boxes
 }
 
 __device__ __forceinline__ float pr_gap(float lo, float hi, float qlo, float qhi) {

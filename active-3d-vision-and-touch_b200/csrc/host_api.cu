@@ -81,6 +81,10 @@ extern "C" void ptk_host_ctx_destroy(ptk_host_ctx *c) {
     free(c);
 }
 
+namespace ptk {
+int chamfer_resolve_algo(int64_t P1, int64_t P2);  // chamfer.cu: the scan ptk_chamfer_fwd will run for these sizes
+}
+
 extern "C" int ptk_host_chamfer(ptk_host_ctx *c, const float *x, const float *y, int64_t B, int64_t P1,
                                 int64_t P2, float *cham, int32_t *idx_x, int32_t *idx_y,
                                 const float *grad_cham, float *grad_x, float *grad_y) {
@@ -121,7 +125,11 @@ extern "C" int ptk_host_chamfer(ptk_host_ctx *c, const float *x, const float *y,
     int64_t bounds[10];
     int nchunks = 0;
     bounds[0] = 0;
-    if (B >= 2 * bc_min) {
+    if (chamfer_resolve_algo(P1, P2) == PTK_CHAMFER_PRUNED && B >= 8) {
+        // the pruned scan is faster than the upload of its own input: equal chunks, the copy engine never waits and
+        // only the last chunk's kernels are exposed
+        for (int ci = 1; ci <= 8; ++ci) bounds[++nchunks] = B * ci / 8;
+    } else if (B >= 2 * bc_min) {
         const int64_t first = B / 8 > 0 ? B / 8 : 1;
         int64_t rest_chunks = (B - first) / bc_min;
         if (rest_chunks < 1) rest_chunks = 1;

@@ -36,9 +36,10 @@ def test_error_codes_without_gpu():
     # shape validation happens before any CUDA call, so it works without a device
     rc = L.ptk_chamfer_fwd(None, None, 1, 10, 10, None, None, None, None, None, None, 0, None)
     assert rc == _lib.PTK_ERR_SHAPE and "null" in _lib.last_error()
-    # PairAux + padded SoA clouds + the pruned scan's boxes (leaves + two levels: 7+1+1 and 4+1+1) + keys / lists / flags
+    # PairAux + padded SoA clouds (+ the pruned scan's staging copy) + its boxes (leaves + two levels: 7+1+1 and 4+1+1)
+    # + keys / lists / flags
     # + rescue counters and bad-cloud flags
-    assert L.ptk_chamfer_workspace_bytes(2, 100, 50) == (16 * 2 + 16 * 2 * (128 + 64) + 32 * 2 * (9 + 6) + 16 * 2 * 150
+    assert L.ptk_chamfer_workspace_bytes(2, 100, 50) == (16 * 2 + 32 * 2 * (128 + 64) + 32 * 2 * (9 + 6) + 16 * 2 * 150
                                                          + 16 * 2)
     assert L.ptk_chamfer_workspace_bytes(0, 100, 50) == 0
 

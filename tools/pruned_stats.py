@@ -7,9 +7,9 @@ import ptk_b200
 dev = torch.device("cuda")
 gen = torch.Generator(device=dev).manual_seed(1)
 lib = ptk_b200._lib.lib()
-buf = (ctypes.c_ulonglong * 8)()
+buf = (ctypes.c_ulonglong * 16)()
 ptk_b200.ops.set_chamfer_algo("pruned")
-for kind, B, P in (("cube", 64, 10000), ("sphere", 64, 10000), ("sphere", 1, 100000), ("cube", 1, 100000), ("sphere", 8, 50000), ("cube", 64, 2000)):
+for kind, B, P in (("cube", 64, 10000), ("cube", 256, 10000), ("sphere", 1, 100000), ("sphere", 8, 50000), ("cube", 64, 2000)):
     if kind == "cube":
         x, y = torch.rand(B, P, 3, device=dev, generator=gen) - 0.5, torch.rand(B, P, 3, device=dev, generator=gen) - 0.5
     else:
@@ -21,3 +21,6 @@ for kind, B, P in (("cube", 64, 10000), ("sphere", 64, 10000), ("sphere", 1, 100
     w = max(buf[0], 1)
     print(f"{kind:7s} B={B:3d} P={P:6d}: warps {buf[0]}, per warp: L2 pops {buf[1] / w:.1f}, L1 pops {buf[2] / w:.1f}, leaf tests {buf[3] / w:.1f}, "
           f"leaf scans {buf[4] / w:.1f}, bails {buf[5]}")
+    n = 2 * B
+    print("         sort kernel, cycles per CTA: " + ", ".join(f"{name} {buf[8 + i] / n:.0f}" for i, name in
+                                                              enumerate(("bbox", "hist", "scan", "scatter", "boxes"))))
