@@ -51,7 +51,8 @@ static std::atomic<int> g_chamfer_algo{PTK_CHAMFER_AUTO};
 
 // workspace: [PairAux B][soa_x B*4*P1p][soa_y B*4*P2p][stage_x B*4*P1p][stage_y B*4*P2p][box_x B*nbx(P1)][box_y B*nbx(P2)]
 //            [keys_x B*P1][keys_y B*P2]
-//            [rescue_x B*P1][rescue_y B*P2][flag_x B*P1][flag_y B*P2][count 2B][bad 2B]
+//            [rescue_x B*P1][rescue_y B*P2][flag_x B*P1][flag_y B*P2][count 2B][bad 2B][wide 2B][ghist 2B*bins]
+//            (the last two only when the wide sort applies: few large clouds, pr_wide_applies)
 //            (P?p = cloud size padded to SOA_PAD points; stage, boxes and `bad` belong to the pruned scan, which also
 //            keeps its cell-sorted clouds in soa_x / soa_y)
 struct ChamferWs {
@@ -60,15 +61,26 @@ struct ChamferWs {
     float4 *stage_x, *stage_y;
     PrBox *box_x, *box_y;
     int *bad;
+    PrWide *wide;
+    unsigned int *ghist;
     u64 *keys_x, *keys_y;
     int *rescue_x, *rescue_y;
     unsigned int *flag_x, *flag_y, *count;
 };
 
+// The wide (multi-launch) sort of the pruned scan: at most 128 clouds, the larger of at least 16k points.  A pure
+// function of the sizes: the workspace layout depends on it.
+static bool pr_wide_applies(int64_t B, int64_t P1, int64_t P2) { return 2 * B <= 128 && (P1 > P2 ? P1 : P2) >= 16384; }
+static bool pr_fine_grid(int64_t P1, int64_t P2) { return (P1 > P2 ? P1 : P2) > 32768; }  // 32^3 cells instead of 16^3
+static size_t pr_wide_bytes(int64_t B, int64_t P1, int64_t P2) {
+    if (!pr_wide_applies(B, P1, P2)) return 0;
+    return (size_t)(2 * B) * (sizeof(PrWide) + 4 * (size_t)(pr_fine_grid(P1, P2) ? 32768 : 4096));
+}
+
 static size_t chamfer_ws_bytes(int64_t B, int64_t P1, int64_t P2) {
     return sizeof(PairAux) * (size_t)B + 32 * (size_t)B * (size_t)(soa_padded((int)P1) + soa_padded((int)P2)) +
            sizeof(PrBox) * (size_t)B * (size_t)(pr_boxes((int)P1) + pr_boxes((int)P2)) +
-           (size_t)B * (size_t)(P1 + P2) * (8 + 4 + 4) + 16 * (size_t)B;
+           (size_t)B * (size_t)(P1 + P2) * (8 + 4 + 4) + 16 * (size_t)B + pr_wide_bytes(B, P1, P2);
 }
 
 static ChamferWs carve(void *workspace, int64_t B, int64_t P1, int64_t P2) {
@@ -103,6 +115,10 @@ static ChamferWs carve(void *workspace, int64_t B, int64_t P1, int64_t P2) {
     w.count = reinterpret_cast<unsigned int *>(p);
     p += 8 * (size_t)B;
     w.bad = reinterpret_cast<int *>(p);
+    p += 8 * (size_t)B;
+    w.wide = reinterpret_cast<PrWide *>(p);
+    p += sizeof(PrWide) * (size_t)(2 * B);
+    w.ghist = reinterpret_cast<unsigned int *>(p);
     return w;
 }
 
@@ -256,8 +272,41 @@ static int launch_nn_pruned(const float *x, const float *y, int64_t B, int64_t P
     PTK_REQUIRE(2 * B <= 0x7fffffffLL && B * ndir <= 65535, PTK_ERR_SHAPE,
                 "chamfer: batch %lld too large for one launch (max 32767 clouds)", (long long)B);
     // 16^3 cells up to 32k points (a 16-point leaf then spans about one or two cells), 32^3 above
-    const bool fine = (P1 > P2 ? P1 : P2) > 32768;
-    if (fine) {
+    const bool fine = pr_fine_grid(P1, P2);
+    if (pr_wide_applies(B, P1, P2)) {
+        // few large clouds: every phase of the sort is its own launch over slices of all clouds
+        const int NC = fine ? 32768 : 4096;
+        const int64_t Pm = P1 > P2 ? P1 : P2;
+        const dim3 sgrid((unsigned)ceil_div(Pm, (int64_t)PRW_SLICE), (unsigned)(2 * B));
+        launch_pdl(pr_wide_init_kernel, dim3((unsigned)(NC / 1024), (unsigned)(2 * B)), dim3(1024), 0, st, w.wide, w.ghist, NC,
+                   w.count);
+        PTK_CHECK_LAUNCH();
+        launch_pdl(pr_wide_bbox_kernel, sgrid, dim3(PRW_THREADS), 0, st, x, y, iP1, iP2, w.wide);
+        PTK_CHECK_LAUNCH();
+        if (fine) {
+            launch_pdl(pr_wide_hist_scatter_kernel<5, false>, sgrid, dim3(PRW_THREADS), 0, st, x, y, iP1, iP2,
+                       (const PrWide *)w.wide, w.ghist, w.soa_x, w.soa_y, w.stage_x, w.stage_y, w.bad);
+            PTK_CHECK_LAUNCH();
+            launch_pdl(pr_wide_scan_kernel<5>, dim3((unsigned)(2 * B)), dim3(1024), 0, st, w.ghist);
+            PTK_CHECK_LAUNCH();
+            launch_pdl(pr_wide_hist_scatter_kernel<5, true>, sgrid, dim3(PRW_THREADS), 0, st, x, y, iP1, iP2,
+                       (const PrWide *)w.wide, w.ghist, w.soa_x, w.soa_y, w.stage_x, w.stage_y, w.bad);
+        } else {
+            launch_pdl(pr_wide_hist_scatter_kernel<4, false>, sgrid, dim3(PRW_THREADS), 0, st, x, y, iP1, iP2,
+                       (const PrWide *)w.wide, w.ghist, w.soa_x, w.soa_y, w.stage_x, w.stage_y, w.bad);
+            PTK_CHECK_LAUNCH();
+            launch_pdl(pr_wide_scan_kernel<4>, dim3((unsigned)(2 * B)), dim3(1024), 0, st, w.ghist);
+            PTK_CHECK_LAUNCH();
+            launch_pdl(pr_wide_hist_scatter_kernel<4, true>, sgrid, dim3(PRW_THREADS), 0, st, x, y, iP1, iP2,
+                       (const PrWide *)w.wide, w.ghist, w.soa_x, w.soa_y, w.stage_x, w.stage_y, w.bad);
+        }
+        PTK_CHECK_LAUNCH();
+        launch_pdl(pr_wide_leaf_kernel, dim3((unsigned)ceil_div((int64_t)soa_padded((int)Pm) / PR_CHUNK, (int64_t)16), (unsigned)(2 * B)),
+                   dim3(256), 0, st, iP1, iP2, (const float4 *)w.stage_x, (const float4 *)w.stage_y, w.soa_x, w.soa_y, w.box_x,
+                   w.box_y);
+        PTK_CHECK_LAUNCH();
+        launch_pdl(pr_wide_inner_kernel, dim3((unsigned)(2 * B)), dim3(1024), 0, st, iP1, iP2, w.box_x, w.box_y);
+    } else if (fine) {
         int dev = 0;
         PTK_CHECK_CUDA(cudaGetDevice(&dev));
         if (dev >= 64 || !((g_pr_optin >> dev) & 1ull)) {

@@ -328,6 +328,274 @@ chamfer_pruned_sort_kernel(const float *__restrict__ x, const float *__restrict_
     PR_PHASE(4);  // boxes
 }
 
+// ------------------------------------------------------------------------------------------------
+// Wide form of the sort for FEW LARGE clouds (2 B <= 128 clouds of >= 16k points): one CTA per cloud leaves the chip
+// idle (100k points: 317 us on 2 SMs), so every phase becomes its own small launch over (slices of 2048 points) x
+// (clouds) and the histogram lives in global memory (L2 atomics):
+//   init -> bbox (atomicMin / atomicMax on order-preserving keys) -> hist (+ cell ranks kept in the not-yet-used leaf
+//   array) -> scan (one CTA per cloud) -> scatter (ATOMG with return, 16-byte staged stores) -> leaves -> inner boxes.
+constexpr int PRW_THREADS = 256, PRW_PER_THREAD = 8, PRW_SLICE = PRW_THREADS * PRW_PER_THREAD;
+
+struct PrWide {      // per-cloud state of the wide sort (global memory)
+    unsigned int lo[3], nhi[3];  // bounding box as order-preserving keys: min of ord(v), min of ~ord(v)
+    int bad;
+    int pad;
+};
+
+__device__ __forceinline__ unsigned pr_ord(float f);
+__device__ __forceinline__ float pr_unord(unsigned k);
+
+// grid (ceil(NC / 1024), 2 * B), block 1024
+__global__ void __launch_bounds__(1024)
+pr_wide_init_kernel(PrWide *__restrict__ st, unsigned int *__restrict__ ghist, int NC, unsigned int *__restrict__ rescue_count) {
+    pdl_wait();
+    const int cl = blockIdx.y;
+    const int c = blockIdx.x * 1024 + threadIdx.x;
+    if (c < NC) ghist[(size_t)cl * NC + c] = 0u;
+    if (c == 0) {
+        PrWide w;
+        w.lo[0] = w.lo[1] = w.lo[2] = w.nhi[0] = w.nhi[1] = w.nhi[2] = 0xffffffffu;
+        w.bad = 0;
+        w.pad = 0;
+        st[cl] = w;
+        rescue_count[cl] = 0u;
+    }
+}
+
+// grid (ceil(Pmax / PRW_SLICE), 2 * B), block 256
+__global__ void __launch_bounds__(PRW_THREADS)
+pr_wide_bbox_kernel(const float *__restrict__ x, const float *__restrict__ y, int P1, int P2, PrWide *__restrict__ st) {
+    pdl_wait();
+    const int cl = blockIdx.y, b = cl >> 1, cloud = cl & 1;
+    const int P = cloud == 0 ? P1 : P2;
+    const int e0 = blockIdx.x * PRW_SLICE * 3, e1 = min(P * 3, e0 + PRW_SLICE * 3);
+    if (e0 >= e1) return;
+    const float *__restrict__ src = cloud == 0 ? x + (size_t)b * P1 * 3 : y + (size_t)b * P2 * 3;
+    const float PINF = __int_as_float(0x7f800000), NINF = __int_as_float(0xff800000);
+    float lo[3] = {PINF, PINF, PINF}, hi[3] = {NINF, NINF, NINF};
+    bool bad = false;
+    // thread t reads elements e0 + t, + 256, ...: the coordinate index advances by 256 % 3 == 1 per step
+    for (int e = e0 + threadIdx.x; e < e1; e += 8 * PRW_THREADS) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = e + u * PRW_THREADS < e1 ? src[e + u * PRW_THREADS] : src[e];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int c = (e + u * PRW_THREADS < e1 ? e + u * PRW_THREADS : e) % 3;
+            bad |= !(fabsf(v[u]) <= 1.0e15f);
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+                if (k == c) {
+                    lo[k] = fminf(lo[k], v[u]);
+                    hi[k] = fmaxf(hi[k], v[u]);
+                }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const unsigned l = __reduce_min_sync(0xffffffffu, pr_ord(lo[k])), h = __reduce_min_sync(0xffffffffu, ~pr_ord(hi[k]));
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&st[cl].lo[k], l);
+            atomicMin(&st[cl].nhi[k], h);
+        }
+    }
+    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(&st[cl].bad, 1);
+}
+
+template <int BITS>
+__device__ __forceinline__ void pr_wide_grid(const PrWide &w, float (&org)[3], float (&scl)[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float l = pr_unord(w.lo[c]), h = pr_unord(~w.nhi[c]);
+        const float ext = h - l;
+        org[c] = w.bad ? 0.f : l;
+        scl[c] = (!w.bad && ext > 0.f) ? (float)(1 << BITS) / ext : 0.f;
+    }
+}
+template <int BITS>
+__device__ __forceinline__ unsigned pr_wide_cell(const float (&org)[3], const float (&scl)[3], float px, float py, float pz) {
+    constexpr int G = 1 << BITS;
+    const int cx = min(G - 1, max(0, __float2int_rz((px - org[0]) * scl[0])));
+    const int cy = min(G - 1, max(0, __float2int_rz((py - org[1]) * scl[1])));
+    const int cz = min(G - 1, max(0, __float2int_rz((pz - org[2]) * scl[2])));
+    return pr_cell_rank<BITS>(cx, cy, cz);
+}
+
+// grid (ceil(Pmax / PRW_SLICE), 2 * B), block 256.  SCATTER = false: histogram + cell ranks (kept in `codes`, the
+// leaf array the last phase overwrites); SCATTER = true: position from the scanned histogram, one staged 16-byte store.
+template <int BITS, bool SCATTER>
+__global__ void __launch_bounds__(PRW_THREADS)
+pr_wide_hist_scatter_kernel(const float *__restrict__ x, const float *__restrict__ y, int P1, int P2,
+                            const PrWide *__restrict__ st, unsigned int *__restrict__ ghist, float *soa_x, float *soa_y,
+                            float4 *__restrict__ stage_x, float4 *__restrict__ stage_y, int *__restrict__ bad_flags) {
+    pdl_wait();
+    constexpr int NC = 1 << (3 * BITS);
+    const int cl = blockIdx.y, b = cl >> 1, cloud = cl & 1;
+    const int P = cloud == 0 ? P1 : P2, Pp = soa_padded(P);
+    const int i0 = blockIdx.x * PRW_SLICE + threadIdx.x;
+    if (blockIdx.x * PRW_SLICE >= P) return;
+    const float *__restrict__ src = cloud == 0 ? x + (size_t)b * P1 * 3 : y + (size_t)b * P2 * 3;
+    unsigned int *codes = reinterpret_cast<unsigned int *>(cloud == 0 ? soa_x + (size_t)b * 4 * Pp : soa_y + (size_t)b * 4 * Pp);
+    float4 *__restrict__ stage = cloud == 0 ? stage_x + (size_t)b * Pp : stage_y + (size_t)b * Pp;
+    unsigned int *__restrict__ hist = ghist + (size_t)cl * NC;
+    const PrWide w = st[cl];
+    float org[3], scl[3];
+    pr_wide_grid<BITS>(w, org, scl);
+    if (!SCATTER && blockIdx.x == 0 && threadIdx.x == 0) bad_flags[cl] = w.bad;
+    float v[PRW_PER_THREAD][3];
+#pragma unroll
+    for (int u = 0; u < PRW_PER_THREAD; ++u) {
+        const int i = min(i0 + u * PRW_THREADS, P - 1);
+        v[u][0] = src[3 * i], v[u][1] = src[3 * i + 1], v[u][2] = src[3 * i + 2];
+    }
+    if (!SCATTER) {
+#pragma unroll
+        for (int u = 0; u < PRW_PER_THREAD; ++u) {
+            const int i = i0 + u * PRW_THREADS;
+            if (i < P) {
+                const unsigned code = pr_wide_cell<BITS>(org, scl, v[u][0], v[u][1], v[u][2]);
+                codes[i] = code;
+                atomicAdd(&hist[code], 1u);
+            }
+        }
+    } else {
+        unsigned int pos[PRW_PER_THREAD];
+#pragma unroll
+        for (int u = 0; u < PRW_PER_THREAD; ++u) {
+            const int i = i0 + u * PRW_THREADS;
+            pos[u] = i < P ? atomicAdd(&hist[codes[i]], 1u) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < PRW_PER_THREAD; ++u) {
+            const int i = i0 + u * PRW_THREADS;
+            if (i < P) stage[pos[u]] = make_float4(v[u][0], v[u][1], v[u][2], __int_as_float(i));
+        }
+    }
+}
+
+// grid 2 * B, block 1024: exclusive scan of a cloud's histogram in place
+template <int BITS>
+__global__ void __launch_bounds__(1024)
+pr_wide_scan_kernel(unsigned int *__restrict__ ghist) {
+    pdl_wait();
+    constexpr int NC = 1 << (3 * BITS), PER = NC / 1024;
+    __shared__ unsigned int swsum[32];
+    unsigned int *__restrict__ hist = ghist + (size_t)blockIdx.x * NC;
+    const int tid = threadIdx.x;
+    // the thread's PER consecutive bins as 128-bit loads / stores (all issued before the first use)
+    uint4 c4[PER / 4];
+    uint4 *__restrict__ h4 = reinterpret_cast<uint4 *>(hist + tid * PER);
+    unsigned int sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER / 4; ++k) c4[k] = h4[k];
+#pragma unroll
+    for (int k = 0; k < PER / 4; ++k) sum += c4[k].x + c4[k].y + c4[k].z + c4[k].w;
+    unsigned int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((tid & 31) >= o) inc += t;
+    }
+    if ((tid & 31) == 31) swsum[tid >> 5] = inc;
+    __syncthreads();
+    if (tid < 32) {
+        unsigned int wv = swsum[tid], winc = wv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, winc, o);
+            if (tid >= o) winc += t;
+        }
+        swsum[tid] = winc - wv;
+    }
+    __syncthreads();
+    unsigned int run = swsum[tid >> 5] + inc - sum;
+#pragma unroll
+    for (int k = 0; k < PER / 4; ++k) {
+        uint4 o;
+        o.x = run, run += c4[k].x;
+        o.y = run, run += c4[k].y;
+        o.z = run, run += c4[k].z;
+        o.w = run, run += c4[k].w;
+        h4[k] = o;
+    }
+}
+
+// grid (ceil(leaves / 16), 2 * B), block 256: a half-warp per leaf -- transpose the staged points into the leaf layout,
+// reduce the leaf box (the same pass as in chamfer_pruned_sort_kernel)
+__global__ void __launch_bounds__(256)
+pr_wide_leaf_kernel(int P1, int P2, const float4 *__restrict__ stage_x, const float4 *__restrict__ stage_y, float *soa_x,
+                    float *soa_y, PrBox *box_x, PrBox *box_y) {
+    pdl_wait();
+    const int cl = blockIdx.y, b = cl >> 1, cloud = cl & 1;
+    const int P = cloud == 0 ? P1 : P2, Pp = soa_padded(P);
+    const int c = blockIdx.x * 16 + (threadIdx.x >> 4), l16 = threadIdx.x & 15, lane = threadIdx.x & 31;
+    if (c >= Pp / PR_CHUNK) return;  // uniform per half-warp
+    const float4 *__restrict__ stage = cloud == 0 ? stage_x + (size_t)b * Pp : stage_y + (size_t)b * Pp;
+    float *o = (cloud == 0 ? soa_x + (size_t)b * 4 * Pp : soa_y + (size_t)b * 4 * Pp) + (size_t)c * 64;
+    PrBox *box0 = (cloud == 0 ? box_x : box_y) + (size_t)b * pr_boxes(P);
+    const float PINF = __int_as_float(0x7f800000), NINF = __int_as_float(0xff800000);
+    const bool live = c * PR_CHUNK + l16 < P;
+    float4 pt = make_float4(PINF, PINF, PINF, __int_as_float(0x7fffffff));
+    if (live) pt = stage[c * PR_CHUNK + l16];
+    o[l16] = pt.x;
+    o[16 + l16] = pt.y;
+    o[32 + l16] = pt.z;
+    o[48 + l16] = pt.w;
+    float l[3] = {pt.x, pt.y, pt.z}, h[3] = {live ? pt.x : NINF, live ? pt.y : NINF, live ? pt.z : NINF};
+    const unsigned hmask = 0xffffu << (lane & 16);
+#pragma unroll
+    for (int off = 8; off > 0; off >>= 1)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            l[k] = fminf(l[k], __shfl_xor_sync(hmask, l[k], off));
+            h[k] = fmaxf(h[k], __shfl_xor_sync(hmask, h[k], off));
+        }
+    if (l16 == 0 && c < pr_nb0(P)) {
+        box0[c].lo = make_float4(l[0], l[1], l[2], 0.f);
+        box0[c].hi = make_float4(h[0], h[1], h[2], 0.f);
+    }
+}
+
+// grid 2 * B, block 1024: the two inner levels (a warp per node, lane = child)
+__global__ void __launch_bounds__(1024)
+pr_wide_inner_kernel(int P1, int P2, PrBox *box_x, PrBox *box_y) {
+    pdl_wait();
+    const int cl = blockIdx.x, b = cl >> 1, cloud = cl & 1;
+    const int P = cloud == 0 ? P1 : P2;
+    PrBox *box0 = (cloud == 0 ? box_x : box_y) + (size_t)b * pr_boxes(P);
+    const int nb0 = pr_nb0(P), nb1 = pr_nb1(P), nb2 = pr_nb2(P);
+    PrBox *box1 = box0 + nb0, *box2 = box1 + nb1;
+    const float PINF = __int_as_float(0x7f800000), NINF = __int_as_float(0xff800000);
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int lvl = 0; lvl < 2; ++lvl) {
+        const PrBox *child = lvl == 0 ? box0 : box1;
+        PrBox *parent = lvl == 0 ? box1 : box2;
+        const int nchild = lvl == 0 ? nb0 : nb1, nparent = lvl == 0 ? nb1 : nb2;
+        for (int n = tid >> 5; n < nparent; n += 32) {
+            const int c = n * PR_FAN + lane;
+            float4 l = make_float4(PINF, PINF, PINF, 0.f), h = make_float4(NINF, NINF, NINF, 0.f);
+            if (c < nchild) {
+                l = child[c].lo;
+                h = child[c].hi;
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                l.x = fminf(l.x, __shfl_xor_sync(0xffffffffu, l.x, off));
+                l.y = fminf(l.y, __shfl_xor_sync(0xffffffffu, l.y, off));
+                l.z = fminf(l.z, __shfl_xor_sync(0xffffffffu, l.z, off));
+                h.x = fmaxf(h.x, __shfl_xor_sync(0xffffffffu, h.x, off));
+                h.y = fmaxf(h.y, __shfl_xor_sync(0xffffffffu, h.y, off));
+                h.z = fmaxf(h.z, __shfl_xor_sync(0xffffffffu, h.z, off));
+            }
+            if (lane == 0) {
+                parent[n].lo = l;
+                parent[n].hi = h;
+            }
+        }
+        __syncthreads();
+    }
+}
+
 __device__ __forceinline__ float pr_gap(float lo, float hi, float qlo, float qhi) {
     return fmaxf(fmaxf(__fsub_rn(lo, qhi), __fsub_rn(qlo, hi)), 0.f);
 }

@@ -653,10 +653,16 @@ def recon_step_measurement(torch, ptk_b200, dev, rank, world):
         step()
         launches = ptk_b200._lib.launch_count() - n0
         ms = _timeit_ranks(torch, step, 5, 2, dev, world)
-        return ms, launches, len(reducer.buckets), (net, adj_info, vision, touch, feats, gt, reducer)
+        try:  # the same step with the Chamfer loss on the pruned scan (bit-identical loss and gradients; 10k-point clouds
+            # are below the PTK_CHAMFER_AUTO threshold, so the numbers above use the brute-force scan)
+            ptk_b200.ops.set_chamfer_algo("pruned")
+            ms_pr = _timeit_ranks(torch, step, 5, 2, dev, world)
+        finally:
+            ptk_b200.ops.set_chamfer_algo("auto")
+        return ms, launches, len(reducer.buckets), (net, adj_info, vision, touch, feats, gt, reducer), ms_pr
 
     Bs = 16
-    ms, launches, nb, state = measure(Bs, Bs * world)
+    ms, launches, nb, state, ms_pr = measure(Bs, Bs * world)
     out = {"shape": "v_t_p GCN part: 16 objects per GPU, 3 x (448->300x18->3), N=1824/1949/1949, 3 x 10k-point "
                     "Chamfer loss, fwd+bwd+Adam; synthetic vertex features (CNN/MLP encoders out of scope)",
            "n_gpus": world, "ms": ms, "steps_per_s": 1e3 / ms, "objects_per_s": world * Bs * 1e3 / ms,
@@ -668,6 +674,10 @@ def recon_step_measurement(torch, ptk_b200, dev, rank, world):
     # pipe utilisation; aggregation, Chamfer and optimizer time count against it.
     out["fp32_peak_tflops"] = fp32_peak
     out["fp32_roofline_frac"] = out["gemm_tflops_per_gpu"] / fp32_peak
+    out["pruned_chamfer"] = {"ms": ms_pr, "steps_per_s": 1e3 / ms_pr, "objects_per_s": world * Bs * 1e3 / ms_pr,
+                             "fp32_roofline_frac": Bs * flop_per_object / (ms_pr * 1e-3) / 1e12 / fp32_peak,
+                             "note": "ops.set_chamfer_algo('pruned'): the 3 x 10k-point Chamfer losses on the pruned scan, "
+                                     "everything else unchanged; loss and gradients are bit-identical"}
     net, adj_info, vision, touch, feats, gt, reducer = state
     graphed = None
     try:  # the same step replayed from one CUDA graph per rank (launch gaps and Python overhead removed); for world > 1
@@ -729,7 +739,7 @@ def recon_step_measurement(torch, ptk_b200, dev, rank, world):
     if world > 1 and 16 % world == 0:
         try:
             Bl = 16 // world
-            ms_s, launches_s, _, st = measure(Bl, 16)
+            ms_s, launches_s, _, st, _ = measure(Bl, 16)
             del st
             out["strong_scaling_global_16"] = {
                 "objects_per_gpu": Bl, "ms": ms_s, "steps_per_s": 1e3 / ms_s, "objects_per_s": 16 * 1e3 / ms_s,
@@ -767,6 +777,11 @@ def policy_measurement(torch, ptk_b200, dev, rank, world):
     call()
     launches = ptk_b200._lib.launch_count() - n0
     ms = _timeit_ranks(torch, call, 3, 1, dev, world)
+    try:  # the same call with the 3 x 1600 Chamfer evaluations on the pruned scan (same scores, same arg-min)
+        ptk_b200.ops.set_chamfer_algo("pruned")
+        ms_pr = _timeit_ranks(torch, call, 3, 1, dev, world)
+    finally:
+        ptk_b200.ops.set_chamfer_algo("auto")
     # scoring alone (candidate meshes given), sharded the same way: what round 1 reported
     cand = torch.cat([vision[:1], touch[:1]], 1).repeat(E * A, 1, 1).reshape(E, A, -1, 3)
     cand = cand * (1.0 + 0.01 * torch.rand(E, A, 1, 1, device=dev, generator=gen))
@@ -776,6 +791,7 @@ def policy_measurement(torch, ptk_b200, dev, rank, world):
                      "(3 x 20 layers, no grad) + 3 x 10k-point samplings + Chamfer each + masked arg-min, one call",
             "n_gpus": world, "sharded": world > 1, "ms": ms, "candidates_per_s": E * A / (ms * 1e-3),
             "ptk_launches_per_call_per_rank": launches,
+            "pruned_chamfer": {"ms": ms_pr, "candidates_per_s": E * A / (ms_pr * 1e-3)},
             "scoring_only": {"ms": ms_score, "candidates_per_s": E * A / (ms_score * 1e-3),
                              "note": "sample + Chamfer + arg-min on given candidate meshes (no GCN)"}}
 

@@ -28,3 +28,7 @@ json.dump({"kernel": "chamfer_nn_filter_tma_kernel", "pairs": 256, "points": 100
           open("$P/chamfer_scan_traffic.json", "w"), indent=1)
 PY
 ls $P/${R}_*
+cp $G/${TAG}_pruned_check.txt $P/${R}_chamfer_pruned_check.txt
+cp $G/${TAG}_pruned_kernels.txt $P/${R}_chamfer_pruned_kernels.txt
+python tools/ncu_summary.py $G/${TAG}_pruned.ncu-rep > $P/${R}_ncu_chamfer_pruned.txt
+ls $P/${R}_*pruned*

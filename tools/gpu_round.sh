@@ -26,3 +26,8 @@ timeout 300 python tools/vertex_front_bench.py > $OUT/${TAG}_vertex_front.txt 2>
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:sgemm_fwd_tma -s 3 -c 1 -f -o $OUT/${TAG}_fwd \
     python tools/fwd_one.py > $OUT/${TAG}_ncu_fwd.log 2>&1
 timeout 300 python tests/torch_gpu_baselines.py > $OUT/${TAG}_torch_gpu_baselines.txt 2>&1
+timeout 400 python tools/pruned_check.py > $OUT/${TAG}_pruned_check.txt 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:chamfer_pruned -s 6 -c 2 -f -o $OUT/${TAG}_pruned \
+    python tools/pruned_profile.py pruned cube 256 10000 > $OUT/${TAG}_ncu_pruned.log 2>&1
+for a in "pruned cube 256 10000" "pruned sphere 256 10000" "pruned sphere 16 50000" "pruned sphere 1 100000"; do
+    timeout 200 python tools/pruned_profile.py $a 2>&1 | grep -v Warn | grep "us  \|pruned " >> $OUT/${TAG}_pruned_kernels.txt; done
