@@ -326,10 +326,20 @@ static int launch_nn_pruned(const float *x, const float *y, int64_t B, int64_t P
     PTK_CHECK_LAUNCH();
     u64 *keys_x = dir_only == 1 ? nullptr : w.keys_x;
     u64 *keys_y = dir_only == 0 ? nullptr : w.keys_y;
-    dim3 qgrid((unsigned)ceil_div(Pq, (int64_t)PR_QUERY_WARPS * 32), (unsigned)(B * ndir));
-    launch_pdl(chamfer_pruned_query_kernel, qgrid, dim3(PR_QUERY_WARPS * 32), 0, st, (const float *)w.soa_x,
-               (const float *)w.soa_y, (const PrBox *)w.box_x, (const PrBox *)w.box_y, (const int *)w.bad, iP1, iP2, keys_x,
-               keys_y, dir_only, w.rescue_x, w.rescue_y, w.count);
+    // One query per lane.  Two per lane (R = 2) halve the leaf loads per query -- the kernel is bound by the L1 return
+    // path -- but the wider query box costs as many extra scans and 72 registers: measured 891 vs 870 us at 256 x 10k,
+    // 422 vs 413 us at 16 x 50k.  Kept selectable for development (PTK_PR_R=2, read per call).
+    int R = 1;
+    if (getenv("PTK_PR_R")) R = atoi(getenv("PTK_PR_R")) == 2 ? 2 : 1;
+    dim3 qgrid((unsigned)ceil_div(Pq, (int64_t)PR_QUERY_WARPS * 32 * R), (unsigned)(B * ndir));
+    if (R == 2)
+        launch_pdl(chamfer_pruned_query_kernel<2>, qgrid, dim3(PR_QUERY_WARPS * 32), 0, st, (const float *)w.soa_x,
+                   (const float *)w.soa_y, (const PrBox *)w.box_x, (const PrBox *)w.box_y, (const int *)w.bad, iP1, iP2, keys_x,
+                   keys_y, dir_only, w.rescue_x, w.rescue_y, w.count);
+    else
+        launch_pdl(chamfer_pruned_query_kernel<1>, qgrid, dim3(PR_QUERY_WARPS * 32), 0, st, (const float *)w.soa_x,
+                   (const float *)w.soa_y, (const PrBox *)w.box_x, (const PrBox *)w.box_y, (const int *)w.bad, iP1, iP2, keys_x,
+                   keys_y, dir_only, w.rescue_x, w.rescue_y, w.count);
     PTK_CHECK_LAUNCH();
     const NNPlan p = plan_nn(B, Pq, Pt, ndir, CH_MINB);
     dim3 rgrid((unsigned)ceil_div(Pq, (int64_t)CH_THREADS * 8), (unsigned)p.n_split, (unsigned)(B * ndir));
