@@ -167,7 +167,9 @@ def _surface(B, P, g, noise=0.0):
 
 
 @pytest.mark.parametrize("kind,B,P1,P2", [("cube", 256, 10000, 10000), ("surface", 64, 10000, 10000), ("surface", 2, 100000, 100000),
-                                          ("cube", 1, 70000, 33000), ("clustered", 3, 6000, 9000), ("lattice", 2, 20000, 20000)])
+                                          ("cube", 1, 70000, 33000), ("clustered", 3, 6000, 9000), ("lattice", 2, 20000, 20000),
+                                          ("surface", 66, 33000, 33500),   # > 64 pairs of > 32k points: one CTA per cloud, 32^3 cells
+                                          ("cube", 70, 17000, 20000)])     # > 64 pairs, 16k..32k points: cell ranks recomputed
 def test_pruned_scan_equals_the_brute_force_scan_at_full_size(kind, B, P1, P2):
     """Sizes the CPU oracle cannot reach (BASELINE config 3 / 5 shapes): the pruned scan must return the brute-force
     scan's indices, distances and Chamfer values bit for bit, whatever the distribution -- volume, surface samples,
