@@ -682,8 +682,8 @@ chamfer_pruned_query_kernel(const float *__restrict__ soa_x, const float *__rest
         const int scan_cap = max(64, nb0 >> 3);
         bool bail = false;
 
-        int st1 = 0, st2 = 0, st3 = 0;
-        (void)st1, (void)st2, (void)st3;
+        int st1 = 0, st2 = 0, st3 = 0, stA = 0, stB = 0, stL = 0;
+        (void)st1, (void)st2, (void)st3, (void)stA, (void)stB, (void)stL;
         unsigned k2 = SENT;
         if (lane < nb2) k2 = __float_as_uint(pr_lb(b2[lane].lo, b2[lane].hi, wlx, wly, wlz, whx, why, whz));
         while (!bail) {
@@ -717,6 +717,14 @@ chamfer_pruned_query_kernel(const float *__restrict__ soa_x, const float *__rest
 #pragma unroll
                     for (int r = 0; r < R; ++r)
                         want |= pr_lb(blo, bhi, qx[r], qy[r], qz[r], qx[r], qy[r], qz[r]) <= best[r];
+#ifdef PTK_PR_STATS
+                    {
+                        const unsigned wb = __ballot_sync(FULL, want);
+                        if (wb & 0xffffu) ++stA;
+                        if (wb >> 16) ++stB;
+                        stL += __popc(wb);
+                    }
+#endif
                     if (!__any_sync(FULL, want)) continue;
                     if (++scans > scan_cap) {
                         bail = true;
@@ -788,6 +796,8 @@ chamfer_pruned_query_kernel(const float *__restrict__ soa_x, const float *__rest
         PR_STAT(3, st3);
         PR_STAT(4, scans);
         PR_STAT(5, bail ? 1 : 0);
+        PR_STAT(6, max(stA, stB));  // leaf scans if each 16-query half walked its own leaves
+        PR_STAT(7, stL);            // (lane, leaf) pairs that wanted the scan
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) {

@@ -20,7 +20,7 @@ for kind, B, P in (("cube", 64, 10000), ("cube", 256, 10000), ("sphere", 1, 1000
     lib.ptk_debug_pr_stats(buf, 1)
     w = max(buf[0], 1)
     print(f"{kind:7s} B={B:3d} P={P:6d}: warps {buf[0]}, per warp: L2 pops {buf[1] / w:.1f}, L1 pops {buf[2] / w:.1f}, leaf tests {buf[3] / w:.1f}, "
-          f"leaf scans {buf[4] / w:.1f}, bails {buf[5]}")
+          f"leaf scans {buf[4] / w:.1f}, bails {buf[5]}, max per half {buf[6] / w:.1f}, wanting lanes per scan {buf[7] / max(buf[4], 1):.1f}")
     n = 2 * B
     print("         sort kernel, cycles per CTA: " + ", ".join(f"{name} {buf[8 + i] / n:.0f}" for i, name in
                                                               enumerate(("bbox", "hist", "scan", "scatter", "boxes"))))
