@@ -97,22 +97,30 @@ def test_adj_init_on_gpu_and_deformation_like_step(golden, objects_dir):
         assert torch.isfinite(layer.weight.grad).all() and float(layer.weight.grad.abs().max()) > 0
 
 
-def test_cuda_graph_capture_of_forward():
-    """Every ABI call is capture-safe (no sync, no allocation inside the library)."""
-    x = torch.rand(4, 2000, 3, device="cuda")
-    y = torch.rand(4, 1500, 3, device="cuda")
-    ref, rix, _ = ptk_b200.ops.chamfer(x, y)
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    s = torch.cuda.Stream()
-    s.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(s):
-        ptk_b200.ops.chamfer(x, y)  # warm-up on the side stream
-        with torch.cuda.graph(g, stream=s):
-            cham, ix, iy = ptk_b200.ops.chamfer(x, y)
-    g.replay()
-    torch.cuda.synchronize()
-    assert torch.equal(cham, ref) and torch.equal(ix, rix)
+@pytest.mark.parametrize("algo,B,P1,P2", [("filter", 4, 2000, 1500), ("pruned", 4, 2000, 1500), ("pruned", 1, 20000, 17000),
+                                          ("pruned", 70, 33000, 3000)])
+def test_cuda_graph_capture_of_forward(algo, B, P1, P2):
+    """Every ABI call is capture-safe (no sync, no allocation inside the library) -- the brute-force scan and all three
+    sort variants of the pruned scan (one CTA per cloud with 16^3 / 32^3 cells, the multi-launch form for few large clouds)."""
+    x = torch.rand(B, P1, 3, device="cuda")
+    y = torch.rand(B, P2, 3, device="cuda")
+    try:
+        ptk_b200.ops.set_chamfer_algo(algo)
+        ref, rix, riy = ptk_b200.ops.chamfer(x, y)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            ptk_b200.ops.chamfer(x, y)  # warm-up on the side stream
+            with torch.cuda.graph(g, stream=s):
+                cham, ix, iy = ptk_b200.ops.chamfer(x, y)
+        for _ in range(2):
+            g.replay()
+        torch.cuda.synchronize()
+    finally:
+        ptk_b200.ops.set_chamfer_algo("auto")
+    assert torch.equal(cham, ref) and torch.equal(ix, rix) and torch.equal(iy, riy)
 
 
 def test_graphed_step_replays_the_eager_step(golden):
