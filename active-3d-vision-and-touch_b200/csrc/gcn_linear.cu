@@ -354,35 +354,28 @@ __device__ __forceinline__ float4 ft_lds_f4(uint32_t a) {
     return v;
 }
 
-__global__ void __launch_bounds__(FT_THREADS, 3)
-sgemm_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                     float *__restrict__ Cm, int M, int N, int K, int ld1, int nsplit, float *__restrict__ C2, int ld2,
-                     int relu2, uint32_t *__restrict__ a_bits) {
-    extern __shared__ __align__(128) uint8_t ft_smem_raw[];
-    const uint32_t smem = (ft_smem_u32(ft_smem_raw) + 127u) & ~127u;  // shared-space address of stage 0
-    __shared__ __align__(8) uint64_t bars[2 * FT_STAGES];
-
-    const uint32_t bar_full = ft_smem_u32(&bars[0]), bar_empty = ft_smem_u32(&bars[FT_STAGES]);
+// One tile of RT * 8 rows x 160 columns (RT rows per thread).  RT = 8 is the main tile; smaller RT are the TAIL tiles of a
+// launch: the time of this kernel is 7 us + 16 us x ceil(CTAs / 148) (tools/fwd_tail_probe.py: every SM works through its
+// CTAs at one per 16 us whatever the residency), so 976 CTAs cost as much as 1036 and 912 as much as 1036 too -- 6 % and
+// 14 % of the launch at the two shapes of a reconstruction step.  The rows beyond the last full round of 148 CTAs are
+// therefore cut into lower tiles, chosen so that they fill one round evenly (launch_fwd_tma).  A tail tile still
+// receives the 64-row TMA box (rows past its own belong to the next tile or are zero-filled) and uses its first RT * 8.
+template <int RT>
+__device__ __forceinline__ void ft_tile(const CUtensorMap &map_a, const CUtensorMap &map_w, float *__restrict__ Cm, int M, int N,
+                                        int K, int ld1, int nsplit, float *__restrict__ C2, int ld2, int relu2,
+                                        uint32_t *__restrict__ a_bits, int m0, uint32_t smem, uint32_t bar_full,
+                                        uint32_t bar_empty) {
+    constexpr int ROWS = RT * 8;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int m0 = blockIdx.y * FT_BM, n0 = blockIdx.x * FW_BN;
+    const int n0 = blockIdx.x * FW_BN;
     const int tx = tid % 16, ty = tid / 16;
+    // row of this thread's i-th accumulator row inside the tile (the full tile keeps its two-halves layout)
+    auto row_of = [&](int i) { return RT == 8 ? (i < 4 ? ty * 4 + i : FT_BM / 2 + ty * 4 + (i - 4)) : ty * RT + i; };
     // Packed ReLU mask of A for the backward: the column tiles of a row tile share the work -- CTA x emits the k-tiles
     // with kt % gridDim.x == x (16 bits each, straight to global memory), so no CTA of a wave is slower than the others.
     const bool emit_any = a_bits != nullptr;
     const int emit_mod = (int)gridDim.x, emit_me = (int)blockIdx.x;
     const int num_kt = (K + FW_BK - 1) / FW_BK;
-    pdl_launch_dependents();
-    if (tid == 0) {
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
-        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
-        for (int s = 0; s < FT_STAGES; ++s) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * s), "r"(1));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_empty + 8 * s), "r"(FT_THREADS / 32));
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    pdl_wait();  // A is the predecessor's output
 
     auto issue = [&](int kt) {  // thread 0 only
         const int s = kt % FT_STAGES;
@@ -398,9 +391,9 @@ sgemm_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (tid == 0)
         for (int kt = 0; kt < FT_STAGES && kt < num_kt; ++kt) issue(kt);
 
-    unsigned long long acc[8][5];
+    unsigned long long acc[RT][5];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < RT; ++i)
 #pragma unroll
         for (int j = 0; j < 5; ++j) acc[i][j] = 0ull;
 
@@ -423,17 +416,14 @@ sgemm_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
                           (v1.x > 0.f ? 16u : 0u) | (v1.y > 0.f ? 32u : 0u) | (v1.z > 0.f ? 64u : 0u) |
                           (v1.w > 0.f ? 128u : 0u)) << (h8 * 8);
             h |= __shfl_xor_sync(0xffffffffu, h, 1);
-            if (h8 == 0 && m0 + r < M)
+            if (h8 == 0 && r < ROWS && m0 + r < M)
                 reinterpret_cast<unsigned short *>(a_bits + (size_t)(m0 + r) * ((K + 31) >> 5))[kt] = (unsigned short)h;
         }
 #pragma unroll
         for (int kq = 0; kq < FW_BK / 2; ++kq) {
-            float2 a2v[8];  // 2 k-steps of this thread's 8 rows (float4 = 4 k-steps spilled at the 168-register cap)
+            float2 a2v[RT];  // 2 k-steps of this thread's rows (float4 = 4 k-steps spilled at the 168-register cap)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int r = i < 4 ? ty * 4 + i : FT_BM / 2 + ty * 4 + (i - 4);
-                a2v[i] = ft_lds_f2(As + 4u * (uint32_t)(r * FW_BK + kq * 2));
-            }
+            for (int i = 0; i < RT; ++i) a2v[i] = ft_lds_f2(As + 4u * (uint32_t)(row_of(i) * FW_BK + kq * 2));
 #pragma unroll
             for (int kk = 0; kk < 2; ++kk) {
                 const uint32_t brow = Bs + 4u * (uint32_t)((kq * 2 + kk) * FW_BN);
@@ -444,7 +434,7 @@ sgemm_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
 #pragma unroll
                 for (int j = 0; j < 5; ++j)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
+                    for (int i = 0; i < RT; ++i) {
                         const float a = kk == 0 ? a2v[i].x : a2v[i].y;
                         unsigned long long a2;
                         asm("mov.b64 %0, {%1, %1};" : "=l"(a2) : "f"(a));
@@ -458,12 +448,12 @@ sgemm_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     if (emit_any && (num_kt & 1) && num_kt % emit_mod == emit_me) {
         // K = 300: 19 k-tiles fill 9.5 words -- the upper half of the last word is zero (columns beyond K)
         const int wpr = (K + 31) >> 5;
-        for (int r = tid; r < FT_BM; r += FT_THREADS)
+        for (int r = tid; r < ROWS; r += FT_THREADS)
             if (m0 + r < M) reinterpret_cast<unsigned short *>(a_bits + (size_t)(m0 + r) * wpr)[num_kt] = 0;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int m = m0 + (i < 4 ? ty * 4 + i : FT_BM / 2 + ty * 4 + (i - 4));
+    for (int i = 0; i < RT; ++i) {
+        const int m = m0 + row_of(i);
         if (m >= M) continue;
         float *row1 = Cm + (size_t)m * ld1;
         float *row2 = C2 + (size_t)m * ld2;
@@ -493,10 +483,38 @@ sgemm_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
     }
 }
 
+// grid (column tiles, n_main + n_tail): row tiles [0, n_main) are 64 rows high, the n_tail tiles behind them RT_TAIL * 8.
+template <int RT_TAIL>
+__global__ void __launch_bounds__(FT_THREADS, 3)
+sgemm_fwd_tma_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                     float *__restrict__ Cm, int M, int N, int K, int ld1, int nsplit, float *__restrict__ C2, int ld2,
+                     int relu2, uint32_t *__restrict__ a_bits, int n_main) {
+    extern __shared__ __align__(128) uint8_t ft_smem_raw[];
+    const uint32_t smem = (ft_smem_u32(ft_smem_raw) + 127u) & ~127u;  // shared-space address of stage 0
+    __shared__ __align__(8) uint64_t bars[2 * FT_STAGES];
+    const uint32_t bar_full = ft_smem_u32(&bars[0]), bar_empty = ft_smem_u32(&bars[FT_STAGES]);
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        for (int s = 0; s < FT_STAGES; ++s) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_full + 8 * s), "r"(1));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_empty + 8 * s), "r"(FT_THREADS / 32));
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    pdl_wait();  // A is the predecessor's output
+    const int y = (int)blockIdx.y;
+    if (RT_TAIL == 8 || y < n_main)
+        ft_tile<8>(map_a, map_w, Cm, M, N, K, ld1, nsplit, C2, ld2, relu2, a_bits, y * FT_BM, smem, bar_full, bar_empty);
+    else
+        ft_tile<RT_TAIL>(map_a, map_w, Cm, M, N, K, ld1, nsplit, C2, ld2, relu2, a_bits,
+                         n_main * FT_BM + (y - n_main) * RT_TAIL * 8, smem, bar_full, bar_empty);
+}
+
 int make_tensor_map_2d(CUtensorMap *map, const float *base, int64_t rows, int64_t cols, int box_cols, int box_rows,
                        bool swizzle);  // gemm_tf32x3.cu
-
-static unsigned long long g_ft_optin = 0ull;  // cudaFuncAttributeMaxDynamicSharedMemorySize is per device
 
 static int launch_fwd_tma(const float *X, const float *W, float *H, int64_t M, int64_t K, int64_t N, cudaStream_t st,
                           int ld1 = 0, int nsplit = -1, float *C2 = nullptr, int ld2 = 0, int relu2 = 0,
@@ -515,13 +533,50 @@ static int launch_fwd_tma(const float *X, const float *W, float *H, int64_t M, i
     const size_t smem = (size_t)FT_STAGES * FT_STAGE_BYTES + 128;
     int dev = 0;
     PTK_CHECK_CUDA(cudaGetDevice(&dev));
-    if (dev >= 64 || !((g_ft_optin >> dev) & 1ull)) {
-        PTK_CHECK_CUDA(cudaFuncSetAttribute(sgemm_fwd_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        if (dev < 64) g_ft_optin |= 1ull << dev;
+    // Tail plan: rows behind the last FULL round of sm_count CTAs go into lower tiles (RT * 8 rows) that fill one more
+    // round as evenly as they can; cost model = rounds x tile height, small tiles charged 3 % per missing row group
+    // (fewer FFMA2 per shared-memory load).  PTK_FWD_TAIL=0 keeps 64-row tiles everywhere (development).
+    const int64_t cx = ceil_div(N, FW_BN), tiles64 = ceil_div(M, (int64_t)FT_BM), Q = sm_count();
+    int64_t n_main = tiles64;
+    int rt_tail = 8;
+    static const bool tail_on = !(getenv("PTK_FWD_TAIL") && atoi(getenv("PTK_FWD_TAIL")) == 0);
+    if (tail_on && (cx * tiles64) % Q != 0) {
+        n_main = (cx * tiles64 / Q) * Q / cx;  // row tiles of the full rounds
+        const int64_t rem = M - n_main * FT_BM;
+        double best = 1e30;
+        for (int rt = 8; rt >= 1; --rt) {
+            const double cost = (double)ceil_div(cx * ceil_div(rem, (int64_t)rt * 8), Q) * rt * (1.0 + 0.03 * (8 - rt));
+            if (cost < best - 1e-9) {
+                best = cost;
+                rt_tail = rt;
+            }
+        }
+        if (rt_tail == 8) n_main = tiles64;
     }
-    dim3 grid((unsigned)ceil_div(N, FW_BN), (unsigned)ceil_div(M, FT_BM));
-    launch_pdl(sgemm_fwd_tma_kernel, grid, dim3(FT_THREADS), smem, st, map_a, map_w, H, (int)M, (int)N, (int)K, ld1, nsplit,
-               C2, ld2, relu2, K <= 32 * FW_MAXW ? a_bits : nullptr);
+    const int64_t n_tail = rt_tail == 8 ? 0 : ceil_div(M - n_main * FT_BM, (int64_t)rt_tail * 8);
+    dim3 grid((unsigned)cx, (unsigned)(n_main + n_tail));
+    uint32_t *bits = K <= 32 * FW_MAXW ? a_bits : nullptr;
+#define PTK_FT_LAUNCH(RT)                                                                                                  \
+    do {                                                                                                                   \
+        static unsigned long long optin = 0ull; /* cudaFuncAttributeMaxDynamicSharedMemorySize is per device */             \
+        if (dev >= 64 || !((optin >> dev) & 1ull)) {                                                                       \
+            PTK_CHECK_CUDA(cudaFuncSetAttribute(sgemm_fwd_tma_kernel<RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+            if (dev < 64) optin |= 1ull << dev;                                                                            \
+        }                                                                                                                  \
+        launch_pdl(sgemm_fwd_tma_kernel<RT>, grid, dim3(FT_THREADS), smem, st, map_a, map_w, H, (int)M, (int)N, (int)K, ld1,   \
+                   nsplit, C2, ld2, relu2, bits, (int)n_main);                                                             \
+    } while (0)
+    switch (rt_tail) {
+        case 1: PTK_FT_LAUNCH(1); break;
+        case 2: PTK_FT_LAUNCH(2); break;
+        case 3: PTK_FT_LAUNCH(3); break;
+        case 4: PTK_FT_LAUNCH(4); break;
+        case 5: PTK_FT_LAUNCH(5); break;
+        case 6: PTK_FT_LAUNCH(6); break;
+        case 7: PTK_FT_LAUNCH(7); break;
+        default: PTK_FT_LAUNCH(8); break;
+    }
+#undef PTK_FT_LAUNCH
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }
