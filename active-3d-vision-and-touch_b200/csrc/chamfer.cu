@@ -123,27 +123,37 @@ static ChamferWs carve(void *workspace, int64_t B, int64_t P1, int64_t P2) {
 }
 
 // Unpack keys -> (dist, idx) and reduce the per-cloud means in a fixed order.
-// grid = B, block = 512.  cham may be NULL (plain knn).
+// grid = (B, nsplit), block = 512.  cham may be NULL (plain knn).  nsplit = fin_splits(P1, P2) is a function of the cloud
+// sizes only (1 up to 16k points): CTA (b, s) handles slice s of both clouds of pair b; with nsplit > 1 it writes its two
+// partial sums to `partial` and chamfer_finalize_sum_kernel adds them in slice order -- deterministic, and a pair's value
+// does not depend on the batch it is computed in.
+constexpr int FIN_SLICE = 16384;
+static int fin_splits(int64_t P1, int64_t P2) {
+    const int64_t n = ceil_div(P1 > P2 ? P1 : P2, (int64_t)FIN_SLICE);
+    return (int)(n < 1 ? 1 : (n > 64 ? 64 : n));
+}
+
 __global__ void __launch_bounds__(512)
 chamfer_finalize_kernel(const unsigned long long *__restrict__ keys_x,
                         const unsigned long long *__restrict__ keys_y, int P1, int P2,
                         float *__restrict__ dist_x, int32_t *__restrict__ idx_x,
                         float *__restrict__ dist_y, int32_t *__restrict__ idx_y,
-                        float *__restrict__ cham) {
+                        float *__restrict__ cham, float *__restrict__ partial) {
     pdl_wait();  // launched with programmatic stream serialization (ptk_common.cuh)
-    const int b = blockIdx.x;
+    const int b = blockIdx.x, sp = blockIdx.y, nsp = gridDim.y;
     const int tid = threadIdx.x;
     __shared__ float red[16];
-    float mean[2] = {0.f, 0.f};
+    float sum[2] = {0.f, 0.f};
     for (int dir = 0; dir < 2; ++dir) {
         const unsigned long long *keys = dir == 0 ? keys_x : keys_y;
         if (keys == nullptr) continue;
         const int P = dir == 0 ? P1 : P2;
+        const int len = (int)(((long long)P + nsp - 1) / nsp), i0 = sp * len, i1 = min(P, i0 + len);
         float *dist = dir == 0 ? dist_x : dist_y;
         int32_t *idx = dir == 0 ? idx_x : idx_y;
         float acc = 0.f;
 #pragma unroll 8
-        for (int i = tid; i < P; i += 512) {
+        for (int i = i0 + tid; i < i1; i += 512) {
             unsigned long long k = keys[(size_t)b * P + i];
             float d = __uint_as_float((unsigned int)(k >> 32));
             if (dist) dist[(size_t)b * P + i] = d;
@@ -157,10 +167,31 @@ chamfer_finalize_kernel(const unsigned long long *__restrict__ keys_x,
         if (tid < 32) {
             float v = tid < 16 ? red[tid] : 0.f;
             v = warp_sum(v);
-            if (tid == 0) mean[dir] = v / (float)P;
+            if (tid == 0) sum[dir] = v;
         }
     }
-    if (tid == 0 && cham) cham[b] = mean[0] + mean[1];
+    if (tid == 0 && cham) {
+        if (nsp == 1) {
+            cham[b] = sum[0] / (float)P1 + sum[1] / (float)P2;
+        } else {
+            partial[((size_t)b * nsp + sp) * 2 + 0] = sum[0];
+            partial[((size_t)b * nsp + sp) * 2 + 1] = sum[1];
+        }
+    }
+}
+
+// grid = ceil(B / 128), block = 128: cham[b] = (sum of the slices' partials, in slice order) / P
+__global__ void __launch_bounds__(128)
+chamfer_finalize_sum_kernel(const float *__restrict__ partial, int B, int nsp, int P1, int P2, float *__restrict__ cham) {
+    pdl_wait();
+    const int b = blockIdx.x * 128 + threadIdx.x;
+    if (b >= B) return;
+    float sx = 0.f, sy = 0.f;
+    for (int s = 0; s < nsp; ++s) {
+        sx += partial[((size_t)b * nsp + s) * 2 + 0];
+        sy += partial[((size_t)b * nsp + s) * 2 + 1];
+    }
+    cham[b] = sx / (float)P1 + sy / (float)P2;
 }
 
 // Backward, phase A (plain stores): the "own point" terms.
@@ -491,8 +522,8 @@ extern "C" int ptk_knn1_fwd(const float *p1, const float *p2, int64_t B, int64_t
     const ChamferWs w = carve(workspace, B, P1, P2);
     rc = launch_nn(p1, p2, B, P1, P2, w, 0, st);
     if (rc) return rc;
-    launch_pdl(chamfer_finalize_kernel, dim3((unsigned)B), dim3(512), 0, st, w.keys_x, nullptr, (int)P1, (int)P2, dist, idx,
-               nullptr, nullptr, nullptr);
+    launch_pdl(chamfer_finalize_kernel, dim3((unsigned)B, (unsigned)fin_splits(P1, P2)), dim3(512), 0, st, w.keys_x, nullptr,
+               (int)P1, (int)P2, dist, idx, nullptr, nullptr, nullptr, nullptr);
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }
@@ -514,8 +545,16 @@ extern "C" int ptk_chamfer_fwd(const float *x, const float *y, int64_t B, int64_
     const ChamferWs w = carve(workspace, B, P1, P2);
     rc = launch_nn(x, y, B, P1, P2, w, -1, st);
     if (rc) return rc;
-    launch_pdl(chamfer_finalize_kernel, dim3((unsigned)B), dim3(512), 0, st, w.keys_x, w.keys_y, (int)P1, (int)P2, dist_x,
-               idx_x, dist_y, idx_y, cham);
+    const int nsp = fin_splits(P1, P2);
+    // partial sums of the slices: the rescue flags are dead once the scan is over (flag_x holds B * P1 >= 2 * B * nsp words)
+    float *partial = reinterpret_cast<float *>(w.flag_x);
+    launch_pdl(chamfer_finalize_kernel, dim3((unsigned)B, (unsigned)nsp), dim3(512), 0, st, w.keys_x, w.keys_y, (int)P1, (int)P2,
+               dist_x, idx_x, dist_y, idx_y, cham, partial);
+    if (nsp > 1) {
+        PTK_CHECK_LAUNCH();
+        launch_pdl(chamfer_finalize_sum_kernel, dim3((unsigned)ceil_div(B, (int64_t)128)), dim3(128), 0, st, (const float *)partial,
+                   (int)B, nsp, (int)P1, (int)P2, cham);
+    }
     PTK_CHECK_LAUNCH();
     return PTK_OK;
 }
