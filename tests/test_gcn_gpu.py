@@ -467,3 +467,21 @@ def test_cluster_forms_of_the_tensor_core_gemm(mode):
     out = subprocess.run([sys.executable, os.path.join(root, "tools", "tc_2sm_check.py")], env=env, capture_output=True,
                          text=True, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+def test_forward_gemm_tail_tiles_are_bit_identical():
+    """The exact forward GEMM cuts the rows behind the last full round of CTAs into lower tiles ('tail
+    tiles'); PTK_FWD_TAIL=0 keeps 64-row tiles everywhere.  Same per-element arithmetic: the bit-level checksums of
+    tools/fwd_exact_check.py (reconstruction-step shapes, one-tile and ragged shapes) must not change.  The switch is read
+    once per process: two child interpreters."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for tail in ("1", "0"):
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "fwd_exact_check.py")],
+                             env=dict(os.environ, PTK_FWD_TAIL=tail), capture_output=True, text=True, timeout=240)
+        assert out.returncode == 0, out.stdout + out.stderr
+        outs.append([l for l in out.stdout.splitlines() if "checksum" in l])
+    assert len(outs[0]) >= 6 and outs[0] == outs[1]

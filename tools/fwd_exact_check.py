@@ -6,7 +6,8 @@ import torch
 import ptk_b200
 from ptk_b200 import _lib
 dev = torch.device("cuda")
-for (M, K, N) in [(31184, 300, 300), (31184, 448, 300), (1949, 300, 300), (100, 52, 64), (64, 16, 160), (63, 20, 68)]:
+for (M, K, N) in [(31184, 300, 300), (29184, 300, 300), (31184, 448, 300), (1949, 300, 300), (3898, 300, 300), (9500, 448, 300),
+                  (100, 52, 64), (64, 16, 160), (63, 20, 68)]:
     g = torch.Generator(device=dev).manual_seed(M + K + N)
     X = torch.randn(M, K, device=dev, generator=g)
     W = torch.randn(K, N, device=dev, generator=g) * 0.1
