@@ -32,3 +32,4 @@ cp $G/${TAG}_pruned_check.txt $P/${R}_chamfer_pruned_check.txt
 cp $G/${TAG}_pruned_kernels.txt $P/${R}_chamfer_pruned_kernels.txt
 python tools/ncu_summary.py $G/${TAG}_pruned.ncu-rep > $P/${R}_ncu_chamfer_pruned.txt
 ls $P/${R}_*pruned*
+cp $G/${TAG}_fwd_tail_probe.txt $P/${R}_fwd_tail_probe.txt

@@ -31,3 +31,4 @@ timeout 300 ncu --set full --clock-control none --import-source on -k regex:cham
     python tools/pruned_profile.py pruned cube 256 10000 > $OUT/${TAG}_ncu_pruned.log 2>&1
 for a in "pruned cube 256 10000" "pruned sphere 256 10000" "pruned sphere 16 50000" "pruned sphere 1 100000"; do
     timeout 200 python tools/pruned_profile.py $a 2>&1 | grep -v Warn | grep "us  \|pruned " >> $OUT/${TAG}_pruned_kernels.txt; done
+(echo "# tail tiles on (default)"; timeout 200 python tools/fwd_tail_probe.py; echo "# PTK_FWD_TAIL=0: 64-row tiles everywhere"; PTK_FWD_TAIL=0 timeout 200 python tools/fwd_tail_probe.py) > $OUT/${TAG}_fwd_tail_probe.txt 2>&1
