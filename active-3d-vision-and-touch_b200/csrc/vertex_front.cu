@@ -240,14 +240,26 @@ vertex_front_colsum1_kernel(const float *__restrict__ g, const float *__restrict
     const long long r0 = (long long)blockIdx.y * VC_ROWS, r1 = r0 + VC_ROWS < M ? r0 + VC_ROWS : M;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (n < N) {
-        for (long long m = r0; m < r1; ++m) {
-            int t = mask ? (int)__ldg(mask + m) : 0;
-            t = t < 0 ? 0 : (t > 3 ? 3 : t);
-            const float v = __ldg(g + (size_t)m * N + n);
-            acc[0] += t == 0 ? v : 0.f;
-            acc[1] += t == 1 ? v : 0.f;
-            acc[2] += t == 2 ? v : 0.f;
-            acc[3] += t == 3 ? v : 0.f;
+        // eight rows' loads in flight per thread (the kernel is latency-bound: 13 warps per SM); the additions stay in
+        // ascending row order per accumulator, so the sums do not depend on the batching
+        for (long long m0 = r0; m0 < r1; m0 += 8) {
+            float v[8];
+            int t[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const long long m = m0 + u < r1 ? m0 + u : r1 - 1;
+                t[u] = mask ? (int)__ldg(mask + m) : 0;
+                v[u] = __ldg(g + (size_t)m * N + n);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (m0 + u >= r1) break;
+                const int tt = t[u] < 0 ? 0 : (t[u] > 3 ? 3 : t[u]);
+                acc[0] += tt == 0 ? v[u] : 0.f;
+                acc[1] += tt == 1 ? v[u] : 0.f;
+                acc[2] += tt == 2 ? v[u] : 0.f;
+                acc[3] += tt == 3 ? v[u] : 0.f;
+            }
         }
 #pragma unroll
         for (int t = 0; t < 4; ++t) part[((size_t)blockIdx.y * 4 + t) * N + n] = acc[t];
