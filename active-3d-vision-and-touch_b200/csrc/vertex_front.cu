@@ -232,16 +232,22 @@ vertex_front_fwd_kernel(const VFParams p) {
 // stage 1: part[slab][t][n] = sum over the slab's rows with token t of g[m][n]; stage 2: fixed-order sum over slabs.
 constexpr int VC_ROWS = 256;
 
-__global__ void __launch_bounds__(128)
+// block (128 columns, 4 row groups): row group y sums rows r0 + 64 y .. + 63 of the slab (eight rows' loads in flight per
+// thread: the kernel is latency-bound), the groups are combined through shared memory in group order -- a fixed
+// summation order, independent of scheduling.
+constexpr int VC_GROUPS = 4;
+__global__ void __launch_bounds__(128 * VC_GROUPS)
 vertex_front_colsum1_kernel(const float *__restrict__ g, const float *__restrict__ mask, long long M, int N,
                             float *__restrict__ part) {
     pdl_wait();
-    const int n = blockIdx.x * 128 + threadIdx.x;
-    const long long r0 = (long long)blockIdx.y * VC_ROWS, r1 = r0 + VC_ROWS < M ? r0 + VC_ROWS : M;
+    __shared__ float sacc[VC_GROUPS][4][128];
+    const int n = blockIdx.x * 128 + threadIdx.x, grp = threadIdx.y;
+    const long long s0 = (long long)blockIdx.y * VC_ROWS;
+    const long long r0 = s0 + (long long)grp * (VC_ROWS / VC_GROUPS);
+    long long r1 = r0 + VC_ROWS / VC_GROUPS;
+    r1 = r1 < M ? r1 : M;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     if (n < N) {
-        // eight rows' loads in flight per thread (the kernel is latency-bound: 13 warps per SM); the additions stay in
-        // ascending row order per accumulator, so the sums do not depend on the batching
         for (long long m0 = r0; m0 < r1; m0 += 8) {
             float v[8];
             int t[8];
@@ -261,8 +267,18 @@ vertex_front_colsum1_kernel(const float *__restrict__ g, const float *__restrict
                 acc[3] += tt == 3 ? v[u] : 0.f;
             }
         }
+    }
 #pragma unroll
-        for (int t = 0; t < 4; ++t) part[((size_t)blockIdx.y * 4 + t) * N + n] = acc[t];
+    for (int t = 0; t < 4; ++t) sacc[grp][t][threadIdx.x] = acc[t];
+    __syncthreads();
+    if (grp == 0 && n < N) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float a = sacc[0][t][threadIdx.x];
+#pragma unroll
+            for (int y = 1; y < VC_GROUPS; ++y) a += sacc[y][t][threadIdx.x];
+            part[((size_t)blockIdx.y * 4 + t) * N + n] = a;
+        }
     }
 }
 
@@ -324,7 +340,7 @@ extern "C" int ptk_vertex_front_colsum(const float *g, const float *mask, int64_
     const int slabs = (int)ceil_div(M, VC_ROWS);
     PTK_REQUIRE(slabs <= 65535, PTK_ERR_SHAPE, "vertex_front_colsum: M too large");
     float *part = reinterpret_cast<float *>(workspace);
-    launch_pdl(vertex_front_colsum1_kernel, dim3((unsigned)ceil_div(width, 128), (unsigned)slabs), dim3(128), 0,
+    launch_pdl(vertex_front_colsum1_kernel, dim3((unsigned)ceil_div(width, 128), (unsigned)slabs), dim3(128, VC_GROUPS), 0,
                as_stream(stream), g, mask, (long long)M, (int)width, part);
     PTK_CHECK_LAUNCH();
     launch_pdl(vertex_front_colsum2_kernel, dim3((unsigned)ceil_div(4 * width, 256)), dim3(256), 0, as_stream(stream),
